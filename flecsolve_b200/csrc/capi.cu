@@ -1,0 +1,612 @@
+// extern "C" surface of libfsb.so: contexts, vectors, reductions, matrix wrappers.
+#include <immintrin.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <random>
+
+#include "fsb_internal.h"
+
+using namespace fsb;
+
+fsb_parcsr_s * fsb_parcsr_create_impl(fsb_ctx_s *, int64_t, const int64_t *, const int64_t *, const int64_t *,
+                                      const double *);
+fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s *, int, int64_t, int64_t, int64_t, double, double);
+void fsb_parcsr_destroy_impl(fsb_parcsr_s *);
+void fsb_parcsr_jacobi_relax_impl(fsb_parcsr_s *, double, int64_t, fsb_vec_s *, fsb_vec_s *, fsb_vec_s *);
+
+namespace fsb {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string & m) { g_last_error = m; }
+} // namespace fsb
+
+// run `body`, translate exceptions into status codes
+template<class F>
+static int guarded(F && body) noexcept {
+	try {
+		body();
+		return FSB_OK;
+	}
+	catch (const fsb::error & e) {
+		set_last_error(e.what());
+		return e.code;
+	}
+	catch (const std::exception & e) {
+		set_last_error(e.what());
+		return FSB_ERR_STATE;
+	}
+	catch (...) {
+		set_last_error("unknown error");
+		return FSB_ERR_STATE;
+	}
+}
+
+extern "C" {
+
+const char * fsb_last_error(void) { return g_last_error.c_str(); }
+int fsb_version(void) { return 100; }
+
+int fsb_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int fsb_nccl_unique_id(void * out128) {
+	return guarded([&] {
+		FSB_REQUIRE(out128, "null output");
+		static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+		ncclUniqueId id;
+		FSB_NCCL(ncclGetUniqueId(&id));
+		std::memcpy(out128, &id, sizeof(id));
+	});
+}
+
+int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(out, "null output");
+		FSB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+		FSB_REQUIRE(nranks == 1 || uid, "nccl_unique_id required when nranks > 1");
+		int ndev = 0;
+		if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+			cudaGetLastError();
+			throw fsb::error(FSB_ERR_NOGPU, "no CUDA device available: this library has no CPU fallback");
+		}
+		FSB_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+		FSB_CUDA(cudaSetDevice(device));
+		cudaDeviceProp prop{};
+		FSB_CUDA(cudaGetDeviceProperties(&prop, device));
+		if (prop.major != 10)
+			throw fsb::error(FSB_ERR_NOGPU, std::string("device is sm_") + std::to_string(prop.major) +
+			                                    std::to_string(prop.minor) + "; kernels are built for sm_100a only");
+		auto * c = new fsb_ctx_s;
+		c->device = device;
+		c->rank = rank;
+		c->nranks = nranks;
+		FSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		FSB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+		FSB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+		FSB_CUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+		FSB_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * MAXR * MAX_RED_BLOCKS));
+		FSB_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned)));
+		FSB_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned)));
+		FSB_CUDA(cudaMalloc(&c->d_results, sizeof(double) * FSB_RED_RING));
+		FSB_CUDA(cudaHostAlloc(&c->h_results, sizeof(double) * FSB_RED_RING, cudaHostAllocMapped));
+		FSB_CUDA(cudaHostAlloc(&c->h_flags, sizeof(int64_t) * FSB_RED_RING, cudaHostAllocMapped));
+		std::memset(c->h_results, 0, sizeof(double) * FSB_RED_RING);
+		std::memset(c->h_flags, 0, sizeof(int64_t) * FSB_RED_RING);
+		FSB_CUDA(cudaHostGetDevicePointer(&c->h_results_dev, c->h_results, 0));
+		FSB_CUDA(cudaHostGetDevicePointer(&c->h_flags_dev, c->h_flags, 0));
+		c->token_op.assign(FSB_RED_RING, 0);
+		c->token_event.resize(FSB_RED_RING, nullptr);
+		if (nranks > 1) {
+			ncclUniqueId id;
+			std::memcpy(&id, uid, sizeof(id));
+			FSB_NCCL(ncclCommInitRank(&c->nccl, nranks, id, rank));
+			FSB_NCCL(ncclCommSplit(c->nccl, 0, rank, &c->nccl_halo_comm, nullptr));
+			for (auto & e : c->token_event)
+				FSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		}
+		if (const char * t = std::getenv("FSB_TRACE"))
+			c->trace = std::atoi(t) != 0;
+		if (const char * t = std::getenv("FSB_FUSION"))
+			c->fusion = std::atoi(t) != 0;
+		*out = c;
+	});
+}
+
+int fsb_ctx_destroy(fsb_ctx_t c) {
+	return guarded([&] {
+		if (!c)
+			return;
+		flush(c);
+		cudaStreamSynchronize(c->stream);
+		cudaStreamSynchronize(c->comm_stream);
+		if (c->nccl_halo_comm)
+			ncclCommDestroy(c->nccl_halo_comm);
+		if (c->nccl)
+			ncclCommDestroy(c->nccl);
+		for (auto e : c->token_event)
+			if (e)
+				cudaEventDestroy(e);
+		cudaFree(c->d_partials);
+		cudaFree(c->d_counter);
+		cudaFree(c->d_results);
+		cudaFree(c->d_flush);
+		cudaFreeHost(c->h_results);
+		cudaFreeHost(c->h_flags);
+		cudaEventDestroy(c->ev_main);
+		cudaEventDestroy(c->ev_comm);
+		cudaStreamDestroy(c->stream);
+		cudaStreamDestroy(c->comm_stream);
+		delete c;
+	});
+}
+
+int fsb_ctx_flush(fsb_ctx_t c) {
+	return guarded([&] { flush(c); });
+}
+
+int fsb_ctx_sync(fsb_ctx_t c) {
+	return guarded([&] {
+		flush(c);
+		FSB_CUDA(cudaStreamSynchronize(c->stream));
+		FSB_CUDA(cudaStreamSynchronize(c->comm_stream));
+		c->stats[FSB_STAT_HOST_SYNCS]++;
+	});
+}
+
+void * fsb_ctx_stream(fsb_ctx_t c) { return c ? c->stream : nullptr; }
+int fsb_ctx_rank(fsb_ctx_t c) { return c->rank; }
+int fsb_ctx_nranks(fsb_ctx_t c) { return c->nranks; }
+
+int fsb_ctx_set_option(fsb_ctx_t c, int option, int64_t value) {
+	return guarded([&] {
+		flush(c);
+		switch (option) {
+		case FSB_OPT_FUSION:
+			c->fusion = value != 0;
+			break;
+		case FSB_OPT_SPMV_ROWS_PER_CTA:
+			c->spmv_rows_per_cta = static_cast<int>(value);
+			break;
+		case FSB_OPT_SPMV_THREADS:
+			c->spmv_threads = static_cast<int>(value);
+			break;
+		case FSB_OPT_TRACE:
+			c->trace = value != 0;
+			break;
+		default:
+			throw fsb::error(FSB_ERR_ARG, "unknown option");
+		}
+	});
+}
+
+int fsb_ctx_get_stat(fsb_ctx_t c, int stat, int64_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(stat >= 0 && stat < 8 && out, "bad stat");
+		*out = c->stats[stat];
+	});
+}
+
+int fsb_ctx_reset_stats(fsb_ctx_t c) {
+	return guarded([&] {
+		for (auto & s : c->stats)
+			s = 0;
+	});
+}
+
+int fsb_ctx_flush_l2(fsb_ctx_t c) {
+	return guarded([&] {
+		flush(c);
+		const size_t bytes = 256u << 20; // 2x the 126 MB L2
+		if (!c->d_flush) {
+			FSB_CUDA(cudaMalloc(&c->d_flush, bytes));
+			c->flush_bytes = bytes;
+		}
+		FSB_CUDA(cudaMemsetAsync(c->d_flush, 1, c->flush_bytes, c->stream));
+	});
+}
+
+// ------------------------------------------------------------------ vectors
+
+int fsb_vec_create(fsb_ctx_t c, int64_t n_owned, int64_t n_ghost, fsb_vec_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(c && out && n_owned >= 0 && n_ghost >= 0, "bad arguments");
+		auto * v = new fsb_vec_s;
+		v->ctx = c;
+		v->n_owned = n_owned;
+		v->n_ghost = n_ghost;
+		v->id = c->next_vec_id++;
+		const size_t n = static_cast<size_t>(n_owned + n_ghost);
+		FSB_CUDA(cudaMalloc(&v->d, std::max<size_t>(n, 2) * sizeof(double)));
+		FSB_CUDA(cudaMemsetAsync(v->d, 0, std::max<size_t>(n, 2) * sizeof(double), c->stream));
+		*out = v;
+	});
+}
+
+int fsb_vec_wrap(fsb_ctx_t c, double * p, int64_t n_owned, int64_t n_ghost, fsb_vec_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(c && out && p && n_owned >= 0 && n_ghost >= 0, "bad arguments");
+		FSB_REQUIRE(reinterpret_cast<uintptr_t>(p) % 16 == 0, "wrapped device pointer must be 16-byte aligned");
+		cudaPointerAttributes at{};
+		FSB_CUDA(cudaPointerGetAttributes(&at, p));
+		FSB_REQUIRE(at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged, "pointer is not device memory");
+		auto * v = new fsb_vec_s;
+		v->ctx = c;
+		v->d = p;
+		v->owns = false;
+		v->n_owned = n_owned;
+		v->n_ghost = n_ghost;
+		v->id = c->next_vec_id++;
+		*out = v;
+	});
+}
+
+int fsb_vec_destroy(fsb_vec_t v) {
+	return guarded([&] {
+		if (!v)
+			return;
+		flush(v->ctx);
+		if (v->owns) {
+			FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+			FSB_CUDA(cudaStreamSynchronize(v->ctx->comm_stream));
+			cudaFree(v->d);
+		}
+		delete v;
+	});
+}
+
+int64_t fsb_vec_local_size(fsb_vec_t v) { return v->n_owned; }
+int64_t fsb_vec_ghost_size(fsb_vec_t v) { return v->n_ghost; }
+double * fsb_vec_device_ptr(fsb_vec_t v) { return v->d; }
+
+int fsb_vec_upload(fsb_vec_t v, const double * host, int64_t n, int64_t offset) {
+	return guarded([&] {
+		FSB_REQUIRE(v && host && n >= 0 && offset >= 0 && offset + n <= v->n_owned, "upload range");
+		flush(v->ctx);
+		FSB_CUDA(cudaMemcpyAsync(v->d + offset, host, n * sizeof(double), cudaMemcpyHostToDevice, v->ctx->stream));
+		FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+		v->halo_valid = false;
+	});
+}
+
+int fsb_vec_download(fsb_vec_t v, double * host, int64_t n, int64_t offset) {
+	return guarded([&] {
+		FSB_REQUIRE(v && host && n >= 0 && offset >= 0 && offset + n <= v->n_owned + v->n_ghost, "download range");
+		flush(v->ctx);
+		FSB_CUDA(cudaMemcpyAsync(host, v->d + offset, n * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
+		FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+		v->ctx->stats[FSB_STAT_HOST_SYNCS]++;
+	});
+}
+
+static void check_same(fsb_vec_t a, fsb_vec_t b) {
+	FSB_REQUIRE(a && b, "null vector");
+	FSB_REQUIRE(a->ctx == b->ctx, "vectors belong to different contexts");
+	FSB_REQUIRE(a->n_owned == b->n_owned, "vector sizes differ");
+}
+
+static void push_ew(int op, fsb_vec_t z, fsb_vec_t x, fsb_vec_t y, double a, double b) {
+	FSB_REQUIRE(z, "null vector");
+	if (x)
+		check_same(z, x);
+	if (y)
+		check_same(z, y);
+	// commutative statements: keep an aliased destination in the y operand
+	if ((op == OP_LIN2 || op == OP_MUL) && z == x && z != y) {
+		std::swap(x, y);
+		std::swap(a, b);
+	}
+	pending p{};
+	p.kind = pending::EW;
+	p.op = op;
+	p.z = z;
+	p.x = x;
+	p.y = y;
+	p.a = a;
+	p.b = b;
+	z->halo_valid = false;
+	enqueue(z->ctx, p);
+}
+
+int fsb_vec_copy(fsb_vec_t z, fsb_vec_t x) {
+	return guarded([&] {
+		if (z == x)
+			return;
+		push_ew(OP_SCALE, z, x, nullptr, 1.0, 0);
+	});
+}
+int fsb_vec_set(fsb_vec_t z, double a) {
+	return guarded([&] { push_ew(OP_SET, z, nullptr, nullptr, a, 0); });
+}
+int fsb_vec_scale(fsb_vec_t z, double a, fsb_vec_t x) {
+	return guarded([&] { push_ew(OP_SCALE, z, x, nullptr, a, 0); });
+}
+int fsb_vec_add(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y) {
+	return guarded([&] { push_ew(OP_LIN2, z, x, y, 1.0, 1.0); });
+}
+int fsb_vec_sub(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y) {
+	return guarded([&] { push_ew(OP_LIN2, z, x, y, 1.0, -1.0); });
+}
+int fsb_vec_mul(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y) {
+	return guarded([&] { push_ew(OP_MUL, z, x, y, 0, 0); });
+}
+int fsb_vec_div(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y) {
+	return guarded([&] { push_ew(OP_DIV, z, x, y, 0, 0); });
+}
+int fsb_vec_recip(fsb_vec_t z, fsb_vec_t x) {
+	return guarded([&] { push_ew(OP_RECIP, z, x, nullptr, 0, 0); });
+}
+int fsb_vec_linear_sum(fsb_vec_t z, double a, fsb_vec_t x, double b, fsb_vec_t y) {
+	return guarded([&] { push_ew(OP_LIN2, z, x, y, a, b); });
+}
+int fsb_vec_axpy(fsb_vec_t z, double a, fsb_vec_t x, fsb_vec_t y) {
+	return guarded([&] { push_ew(OP_LIN2, z, x, y, a, 1.0); });
+}
+int fsb_vec_axpby(fsb_vec_t z, double a, double b, fsb_vec_t x) {
+	return guarded([&] { push_ew(OP_LIN2, z, x, z, a, b); });
+}
+int fsb_vec_abs(fsb_vec_t z, fsb_vec_t x) {
+	return guarded([&] { push_ew(OP_ABS, z, x, nullptr, 0, 0); });
+}
+int fsb_vec_add_scalar(fsb_vec_t z, fsb_vec_t x, double a) {
+	return guarded([&] { push_ew(OP_ADDS, z, x, nullptr, a, 0); });
+}
+
+int fsb_vec_set_random(fsb_vec_t z, unsigned seed) {
+	return guarded([&] {
+		FSB_REQUIRE(z, "null vector");
+		std::mt19937 gen(seed);
+		std::uniform_real_distribution<double> dis(0., 1.);
+		std::vector<double> h(static_cast<size_t>(z->n_owned));
+		for (auto & v : h)
+			v = dis(gen);
+		flush(z->ctx);
+		if (!h.empty())
+			FSB_CUDA(cudaMemcpyAsync(z->d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, z->ctx->stream));
+		FSB_CUDA(cudaStreamSynchronize(z->ctx->stream));
+		z->halo_valid = false;
+	});
+}
+
+int fsb_vec_dump(fsb_vec_t x, const char * prefix) {
+	return guarded([&] {
+		FSB_REQUIRE(x && prefix, "bad arguments");
+		std::vector<double> h(static_cast<size_t>(x->n_owned));
+		flush(x->ctx);
+		if (!h.empty())
+			FSB_CUDA(cudaMemcpyAsync(h.data(), x->d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, x->ctx->stream));
+		FSB_CUDA(cudaStreamSynchronize(x->ctx->stream));
+		std::ofstream f(std::string(prefix) + "-" + std::to_string(x->ctx->rank));
+		for (double v : h)
+			f << v << '\n';
+	});
+}
+
+// ------------------------------------------------------------------ reductions
+
+static void push_red(int op, fsb_vec_t x, fsb_vec_t y, double a, fsb_token_t * tok) {
+	FSB_REQUIRE(x && tok, "bad arguments");
+	if (y)
+		check_same(x, y);
+	fsb_ctx_s * c = x->ctx;
+	pending p{};
+	p.kind = pending::RED;
+	p.op = op;
+	p.x = x;
+	p.y = y;
+	p.a = a;
+	p.token = new_token(c, fold_of(op));
+	*tok = p.token;
+	enqueue(c, p);
+}
+
+int fsb_vec_dot(fsb_vec_t x, fsb_vec_t y, fsb_token_t * tok) {
+	return guarded([&] { push_red(RD_DOT, x, y, 0, tok); });
+}
+int fsb_vec_sumsq(fsb_vec_t x, fsb_token_t * tok) {
+	return guarded([&] { push_red(RD_DOT, x, x, 0, tok); });
+}
+int fsb_vec_asum(fsb_vec_t x, fsb_token_t * tok) {
+	return guarded([&] { push_red(RD_ASUM, x, nullptr, 0, tok); });
+}
+int fsb_vec_powsum(fsb_vec_t x, int p, fsb_token_t * tok) {
+	return guarded([&] { push_red(RD_POWSUM, x, nullptr, static_cast<double>(p), tok); });
+}
+int fsb_vec_amax(fsb_vec_t x, fsb_token_t * tok) {
+	return guarded([&] { push_red(RD_AMAX, x, nullptr, 0, tok); });
+}
+int fsb_vec_min(fsb_vec_t x, fsb_token_t * tok) {
+	return guarded([&] { push_red(RD_MIN, x, nullptr, 0, tok); });
+}
+int fsb_vec_max(fsb_vec_t x, fsb_token_t * tok) {
+	return guarded([&] { push_red(RD_MAX, x, nullptr, 0, tok); });
+}
+
+int fsb_vec_global_size(fsb_vec_t x, int64_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(x && out, "bad arguments");
+		fsb_ctx_s * c = x->ctx;
+		if (c->nranks == 1) {
+			*out = x->n_owned;
+			return;
+		}
+		flush(c);
+		long long * d = nullptr;
+		FSB_CUDA(cudaMalloc(&d, sizeof(long long)));
+		long long v = x->n_owned;
+		FSB_CUDA(cudaMemcpyAsync(d, &v, sizeof(v), cudaMemcpyHostToDevice, c->stream));
+		FSB_NCCL(ncclAllReduce(d, d, 1, ncclInt64, ncclSum, c->nccl, c->stream));
+		FSB_CUDA(cudaMemcpyAsync(&v, d, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+		FSB_CUDA(cudaStreamSynchronize(c->stream));
+		cudaFree(d);
+		*out = v;
+	});
+}
+
+static void wait_token(fsb_ctx_t c, fsb_token_t tok) {
+	FSB_REQUIRE(c, "null context");
+	FSB_REQUIRE(tok > 0 && tok < c->next_token, "unknown reduction token");
+	FSB_REQUIRE(tok + FSB_RED_RING > c->next_token - 1, "reduction token expired");
+	flush(c);
+	const int slot = static_cast<int>(tok % FSB_RED_RING);
+	if (c->nranks > 1) {
+		FSB_CUDA(cudaEventSynchronize(c->token_event[slot]));
+	}
+	else {
+		// the producing kernel stores the value, then the token, into mapped pinned memory
+		volatile int64_t * flag = c->h_flags + slot;
+		unsigned spins = 0;
+		while (*flag != tok) {
+			_mm_pause();
+			if ((++spins & 0xfffffu) == 0) { // every ~1M spins make sure the stream is still alive
+				cudaError_t q = cudaStreamQuery(c->stream);
+				if (q != cudaSuccess && q != cudaErrorNotReady)
+					FSB_CUDA(q);
+				if (q == cudaSuccess && *flag != tok)
+					throw fsb::error(FSB_ERR_STATE, "reduction result never arrived");
+			}
+		}
+	}
+	c->stats[FSB_STAT_HOST_SYNCS]++;
+}
+
+int fsb_red_wait(fsb_ctx_t c, fsb_token_t tok) {
+	return guarded([&] { wait_token(c, tok); });
+}
+
+int fsb_red_get(fsb_ctx_t c, fsb_token_t tok, double * out) {
+	return guarded([&] {
+		FSB_REQUIRE(out, "null output");
+		wait_token(c, tok);
+		*out = *(volatile double *)(c->h_results + tok % FSB_RED_RING);
+	});
+}
+
+// ------------------------------------------------------------------ matrix
+
+int fsb_parcsr_create(fsb_ctx_t c, int64_t n_global, const int64_t * row_part, const int64_t * rowptr,
+                      const int64_t * col, const double * val, fsb_parcsr_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(c && row_part && rowptr && out, "bad arguments");
+		*out = fsb_parcsr_create_impl(c, n_global, row_part, rowptr, col, val);
+	});
+}
+
+int fsb_parcsr_create_stencil(fsb_ctx_t c, int kind, int64_t nx, int64_t ny, int64_t nz, double diag_shift,
+                              double scale, fsb_parcsr_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(c && out, "bad arguments");
+		*out = fsb_parcsr_create_stencil_impl(c, kind, nx, ny, nz, diag_shift, scale);
+	});
+}
+
+int fsb_parcsr_destroy(fsb_parcsr_t A) {
+	return guarded([&] {
+		if (A)
+			fsb_parcsr_destroy_impl(A);
+	});
+}
+
+int64_t fsb_parcsr_local_rows(fsb_parcsr_t A) { return A->n_local; }
+int64_t fsb_parcsr_global_rows(fsb_parcsr_t A) { return A->n_global; }
+int64_t fsb_parcsr_num_ghosts(fsb_parcsr_t A) { return A->n_ghost; }
+int64_t fsb_parcsr_row_begin(fsb_parcsr_t A) { return A->row_begin; }
+int64_t fsb_parcsr_local_nnz(fsb_parcsr_t A, int which) { return which == 0 ? A->diag.nnz : A->offd.nnz; }
+
+int fsb_parcsr_download(fsb_parcsr_t A, int which, int64_t * rowptr, int32_t * col, double * val) {
+	return guarded([&] {
+		FSB_REQUIRE(A && (which == 0 || which == 1), "bad arguments");
+		fsb_ctx_s * c = A->ctx;
+		flush(c);
+		const csr_block & B = which == 0 ? A->diag : A->offd;
+		if (rowptr) {
+			// expand to one offset per local row (the offd block is stored over a row subset)
+			std::vector<int64_t> rp(static_cast<size_t>(B.n_rows) + 1, 0);
+			if (B.n_rows > 0) {
+				if (B.wide) {
+					FSB_CUDA(cudaMemcpy(rp.data(), B.rowptr, rp.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+				}
+				else {
+					std::vector<int32_t> t(rp.size());
+					FSB_CUDA(cudaMemcpy(t.data(), B.rowptr, t.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+					std::copy(t.begin(), t.end(), rp.begin());
+				}
+			}
+			if (B.row_ids || which == 1) {
+				std::vector<int32_t> ids(static_cast<size_t>(B.n_rows));
+				if (B.n_rows > 0)
+					FSB_CUDA(cudaMemcpy(ids.data(), B.row_ids, ids.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+				std::vector<int64_t> cnt(static_cast<size_t>(A->n_local), 0);
+				for (int64_t k = 0; k < B.n_rows; ++k)
+					cnt[ids[k]] = rp[k + 1] - rp[k];
+				rowptr[0] = 0;
+				for (int64_t r = 0; r < A->n_local; ++r)
+					rowptr[r + 1] = rowptr[r] + cnt[r];
+			}
+			else {
+				std::copy(rp.begin(), rp.end(), rowptr);
+			}
+		}
+		if (col && B.nnz > 0)
+			FSB_CUDA(cudaMemcpy(col, B.col, B.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+		if (val && B.nnz > 0)
+			FSB_CUDA(cudaMemcpy(val, B.val, B.nnz * sizeof(double), cudaMemcpyDeviceToHost));
+	});
+}
+
+int fsb_parcsr_download_colmap(fsb_parcsr_t A, int64_t * colmap) {
+	return guarded([&] {
+		FSB_REQUIRE(A && colmap, "bad arguments");
+		std::copy(A->colmap.begin(), A->colmap.end(), colmap);
+	});
+}
+
+int fsb_parcsr_spmv(fsb_parcsr_t A, fsb_vec_t x, fsb_vec_t y) {
+	return guarded([&] {
+		FSB_REQUIRE(A && x && y, "null argument");
+		FSB_REQUIRE(x != y && x->d != y->d, "spmv: x and y must be different vectors");
+		FSB_REQUIRE(x->ctx == A->ctx && y->ctx == A->ctx, "spmv: context mismatch");
+		FSB_REQUIRE(x->n_owned == A->n_local && y->n_owned == A->n_local, "spmv: vector length != local rows");
+		FSB_REQUIRE(x->n_ghost >= A->n_ghost, "spmv: x has too few ghost entries for this matrix");
+		pending p{};
+		p.kind = pending::SPMV;
+		p.op = -1;
+		p.A = A;
+		p.x = x;
+		p.y = y;
+		p.z = y;
+		enqueue(A->ctx, p);
+	});
+}
+
+int fsb_parcsr_extract_dinv(fsb_parcsr_t A, fsb_vec_t d) {
+	return guarded([&] {
+		FSB_REQUIRE(A && d && d->n_owned == A->n_local, "extract_dinv: bad arguments");
+		flush(A->ctx);
+		extract_dinv(A, d->d);
+		d->halo_valid = false;
+	});
+}
+
+int fsb_parcsr_jacobi_relax(fsb_parcsr_t A, double omega, int64_t nrelax, fsb_vec_t b, fsb_vec_t x, fsb_vec_t tmp) {
+	return guarded([&] {
+		FSB_REQUIRE(A && b && x && tmp, "null argument");
+		fsb_parcsr_jacobi_relax_impl(A, omega, nrelax, b, x, tmp);
+	});
+}
+
+int fsb_parcsr_halo_exchange(fsb_parcsr_t A, fsb_vec_t x) {
+	return guarded([&] {
+		FSB_REQUIRE(A && x, "null argument");
+		halo_exchange(A, x);
+	});
+}
+
+} // extern "C"

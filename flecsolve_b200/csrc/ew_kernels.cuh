@@ -1,0 +1,214 @@
+// Fused element-wise / reduction kernels, one instantiation per registered program.
+//
+// HBM-bound streaming kernels (<= 0.125 flop/B): 128-bit loads and stores, a grid-stride loop
+// with EW_CTAS_PER_SM x 148 CTAs so every SM keeps >= 2048 threads of loads in flight,
+// warp-shuffle + shared-memory block reduction, and a "last CTA" epilogue that folds the
+// per-CTA partials in a fixed order (bitwise reproducible) and publishes the result to
+// pinned host memory so the host can poll instead of synchronising the stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <utility>
+
+#include "program.h"
+
+namespace fsb {
+
+constexpr int EW_BLOCK = 256; // threads per CTA of every element-wise kernel
+
+struct red_out {
+	double * d_value; // device result slot
+	double * h_value; // mapped host slot or nullptr (multi-rank: NCCL finishes the job)
+	long long * h_flag;
+	long long token;
+};
+
+struct ew_args {
+	double * v[MAXV];
+	double s[MAXSC];
+	long long n;
+	double * partials; // [MAXR][MAX_RED_BLOCKS]
+	unsigned * counter;
+	int partial_stride;
+	red_out r[MAXR];
+};
+
+template<int FOLD>
+__device__ __forceinline__ double fold(double a, double b) {
+	if constexpr (FOLD == 0)
+		return a + b;
+	else if constexpr (FOLD == 1)
+		return fmax(a, b);
+	else
+		return fmin(a, b);
+}
+
+template<int FOLD>
+__device__ __forceinline__ double fold_identity() {
+	if constexpr (FOLD == 0)
+		return 0.0;
+	else if constexpr (FOLD == 1)
+		return -__longlong_as_double(0x7ff0000000000000LL); // -inf
+	else
+		return __longlong_as_double(0x7ff0000000000000LL); // +inf
+}
+
+template<int FOLD>
+__device__ __forceinline__ double warp_fold(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v = fold<FOLD>(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+// Fold one value per thread over the CTA; result valid in thread 0. `scratch` holds >= 32 doubles.
+template<int FOLD>
+__device__ __forceinline__ double block_fold(double v, double * scratch) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	v = warp_fold<FOLD>(v);
+	__syncthreads(); // scratch may still be read from a previous call
+	if (lane == 0)
+		scratch[warp] = v;
+	__syncthreads();
+	const int nwarps = (blockDim.x + 31) >> 5;
+	if (warp == 0) {
+		v = lane < nwarps ? scratch[lane] : fold_identity<FOLD>();
+		v = warp_fold<FOLD>(v);
+	}
+	return v;
+}
+
+template<class PT, int I>
+__device__ __forceinline__ void exec_stmt(double (&v)[MAXV], double (&acc)[MAXR], const ew_args & a) {
+	constexpr stmt S = PT::value.st[I];
+	// products and sums are rounded separately on purpose (see fsb.h): the reference's
+	// task bodies (vectors/operations/topo_tasks.hh) compiled for baseline x86-64 do the same.
+	if constexpr (S.op == OP_SET)
+		v[S.z] = a.s[S.a];
+	else if constexpr (S.op == OP_SCALE)
+		v[S.z] = __dmul_rn(v[S.x], a.s[S.a]);
+	else if constexpr (S.op == OP_LIN2)
+		v[S.z] = __dadd_rn(__dmul_rn(a.s[S.a], v[S.x]), __dmul_rn(a.s[S.b], v[S.y]));
+	else if constexpr (S.op == OP_MUL)
+		v[S.z] = __dmul_rn(v[S.x], v[S.y]);
+	else if constexpr (S.op == OP_DIV)
+		v[S.z] = __ddiv_rn(v[S.x], v[S.y]);
+	else if constexpr (S.op == OP_RECIP)
+		v[S.z] = __ddiv_rn(1.0, v[S.x]);
+	else if constexpr (S.op == OP_ABS)
+		v[S.z] = fabs(v[S.x]);
+	else if constexpr (S.op == OP_ADDS)
+		v[S.z] = __dadd_rn(v[S.x], a.s[S.a]);
+	else if constexpr (S.op == RD_DOT)
+		acc[S.z] = fma(v[S.x], v[S.y], acc[S.z]);
+	else if constexpr (S.op == RD_ASUM)
+		acc[S.z] += fabs(v[S.x]);
+	else if constexpr (S.op == RD_AMAX)
+		acc[S.z] = fmax(acc[S.z], fabs(v[S.x]));
+	else if constexpr (S.op == RD_MIN)
+		acc[S.z] = fmin(acc[S.z], v[S.x]);
+	else if constexpr (S.op == RD_MAX)
+		acc[S.z] = fmax(acc[S.z], v[S.x]);
+	else if constexpr (S.op == RD_POWSUM)
+		acc[S.z] += pow(v[S.x], a.s[S.a]);
+}
+
+template<class PT>
+__device__ __forceinline__ void exec_all(double (&v)[MAXV], double (&acc)[MAXR], const ew_args & a) {
+	[&]<size_t... I>(std::index_sequence<I...>) {
+		(exec_stmt<PT, static_cast<int>(I)>(v, acc, a), ...);
+	}(std::make_index_sequence<PT::value.n>{});
+}
+
+// fold kind of reduction output R of program P
+template<class PT, int R>
+constexpr int red_fold() {
+	for (int i = 0; i < PT::value.n; ++i)
+		if (is_reduction(PT::value.st[i].op) && PT::value.st[i].z == R)
+			return fold_of(PT::value.st[i].op);
+	return 0;
+}
+
+template<class PT>
+__global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_constant__ ew_args a) {
+	constexpr program P = PT::value;
+	double acc[MAXR];
+	[&]<size_t... R>(std::index_sequence<R...>) {
+		((acc[R] = fold_identity<red_fold<PT, static_cast<int>(R)>()>()), ...);
+	}(std::make_index_sequence<(P.nr > 0 ? P.nr : 0)>{});
+
+	const long long n2 = a.n >> 1; // number of double2 packets
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2; i += stride) {
+		double lo[MAXV], hi[MAXV];
+#pragma unroll
+		for (int k = 0; k < P.nv; ++k) {
+			if (P.load_mask & (1u << k)) {
+				const double2 t = reinterpret_cast<const double2 *>(a.v[k])[i];
+				lo[k] = t.x;
+				hi[k] = t.y;
+			}
+		}
+		exec_all<PT>(lo, acc, a);
+		exec_all<PT>(hi, acc, a);
+#pragma unroll
+		for (int k = 0; k < P.nv; ++k) {
+			if (P.store_mask & (1u << k))
+				reinterpret_cast<double2 *>(a.v[k])[i] = make_double2(lo[k], hi[k]);
+		}
+	}
+	if ((a.n & 1) && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { // odd tail element
+		const long long i = a.n - 1;
+		double t[MAXV];
+#pragma unroll
+		for (int k = 0; k < P.nv; ++k)
+			if (P.load_mask & (1u << k))
+				t[k] = a.v[k][i];
+		exec_all<PT>(t, acc, a);
+#pragma unroll
+		for (int k = 0; k < P.nv; ++k)
+			if (P.store_mask & (1u << k))
+				a.v[k][i] = t[k];
+	}
+
+	if constexpr (P.nr > 0) {
+		__shared__ double scratch[32];
+		__shared__ bool is_last;
+		[&]<size_t... R>(std::index_sequence<R...>) {
+			((acc[R] = block_fold<red_fold<PT, static_cast<int>(R)>()>(acc[R], scratch)), ...);
+		}(std::make_index_sequence<P.nr>{});
+		if (threadIdx.x == 0) {
+#pragma unroll
+			for (int r = 0; r < P.nr; ++r)
+				a.partials[r * a.partial_stride + blockIdx.x] = acc[r];
+			__threadfence();
+			const unsigned ticket = atomicAdd(a.counter, 1u);
+			is_last = (ticket == gridDim.x - 1);
+		}
+		__syncthreads();
+		if (is_last) {
+			__threadfence();
+			[&]<size_t... R>(std::index_sequence<R...>) {
+				(([&] {
+					 constexpr int F = red_fold<PT, static_cast<int>(R)>();
+					 double t = fold_identity<F>();
+					 for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += blockDim.x)
+						 t = fold<F>(t, __ldcg(&a.partials[R * a.partial_stride + b]));
+					 t = block_fold<F>(t, scratch);
+					 if (threadIdx.x == 0) {
+						 *a.r[R].d_value = t;
+						 if (a.r[R].h_value) {
+							 *reinterpret_cast<volatile double *>(a.r[R].h_value) = t;
+							 __threadfence_system();
+							 *reinterpret_cast<volatile long long *>(a.r[R].h_flag) = a.r[R].token;
+						 }
+					 }
+				 }()),
+				 ...);
+			}(std::make_index_sequence<P.nr>{});
+			if (threadIdx.x == 0)
+				*a.counter = 0u;
+		}
+	}
+}
+
+} // namespace fsb

@@ -1,0 +1,179 @@
+// Internal declarations shared by the translation units of libfsb.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fsb.h"
+#include "program.h"
+
+namespace fsb {
+
+struct error : std::runtime_error {
+	int code;
+	error(int c, const std::string & m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string & m);
+
+#define FSB_CUDA(call)                                                                      \
+	do {                                                                                    \
+		cudaError_t e_ = (call);                                                            \
+		if (e_ != cudaSuccess)                                                              \
+			throw ::fsb::error(FSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + \
+			                                     " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+	} while (0)
+
+#define FSB_NCCL(call)                                                                      \
+	do {                                                                                    \
+		ncclResult_t r_ = (call);                                                           \
+		if (r_ != ncclSuccess)                                                              \
+			throw ::fsb::error(FSB_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_) + \
+			                                     " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+	} while (0)
+
+#define FSB_REQUIRE(cond, msg)                                    \
+	do {                                                          \
+		if (!(cond))                                              \
+			throw ::fsb::error(FSB_ERR_ARG, std::string(msg));   \
+	} while (0)
+
+constexpr int SM_COUNT = 148; // B200
+constexpr int EW_THREADS = 256;
+constexpr int EW_CTAS_PER_SM = 8;
+constexpr int MAX_RED_BLOCKS = 4096; // partial slots per reduction output
+
+// One queued statement (vector operands are handles; scalars are values).
+struct pending {
+	enum kind_t { EW, RED, SPMV } kind;
+	int op; // ew_op for EW/RED
+	fsb_vec_s * z = nullptr;
+	fsb_vec_s * x = nullptr;
+	fsb_vec_s * y = nullptr;
+	double a = 0, b = 0;
+	int64_t token = -1; // RED
+	fsb_parcsr_s * A = nullptr; // SPMV
+};
+
+struct red_slot {
+	double * d_value; // device result (post intra-rank reduction)
+	volatile double * h_value; // pinned mapped host mirror
+	volatile int64_t * h_flag; // token written after the value
+	int nccl_op; // 0 sum 1 max 2 min
+};
+
+} // namespace fsb
+
+struct fsb_ctx_s {
+	int device = 0, rank = 0, nranks = 1;
+	cudaStream_t stream = nullptr;
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+	ncclComm_t nccl = nullptr; // reductions + setup, used on `stream`
+	ncclComm_t nccl_halo_comm = nullptr; // ghost exchange, used on `comm_stream`
+	ncclComm_t nccl_halo() const { return nccl_halo_comm; }
+
+	// reductions
+	double * d_partials = nullptr; // [MAX_RED][MAX_RED_BLOCKS]
+	unsigned * d_counter = nullptr;
+	double * d_results = nullptr; // [FSB_RED_RING]
+	double * h_results = nullptr; // pinned+mapped [FSB_RED_RING]
+	double * h_results_dev = nullptr; // device alias of h_results
+	int64_t * h_flags = nullptr; // pinned+mapped [FSB_RED_RING]
+	int64_t * h_flags_dev = nullptr;
+	int64_t next_token = 1;
+	std::vector<int> token_op; // per ring slot: nccl op kind of the reduction
+	std::vector<cudaEvent_t> token_event; // multi-rank path
+
+	// deferred statements
+	std::vector<fsb::pending> queue;
+	bool fusion = true;
+	bool trace = false;
+	int spmv_rows_per_cta = 0; // 0 = auto
+	int spmv_threads = 0;
+
+	// L2 flush scratch
+	void * d_flush = nullptr;
+	size_t flush_bytes = 0;
+
+	int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	uint64_t next_vec_id = 1;
+};
+
+struct fsb_vec_s {
+	fsb_ctx_s * ctx = nullptr;
+	double * d = nullptr;
+	int64_t n_owned = 0, n_ghost = 0;
+	bool owns = true;
+	bool halo_valid = false;
+	uint64_t id = 0;
+};
+
+namespace fsb {
+
+// one CSR block (diag or offd) in device memory
+struct csr_block {
+	int64_t n_rows = 0; // rows described by rowptr
+	int64_t nnz = 0;
+	bool wide = false; // 64-bit row offsets
+	void * rowptr = nullptr; // int32 or int64 [n_rows+1]
+	int32_t * col = nullptr; // [nnz padded]
+	double * val = nullptr; // [nnz padded]
+	// row-block work descriptors for the streaming kernel
+	int32_t * blk_row = nullptr; // [n_blk+1] first row of each CTA's row block
+	int n_blk = 0;
+	int max_blk_nnz = 0; // max nnz staged by one CTA (smem sizing)
+	int max_blk_rows = 0;
+	int32_t * row_ids = nullptr; // compressed row list (offd): row index per compressed row, or null
+};
+
+struct neighbour {
+	int rank;
+	int64_t send_count, recv_count;
+	int64_t recv_offset; // offset into ghost region
+	int64_t send_offset; // offset into packed send buffer
+	int64_t contiguous_start; // >= 0: send list is the range [start, start+count) of x (no pack)
+};
+
+} // namespace fsb
+
+struct fsb_parcsr_s {
+	fsb_ctx_s * ctx = nullptr;
+	int64_t n_global = 0, n_local = 0, n_ghost = 0, row_begin = 0;
+	fsb::csr_block diag, offd;
+	int64_t * d_colmap = nullptr;
+	std::vector<int64_t> colmap; // host copy
+	std::vector<int64_t> row_part;
+	std::vector<fsb::neighbour> nbrs;
+	int32_t * d_send_idx = nullptr; // packed send lists
+	double * d_send_buf = nullptr;
+	int64_t send_total = 0;
+	bool need_pack = false;
+	double * d_dinv = nullptr; // lazily computed 1/diag (jacobi relax)
+};
+
+namespace fsb {
+
+// queue / fuser (fuser.cu)
+void enqueue(fsb_ctx_s * c, const pending & p);
+void flush(fsb_ctx_s * c);
+int64_t new_token(fsb_ctx_s * c, int nccl_op);
+
+// kernels (declared here, defined in their .cu)
+void launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
+                 const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s);
+int spmv_partial_count(const csr_block & B);
+void finalize_reduction(fsb_ctx_s * c, int n_partials, int64_t token, int op_kind);
+void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x);
+
+void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * host_rowptr);
+void extract_dinv(fsb_parcsr_s * A, double * d);
+void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot);
+
+} // namespace fsb

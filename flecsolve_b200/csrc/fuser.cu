@@ -1,0 +1,365 @@
+// Deferred-execution queue: groups queued statements into registered fused kernels.
+//
+// Why: the reference's Krylov loops issue one task per vector operation
+// (solvers/cg.hh:95-130: 1 SpMV, 3 axpy, 2 dot, 1 norm, 1 preconditioner apply per
+// iteration = 8 passes over HBM).  Keeping that call sequence as the API, the queue
+// launches e.g. {x += a p; r -= a w; |r|^2} as ONE kernel when the norm is read.
+// Statements are evaluated in program order per element, so fusing never changes a
+// value; only reductions see a different (fixed, reproducible) summation order.
+#include <cstring>
+#include <string>
+#include <unordered_map>
+
+#include "ew_kernels.cuh"
+#include "fsb_internal.h"
+
+namespace fsb {
+
+// ---------------------------------------------------------------- registry
+
+using launcher_t = void (*)(const ew_args &, int grid, cudaStream_t);
+
+template<class PT>
+static void launch_program(const ew_args & a, int grid, cudaStream_t s) {
+	ew_program_kernel<PT><<<grid, EW_BLOCK, 0, s>>>(a);
+}
+
+static std::string key_of(const program & p) {
+	std::string k(reinterpret_cast<const char *>(&p.n), sizeof(int));
+	k.append(reinterpret_cast<const char *>(p.st), sizeof(stmt) * p.n);
+	return k;
+}
+
+struct registry_t {
+	std::unordered_map<std::string, launcher_t> map;
+	template<class PT>
+	void add() {
+		static_assert(PT::ok, "program exceeds slot limits");
+		map.emplace(key_of(PT::value), &launch_program<PT>);
+	}
+};
+
+// Programs are written with small vector names; canonicalize() renames them.
+#define FSB_PROGRAM(NAME, ...)                                                          \
+	struct NAME {                                                                       \
+		static constexpr raw_stmt raw[] = {__VA_ARGS__};                               \
+		static constexpr canon_result cr = canonicalize(raw, sizeof(raw) / sizeof(raw_stmt)); \
+		static constexpr bool ok = cr.ok;                                               \
+		static constexpr program value = cr.p;                                          \
+	};
+
+// shorthand: {op, z, x, y}
+#define S_SET(z) {OP_SET, z, -1, -1}
+#define S_SCALE(z, x) {OP_SCALE, z, x, -1}
+#define S_LIN2(z, x, y) {OP_LIN2, z, x, y}
+#define S_MUL(z, x, y) {OP_MUL, z, x, y}
+#define S_DIV(z, x, y) {OP_DIV, z, x, y}
+#define S_RECIP(z, x) {OP_RECIP, z, x, -1}
+#define S_ABS(z, x) {OP_ABS, z, x, -1}
+#define S_ADDS(z, x) {OP_ADDS, z, x, -1}
+#define R_DOT(x, y) {RD_DOT, -1, x, y}
+#define R_ASUM(x) {RD_ASUM, -1, x, -1}
+#define R_AMAX(x) {RD_AMAX, -1, x, -1}
+#define R_MIN(x) {RD_MIN, -1, x, -1}
+#define R_MAX(x) {RD_MAX, -1, x, -1}
+#define R_POWSUM(x) {RD_POWSUM, -1, x, -1}
+
+// ---- every single statement, in every alias pattern that survives normalisation ----
+FSB_PROGRAM(p_set, S_SET(0))
+FSB_PROGRAM(p_scale, S_SCALE(1, 0))
+FSB_PROGRAM(p_scale_self, S_SCALE(0, 0))
+FSB_PROGRAM(p_lin2, S_LIN2(2, 0, 1))
+FSB_PROGRAM(p_lin2_zy, S_LIN2(1, 0, 1))
+FSB_PROGRAM(p_lin2_xx, S_LIN2(1, 0, 0))
+FSB_PROGRAM(p_lin2_xxx, S_LIN2(0, 0, 0))
+FSB_PROGRAM(p_mul, S_MUL(2, 0, 1))
+FSB_PROGRAM(p_mul_zy, S_MUL(1, 0, 1))
+FSB_PROGRAM(p_mul_xx, S_MUL(1, 0, 0))
+FSB_PROGRAM(p_mul_xxx, S_MUL(0, 0, 0))
+FSB_PROGRAM(p_div, S_DIV(2, 0, 1))
+FSB_PROGRAM(p_div_zx, S_DIV(0, 0, 1))
+FSB_PROGRAM(p_div_zy, S_DIV(1, 0, 1))
+FSB_PROGRAM(p_div_xx, S_DIV(1, 0, 0))
+FSB_PROGRAM(p_div_xxx, S_DIV(0, 0, 0))
+FSB_PROGRAM(p_recip, S_RECIP(1, 0))
+FSB_PROGRAM(p_recip_self, S_RECIP(0, 0))
+FSB_PROGRAM(p_abs, S_ABS(1, 0))
+FSB_PROGRAM(p_abs_self, S_ABS(0, 0))
+FSB_PROGRAM(p_adds, S_ADDS(1, 0))
+FSB_PROGRAM(p_adds_self, S_ADDS(0, 0))
+FSB_PROGRAM(p_dot, R_DOT(0, 1))
+FSB_PROGRAM(p_sumsq, R_DOT(0, 0))
+FSB_PROGRAM(p_asum, R_ASUM(0))
+FSB_PROGRAM(p_amax, R_AMAX(0))
+FSB_PROGRAM(p_min, R_MIN(0))
+FSB_PROGRAM(p_max, R_MAX(0))
+FSB_PROGRAM(p_powsum, R_POWSUM(0))
+
+// ---- fused groups the Krylov loops produce (reference line numbers in comments) ----
+// CG update, cg.hh:108-111:  x = a p + x ; r = -a w + r ; |r|^2
+FSB_PROGRAM(p_cg_update, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), R_DOT(3, 3))
+// same without the norm (diagnostic reads x first) and the tail alone
+FSB_PROGRAM(p_axpy2, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3))
+FSB_PROGRAM(p_axpy_sumsq, S_LIN2(1, 0, 1), R_DOT(1, 1))
+FSB_PROGRAM(p_lin2_sumsq, S_LIN2(2, 0, 1), R_DOT(2, 2))
+// Jacobi apply + r.z, cg.hh:124-127:  z = dinv * r ; r.z   (and z.r before the loop, cg.hh:87)
+FSB_PROGRAM(p_jacobi_dot_rz, S_MUL(2, 0, 1), R_DOT(1, 2))
+FSB_PROGRAM(p_jacobi_dot_zr, S_MUL(2, 0, 1), R_DOT(2, 1))
+// identity preconditioner: z = r ; r.z
+FSB_PROGRAM(p_copy_dot_rz, S_SCALE(1, 0), R_DOT(0, 1))
+FSB_PROGRAM(p_copy_dot_zr, S_SCALE(1, 0), R_DOT(1, 0))
+// residual r = b - r then its norm (operators/core.hh:140, cg.hh:71-74)
+FSB_PROGRAM(p_resid_sumsq, S_LIN2(1, 0, 1), R_DOT(1, 1))
+// GMRES modified Gram-Schmidt, gmres.hh:269-276:  v -= h q_j ; v.q_{j+1}   /  v -= h q_j ; |v|^2
+FSB_PROGRAM(p_mgs_step, S_LIN2(1, 0, 1), R_DOT(1, 2))
+// GMRES normalise + store + identity precondition, gmres.hh:156-162,143-146
+FSB_PROGRAM(p_scale_copy, S_SCALE(0, 0), S_SCALE(1, 0))
+FSB_PROGRAM(p_scale_copy_copy, S_SCALE(0, 0), S_SCALE(1, 0), S_SCALE(2, 1))
+FSB_PROGRAM(p_scale_copy_mul, S_SCALE(0, 0), S_SCALE(1, 0), S_MUL(3, 2, 1))
+FSB_PROGRAM(p_copy_copy, S_SCALE(1, 0), S_SCALE(2, 1))
+FSB_PROGRAM(p_copy_mul, S_SCALE(1, 0), S_MUL(3, 2, 1))
+// GMRES correction, gmres.hh:249-258: z = 0 ; z += y_i q_i (pairs)
+FSB_PROGRAM(p_set_axpy, S_SET(0), S_LIN2(0, 1, 0))
+FSB_PROGRAM(p_axpy_axpy_same, S_LIN2(1, 0, 1), S_LIN2(1, 2, 1))
+FSB_PROGRAM(p_axpy4_same, S_LIN2(1, 0, 1), S_LIN2(1, 2, 1), S_LIN2(1, 3, 1), S_LIN2(1, 4, 1))
+// BiCGStab, bicgstab.hh:120-124: p = -w v + p ; p = b p + res ; p_hat = P p
+FSB_PROGRAM(p_bicg_dir_jacobi, S_LIN2(1, 0, 1), S_LIN2(1, 2, 1), S_MUL(4, 3, 1))
+FSB_PROGRAM(p_bicg_dir_copy, S_LIN2(1, 0, 1), S_LIN2(1, 2, 1), S_SCALE(3, 1))
+FSB_PROGRAM(p_bicg_dir, S_LIN2(1, 0, 1), S_LIN2(1, 2, 1))
+// bicgstab.hh:132-134: s = -a v + res ; |s|^2        (p_lin2_sumsq)
+// bicgstab.hh:145: s_hat = P s
+// bicgstab.hh:153-158: x += a p_hat ; x += w s_hat ; res = -w t + s ; |res|^2
+FSB_PROGRAM(p_bicg_update, S_LIN2(1, 0, 1), S_LIN2(1, 2, 1), S_LIN2(5, 3, 4), R_DOT(5, 5))
+// two dots sharing an operand (bicgstab.hh:149-150 when both are queued)
+FSB_PROGRAM(p_dot2, R_DOT(0, 0), R_DOT(0, 1))
+// operator_adapter, time-integrators/operator_adapter.hh:29-35: y = -g y + x
+// (single p_lin2_zy after normalisation)
+// preconditioned residual pair used by left-preconditioned paths: z = d*r ; |z|^2
+FSB_PROGRAM(p_mul_sumsq, S_MUL(2, 0, 1), R_DOT(2, 2))
+// two independent norms / dots queued back to back (vec::multi with 2 components)
+FSB_PROGRAM(p_sumsq2, R_DOT(0, 0), R_DOT(1, 1))
+FSB_PROGRAM(p_dot_dot, R_DOT(0, 1), R_DOT(2, 3))
+FSB_PROGRAM(p_lin2_lin2, S_LIN2(2, 0, 1), S_LIN2(5, 3, 4))
+FSB_PROGRAM(p_scale2, S_SCALE(1, 0), S_SCALE(3, 2))
+FSB_PROGRAM(p_set2, S_SET(0), S_SET(1))
+
+static registry_t & registry() {
+	static registry_t r = [] {
+		registry_t g;
+		g.add<p_set>(); g.add<p_scale>(); g.add<p_scale_self>();
+		g.add<p_lin2>(); g.add<p_lin2_zy>(); g.add<p_lin2_xx>(); g.add<p_lin2_xxx>();
+		g.add<p_mul>(); g.add<p_mul_zy>(); g.add<p_mul_xx>(); g.add<p_mul_xxx>();
+		g.add<p_div>(); g.add<p_div_zx>(); g.add<p_div_zy>(); g.add<p_div_xx>(); g.add<p_div_xxx>();
+		g.add<p_recip>(); g.add<p_recip_self>(); g.add<p_abs>(); g.add<p_abs_self>();
+		g.add<p_adds>(); g.add<p_adds_self>();
+		g.add<p_dot>(); g.add<p_sumsq>(); g.add<p_asum>(); g.add<p_amax>(); g.add<p_min>(); g.add<p_max>();
+		g.add<p_powsum>();
+		g.add<p_cg_update>(); g.add<p_axpy2>(); g.add<p_axpy_sumsq>(); g.add<p_lin2_sumsq>();
+		g.add<p_jacobi_dot_rz>(); g.add<p_jacobi_dot_zr>(); g.add<p_copy_dot_rz>(); g.add<p_copy_dot_zr>();
+		g.add<p_resid_sumsq>(); g.add<p_mgs_step>();
+		g.add<p_scale_copy>(); g.add<p_scale_copy_copy>(); g.add<p_scale_copy_mul>();
+		g.add<p_copy_copy>(); g.add<p_copy_mul>();
+		g.add<p_set_axpy>(); g.add<p_axpy_axpy_same>(); g.add<p_axpy4_same>();
+		g.add<p_bicg_dir_jacobi>(); g.add<p_bicg_dir_copy>(); g.add<p_bicg_dir>(); g.add<p_bicg_update>();
+		g.add<p_dot2>(); g.add<p_mul_sumsq>(); g.add<p_sumsq2>(); g.add<p_dot_dot>();
+		g.add<p_lin2_lin2>(); g.add<p_scale2>(); g.add<p_set2>();
+		return g;
+	}();
+	return r;
+}
+
+// ---------------------------------------------------------------- queue
+
+static int64_t length_of(const pending & p) {
+	return p.kind == pending::RED ? p.x->n_owned : p.z->n_owned;
+}
+
+static std::string describe(const pending * q, int n) {
+	static const char * names[] = {"set", "scale", "lin2", "mul", "div", "recip", "abs", "adds"};
+	static const char * rnames[] = {"dot", "asum", "amax", "min", "max", "powsum"};
+	std::string s;
+	for (int i = 0; i < n; ++i) {
+		if (i)
+			s += " ; ";
+		if (q[i].kind == pending::SPMV) {
+			s += "spmv";
+			continue;
+		}
+		s += is_reduction(q[i].op) ? rnames[q[i].op - RD_FIRST] : names[q[i].op];
+		auto id = [](fsb_vec_s * v) { return v ? std::to_string(v->id) : std::string("-"); };
+		s += "(z" + id(q[i].z) + ",x" + id(q[i].x) + ",y" + id(q[i].y) + ")";
+	}
+	return s;
+}
+
+struct bound_group {
+	launcher_t launch = nullptr;
+	ew_args args{};
+	int nr = 0;
+};
+
+// try to bind queue[i, i+len) to a registered kernel
+static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & g) {
+	raw_stmt rs[MAXS];
+	fsb_vec_s * vecs[3 * MAXS];
+	int nvec = 0;
+	auto id_of = [&](fsb_vec_s * v) {
+		for (int k = 0; k < nvec; ++k)
+			if (vecs[k] == v)
+				return k;
+		vecs[nvec] = v;
+		return nvec++;
+	};
+	for (int i = 0; i < len; ++i) {
+		rs[i].op = q[i].op;
+		rs[i].x = reads_x(q[i].op) ? id_of(q[i].x) : -1;
+		rs[i].y = reads_y(q[i].op) ? id_of(q[i].y) : -1;
+		rs[i].z = is_reduction(q[i].op) ? -1 : id_of(q[i].z);
+	}
+	const canon_result cr = canonicalize(rs, len);
+	if (!cr.ok)
+		return false;
+	auto it = registry().map.find(key_of(cr.p));
+	if (it == registry().map.end())
+		return false;
+	g.launch = it->second;
+	g.nr = cr.p.nr;
+	ew_args & a = g.args;
+	for (int k = 0; k < cr.p.nv; ++k)
+		a.v[k] = vecs[cr.id_of_slot[k]]->d;
+	a.n = length_of(q[0]);
+	a.partials = c->d_partials;
+	a.counter = c->d_counter;
+	a.partial_stride = MAX_RED_BLOCKS;
+	for (int i = 0; i < len; ++i) {
+		const stmt & s = cr.p.st[i];
+		if (s.a >= 0)
+			a.s[s.a] = q[i].a;
+		if (s.b >= 0)
+			a.s[s.b] = q[i].b;
+		if (is_reduction(s.op)) {
+			const int slot = static_cast<int>(q[i].token % FSB_RED_RING);
+			red_out & r = a.r[s.z];
+			r.d_value = c->d_results + slot;
+			r.token = q[i].token;
+			if (c->nranks == 1) {
+				r.h_value = c->h_results_dev + slot;
+				r.h_flag = reinterpret_cast<long long *>(c->h_flags_dev + slot);
+			}
+			else {
+				r.h_value = nullptr;
+				r.h_flag = nullptr;
+			}
+		}
+	}
+	return true;
+}
+
+// After a kernel that produced intra-rank reduction values: finish across ranks.
+static void publish_multi_rank(fsb_ctx_s * c, const pending * q, int len) {
+	if (c->nranks == 1)
+		return;
+	for (int i = 0; i < len; ++i) {
+		if (q[i].kind != pending::RED)
+			continue;
+		const int slot = static_cast<int>(q[i].token % FSB_RED_RING);
+		const int f = fold_of(q[i].op);
+		const ncclRedOp_t op = f == 0 ? ncclSum : (f == 1 ? ncclMax : ncclMin);
+		FSB_NCCL(ncclAllReduce(c->d_results + slot, c->d_results + slot, 1, ncclDouble, op, c->nccl, c->stream));
+		c->stats[FSB_STAT_ALLREDUCES]++;
+		FSB_CUDA(cudaMemcpyAsync(c->h_results + slot, c->d_results + slot, sizeof(double), cudaMemcpyDeviceToHost,
+		                         c->stream));
+		FSB_CUDA(cudaEventRecord(c->token_event[slot], c->stream));
+	}
+}
+
+void flush(fsb_ctx_s * c) {
+	if (c->queue.empty())
+		return;
+	std::vector<pending> q;
+	q.swap(c->queue); // launches below must not re-enter the queue
+	const int total = static_cast<int>(q.size());
+	int i = 0;
+	while (i < total) {
+		if (q[i].kind == pending::SPMV) {
+			// y = A x, optionally fused with a following dot that involves y
+			const pending * dot = nullptr;
+			if (c->fusion && i + 1 < total && q[i + 1].kind == pending::RED && q[i + 1].op == RD_DOT &&
+			    (q[i + 1].x == q[i].y || q[i + 1].y == q[i].y))
+				dot = &q[i + 1];
+			if (c->trace)
+				fprintf(stderr, "[fsb] launch: spmv%s\n", dot ? " + dot" : "");
+			spmv_group(c, q[i], dot);
+			if (dot) {
+				publish_multi_rank(c, dot, 1);
+				c->stats[FSB_STAT_FUSED_STATEMENTS] += 2;
+			}
+			i += dot ? 2 : 1;
+			continue;
+		}
+		int j = i;
+		const int64_t n = length_of(q[i]);
+		const int cap = c->fusion ? MAXS : 1;
+		while (j < total && j - i < cap && q[j].kind != pending::SPMV && length_of(q[j]) == n)
+			++j;
+		bound_group g;
+		int len = j - i;
+		for (; len >= 1; --len)
+			if (bind_group(c, &q[i], len, g))
+				break;
+		if (len < 1)
+			throw error(FSB_ERR_STATE, "no kernel for statement: " + describe(&q[i], 1));
+		if (len < j - i)
+			c->stats[FSB_STAT_UNMATCHED_GROUPS]++;
+		if (c->trace)
+			fprintf(stderr, "[fsb] launch: %s%s\n", describe(&q[i], len).c_str(),
+			        len < j - i ? ("   <-- split from: " + describe(&q[i], j - i)).c_str() : "");
+		if (n > 0) {
+			long long packets = (n + 1) / 2;
+			long long want = (packets + EW_BLOCK - 1) / EW_BLOCK;
+			int grid = static_cast<int>(std::min<long long>(want, SM_COUNT * EW_CTAS_PER_SM));
+			if (grid < 1)
+				grid = 1;
+			g.launch(g.args, grid, c->stream);
+			FSB_CUDA(cudaGetLastError());
+			c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+		}
+		else if (g.nr > 0) {
+			// empty local part: publish fold identities without a kernel
+			for (int k = i; k < i + len; ++k) {
+				if (q[k].kind != pending::RED)
+					continue;
+				const int slot = static_cast<int>(q[k].token % FSB_RED_RING);
+				const int f = fold_of(q[k].op);
+				const double ident = f == 0 ? 0.0 : (f == 1 ? -HUGE_VAL : HUGE_VAL);
+				FSB_CUDA(cudaMemcpyAsync(c->d_results + slot, &ident, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+				if (c->nranks == 1) {
+					FSB_CUDA(cudaStreamSynchronize(c->stream));
+					c->h_results[slot] = ident;
+					c->h_flags[slot] = q[k].token;
+				}
+			}
+		}
+		for (int k = i; k < i + len; ++k) // ghost copies of overwritten vectors are stale from here on
+			if (q[k].kind == pending::EW)
+				q[k].z->halo_valid = false;
+		if (len > 1)
+			c->stats[FSB_STAT_FUSED_STATEMENTS] += len;
+		publish_multi_rank(c, &q[i], len);
+		i += len;
+	}
+}
+
+void enqueue(fsb_ctx_s * c, const pending & p) {
+	c->queue.push_back(p);
+	if (!c->fusion || c->queue.size() >= 64)
+		flush(c);
+}
+
+int64_t new_token(fsb_ctx_s * c, int fold) {
+	const int64_t t = c->next_token++;
+	c->token_op[t % FSB_RED_RING] = fold;
+	return t;
+}
+
+} // namespace fsb

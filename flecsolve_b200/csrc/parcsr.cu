@@ -1,0 +1,688 @@
+// Parallel CSR matrix: construction (ghost discovery, diag/offd split, halo plan),
+// synthetic stencil generators, SpMV orchestration with halo overlap, Jacobi.
+//
+// Reference: topo::csr::color() / init_mats() (topo/csr.hh:482-618), the ghost copy plan
+// (topo/csr.hh:116-187,277-304), mat::parcsr_ops::spmv (matrices/parcsr.hh:61-91),
+// mg::bound_jacobi::relax (solvers/mg/jacobi.hh:44-93), Dinv() (util/test/mesh.hh:123-140).
+#include <algorithm>
+#include <cub/cub.cuh>
+#include <numeric>
+#include <thrust/iterator/transform_iterator.h>
+
+#include "fsb_internal.h"
+
+namespace fsb {
+
+// ------------------------------------------------------------------ helpers
+
+template<class T>
+static T * dev_alloc(size_t n) {
+	T * p = nullptr;
+	FSB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+	return p;
+}
+
+template<class T>
+static T * dev_upload(fsb_ctx_s * c, const std::vector<T> & h, size_t pad = 0) {
+	T * p = dev_alloc<T>(h.size() + pad);
+	if (!h.empty())
+		FSB_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+	return p;
+}
+
+static void free_block(csr_block & B) {
+	cudaFree(B.rowptr);
+	cudaFree(B.col);
+	cudaFree(B.val);
+	cudaFree(B.blk_row);
+	cudaFree(B.row_ids);
+	B = csr_block{};
+}
+
+// upload a host CSR block (int64 rowptr) choosing 32- or 64-bit offsets
+static void upload_block(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> & rowptr,
+                         const std::vector<int32_t> & col, const std::vector<double> & val,
+                         const std::vector<int32_t> * row_ids) {
+	B.n_rows = static_cast<int64_t>(rowptr.size()) - 1;
+	B.nnz = rowptr.empty() ? 0 : rowptr.back();
+	B.wide = B.nnz >= (1LL << 31) - 16;
+	if (B.wide) {
+		B.rowptr = dev_upload<int64_t>(c, rowptr);
+	}
+	else {
+		std::vector<int32_t> rp32(rowptr.begin(), rowptr.end());
+		B.rowptr = dev_upload<int32_t>(c, rp32);
+		FSB_CUDA(cudaStreamSynchronize(c->stream)); // rp32 is a temporary
+	}
+	B.col = dev_upload<int32_t>(c, col, 16);
+	B.val = dev_upload<double>(c, val, 16);
+	if (row_ids)
+		B.row_ids = dev_upload<int32_t>(c, *row_ids);
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	if (B.n_rows > 0)
+		build_blocks(c, B, &rowptr);
+}
+
+// ------------------------------------------------------------------ halo plan (general)
+
+// Exchange the ghost lists: every rank tells each owner which of its entries it needs.
+static void build_halo_plan(fsb_parcsr_s * A) {
+	fsb_ctx_s * c = A->ctx;
+	const int P = c->nranks, me = c->rank;
+	A->nbrs.clear();
+	if (P == 1)
+		return;
+	// recv side: ghosts are sorted by global id, owners are contiguous ranges
+	std::vector<int64_t> recv_cnt(P, 0), recv_off(P, 0);
+	{
+		size_t g = 0;
+		for (int q = 0; q < P; ++q) {
+			recv_off[q] = static_cast<int64_t>(g);
+			while (g < A->colmap.size() && A->colmap[g] < A->row_part[q + 1])
+				++g;
+			recv_cnt[q] = static_cast<int64_t>(g) - recv_off[q];
+		}
+	}
+	// all-gather the P x P count matrix
+	int64_t * d_cnt = dev_alloc<int64_t>(static_cast<size_t>(P) * P);
+	FSB_CUDA(cudaMemcpyAsync(d_cnt + static_cast<size_t>(me) * P, recv_cnt.data(), P * sizeof(int64_t),
+	                         cudaMemcpyHostToDevice, c->stream));
+	FSB_NCCL(ncclAllGather(d_cnt + static_cast<size_t>(me) * P, d_cnt, P, ncclInt64, c->nccl, c->stream));
+	std::vector<int64_t> all(static_cast<size_t>(P) * P);
+	FSB_CUDA(cudaMemcpyAsync(all.data(), d_cnt, all.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(d_cnt);
+
+	std::vector<int64_t> send_cnt(P, 0), send_off(P, 0);
+	int64_t send_total = 0;
+	for (int q = 0; q < P; ++q) {
+		send_cnt[q] = all[static_cast<size_t>(q) * P + me]; // what q receives from me
+		send_off[q] = send_total;
+		send_total += send_cnt[q];
+	}
+	// ship the requested global ids to their owners
+	int64_t * d_want = dev_alloc<int64_t>(A->colmap.size());
+	int64_t * d_asked = dev_alloc<int64_t>(static_cast<size_t>(send_total));
+	if (!A->colmap.empty())
+		FSB_CUDA(cudaMemcpyAsync(d_want, A->colmap.data(), A->colmap.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
+		                         c->stream));
+	FSB_NCCL(ncclGroupStart());
+	for (int q = 0; q < P; ++q) {
+		if (q == me)
+			continue;
+		if (recv_cnt[q] > 0)
+			FSB_NCCL(ncclSend(d_want + recv_off[q], recv_cnt[q], ncclInt64, q, c->nccl, c->stream));
+		if (send_cnt[q] > 0)
+			FSB_NCCL(ncclRecv(d_asked + send_off[q], send_cnt[q], ncclInt64, q, c->nccl, c->stream));
+	}
+	FSB_NCCL(ncclGroupEnd());
+	std::vector<int64_t> asked(static_cast<size_t>(send_total));
+	if (send_total > 0)
+		FSB_CUDA(cudaMemcpyAsync(asked.data(), d_asked, asked.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(d_want);
+	cudaFree(d_asked);
+
+	std::vector<int32_t> send_idx(static_cast<size_t>(send_total));
+	bool need_pack = false;
+	for (int q = 0; q < P; ++q) {
+		if (q == me || (send_cnt[q] == 0 && recv_cnt[q] == 0))
+			continue;
+		neighbour nb{};
+		nb.rank = q;
+		nb.send_count = send_cnt[q];
+		nb.recv_count = recv_cnt[q];
+		nb.recv_offset = recv_off[q];
+		nb.send_offset = send_off[q];
+		bool contiguous = true;
+		for (int64_t k = 0; k < send_cnt[q]; ++k) {
+			const int64_t local = asked[send_off[q] + k] - A->row_begin;
+			FSB_REQUIRE(local >= 0 && local < A->n_local, "halo plan: peer asked for an entry this rank does not own");
+			send_idx[send_off[q] + k] = static_cast<int32_t>(local);
+			if (k > 0 && send_idx[send_off[q] + k] != send_idx[send_off[q] + k - 1] + 1)
+				contiguous = false;
+		}
+		nb.contiguous_start = (contiguous && send_cnt[q] > 0) ? send_idx[send_off[q]] : -1;
+		if (!contiguous)
+			need_pack = true;
+		A->nbrs.push_back(nb);
+	}
+	A->send_total = send_total;
+	A->need_pack = need_pack;
+	if (need_pack) {
+		A->d_send_idx = dev_upload<int32_t>(c, send_idx);
+		A->d_send_buf = dev_alloc<double>(static_cast<size_t>(send_total));
+		FSB_CUDA(cudaStreamSynchronize(c->stream));
+	}
+}
+
+__global__ void pack_kernel(const double * __restrict__ x, const int32_t * __restrict__ idx, double * __restrict__ buf,
+                            long long n) {
+	const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i < n)
+		buf[i] = x[idx[i]];
+}
+
+// Ghost update of x on the communication stream; the caller orders streams around it.
+static void halo_exchange_async(fsb_parcsr_s * A, fsb_vec_s * x) {
+	fsb_ctx_s * c = A->ctx;
+	// x must be complete on the main stream before it is packed/sent
+	FSB_CUDA(cudaEventRecord(c->ev_main, c->stream));
+	FSB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_main, 0));
+	if (A->need_pack) {
+		const long long n = A->send_total;
+		pack_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, c->comm_stream>>>(x->d, A->d_send_idx, A->d_send_buf, n);
+		FSB_CUDA(cudaGetLastError());
+		c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+	}
+	FSB_NCCL(ncclGroupStart());
+	for (const neighbour & nb : A->nbrs) {
+		if (nb.send_count > 0) {
+			const double * src = (A->need_pack && nb.contiguous_start < 0) ? A->d_send_buf + nb.send_offset
+			                                                                : x->d + nb.contiguous_start;
+			FSB_NCCL(ncclSend(src, nb.send_count, ncclDouble, nb.rank, c->nccl_halo(), c->comm_stream));
+		}
+		if (nb.recv_count > 0)
+			FSB_NCCL(ncclRecv(x->d + x->n_owned + nb.recv_offset, nb.recv_count, ncclDouble, nb.rank, c->nccl_halo(),
+			                  c->comm_stream));
+	}
+	FSB_NCCL(ncclGroupEnd());
+	FSB_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
+	c->stats[FSB_STAT_HALO_EXCHANGES]++;
+	x->halo_valid = true;
+}
+
+void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x) {
+	fsb_ctx_s * c = A->ctx;
+	flush(c);
+	if (c->nranks == 1 || A->nbrs.empty())
+		return;
+	FSB_REQUIRE(x->n_owned == A->n_local && x->n_ghost >= A->n_ghost, "halo_exchange: vector does not match the matrix");
+	halo_exchange_async(A, x);
+	FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+}
+
+// ------------------------------------------------------------------ SpMV orchestration
+
+// y = A x (+ optional fused dot).  Called by the queue flush.
+void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot) {
+	fsb_parcsr_s * A = sp.A;
+	fsb_vec_s *x = sp.x, *y = sp.y;
+	const bool multi = c->nranks > 1 && !A->nbrs.empty();
+	bool waited = true;
+	if (multi && !x->halo_valid) {
+		halo_exchange_async(A, x); // overlaps the diag block below
+		waited = false;
+	}
+	const double * u = nullptr;
+	if (dot) {
+		fsb_vec_s * other = dot->x == y ? dot->y : dot->x;
+		u = other->d; // other == y gives sum y^2
+	}
+	const int np_diag = u ? spmv_partial_count(A->diag) : 0;
+	launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream);
+	int np_offd = 0;
+	if (A->offd.n_blk > 0) {
+		if (!waited)
+			FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+		waited = true;
+		np_offd = u ? spmv_partial_count(A->offd) : 0;
+		launch_spmv(c, A->offd, x->d, y->d, true, u, c->d_partials, np_diag, c->stream);
+	}
+	if (!waited) // ghosts were requested but no row uses them: still order the streams
+		FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+	if (dot)
+		finalize_reduction(c, np_diag + np_offd, dot->token, 0);
+	y->halo_valid = false;
+}
+
+// ------------------------------------------------------------------ creation from host CSR
+
+} // namespace fsb
+
+using namespace fsb;
+
+fsb_parcsr_s * fsb_parcsr_create_impl(fsb_ctx_s * c, int64_t n_global, const int64_t * row_part, const int64_t * rowptr,
+                                      const int64_t * col, const double * val) {
+	flush(c);
+	const int P = c->nranks, me = c->rank;
+	auto * A = new fsb_parcsr_s;
+	A->ctx = c;
+	A->n_global = n_global;
+	A->row_part.assign(row_part, row_part + P + 1);
+	FSB_REQUIRE(A->row_part[0] == 0 && A->row_part[P] == n_global, "parcsr: row_part must span [0, n_global]");
+	A->row_begin = row_part[me];
+	const int64_t row_end = row_part[me + 1];
+	A->n_local = row_end - A->row_begin;
+	const int64_t nnz = rowptr[A->n_local];
+
+	// color(): ghosts = sorted unique off-rank column ids (topo/csr.hh:506-524)
+	std::vector<int64_t> ghosts;
+	for (int64_t k = 0; k < nnz; ++k) {
+		FSB_REQUIRE(col[k] >= 0 && col[k] < n_global, "parcsr: column index out of range");
+		if (col[k] < A->row_begin || col[k] >= row_end)
+			ghosts.push_back(col[k]);
+	}
+	std::sort(ghosts.begin(), ghosts.end());
+	ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+	A->n_ghost = static_cast<int64_t>(ghosts.size());
+	A->colmap = ghosts;
+	FSB_REQUIRE(A->n_local + A->n_ghost < (1LL << 31), "parcsr: local column space exceeds int32");
+
+	// init_mats(): split rows, keeping the input order inside each row (topo/csr.hh:583-616)
+	std::vector<int64_t> drp(A->n_local + 1, 0), orp_full(A->n_local + 1, 0);
+	std::vector<int32_t> dcol, ocol;
+	std::vector<double> dval, oval;
+	dcol.reserve(nnz);
+	dval.reserve(nnz);
+	for (int64_t r = 0; r < A->n_local; ++r) {
+		for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+			const int64_t cid = col[k];
+			if (cid >= A->row_begin && cid < row_end) {
+				dcol.push_back(static_cast<int32_t>(cid - A->row_begin));
+				dval.push_back(val[k]);
+			}
+			else {
+				const int64_t g = std::lower_bound(ghosts.begin(), ghosts.end(), cid) - ghosts.begin();
+				ocol.push_back(static_cast<int32_t>(A->n_local + g));
+				oval.push_back(val[k]);
+			}
+		}
+		drp[r + 1] = static_cast<int64_t>(dcol.size());
+		orp_full[r + 1] = static_cast<int64_t>(ocol.size());
+	}
+	// device offd block is stored over the rows that have off-process entries only
+	std::vector<int64_t> orp(1, 0);
+	std::vector<int32_t> orows;
+	for (int64_t r = 0; r < A->n_local; ++r)
+		if (orp_full[r + 1] > orp_full[r]) {
+			orows.push_back(static_cast<int32_t>(r));
+			orp.push_back(orp_full[r + 1]);
+		}
+	upload_block(c, A->diag, drp, dcol, dval, nullptr);
+	if (!orows.empty())
+		upload_block(c, A->offd, orp, ocol, oval, &orows);
+	A->d_colmap = dev_upload<int64_t>(c, A->colmap);
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	build_halo_plan(A);
+	return A;
+}
+
+// ------------------------------------------------------------------ stencil generators
+
+namespace fsb {
+
+struct grid_desc {
+	long long nx, ny, nz;
+	long long row_begin, row_end; // owned global rows
+	long long lower, upper; // ghost counts below / above
+	double diag, off;
+	int kind; // 5, 7, 27
+};
+
+// visit the stencil of global row g in ascending column order
+template<class F>
+__device__ __forceinline__ void visit_stencil(const grid_desc & G, long long g, F && f) {
+	const long long i = g % G.nx, j = (g / G.nx) % G.ny, k = g / (G.nx * G.ny);
+	if (G.kind == 27) {
+		for (int dk = -1; dk <= 1; ++dk)
+			for (int dj = -1; dj <= 1; ++dj)
+				for (int di = -1; di <= 1; ++di) {
+					const long long ii = i + di, jj = j + dj, kk = k + dk;
+					if (ii < 0 || ii >= G.nx || jj < 0 || jj >= G.ny || kk < 0 || kk >= G.nz)
+						continue;
+					f(ii + G.nx * (jj + G.ny * kk), (di == 0 && dj == 0 && dk == 0) ? G.diag : G.off);
+				}
+	}
+	else {
+		if (G.kind == 7 && k > 0)
+			f(g - G.nx * G.ny, G.off);
+		if (j > 0)
+			f(g - G.nx, G.off);
+		if (i > 0)
+			f(g - 1, G.off);
+		f(g, G.diag);
+		if (i < G.nx - 1)
+			f(g + 1, G.off);
+		if (j < G.ny - 1)
+			f(g + G.nx, G.off);
+		if (G.kind == 7 && k < G.nz - 1)
+			f(g + G.nx * G.ny, G.off);
+	}
+}
+
+__global__ void stencil_count_kernel(grid_desc G, int * __restrict__ cnt_diag, int * __restrict__ cnt_offd) {
+	const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (r >= G.row_end - G.row_begin)
+		return;
+	int d = 0, o = 0;
+	visit_stencil(G, G.row_begin + r, [&](long long c, double) {
+		if (c >= G.row_begin && c < G.row_end)
+			++d;
+		else
+			++o;
+	});
+	cnt_diag[r] = d;
+	cnt_offd[r] = o;
+}
+
+template<class OffT>
+__global__ void stencil_fill_diag_kernel(grid_desc G, const OffT * __restrict__ rowptr, int32_t * __restrict__ col,
+                                         double * __restrict__ val) {
+	const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (r >= G.row_end - G.row_begin)
+		return;
+	long long p = static_cast<long long>(rowptr[r]);
+	visit_stencil(G, G.row_begin + r, [&](long long c, double v) {
+		if (c >= G.row_begin && c < G.row_end) {
+			col[p] = static_cast<int32_t>(c - G.row_begin);
+			val[p] = v;
+			++p;
+		}
+	});
+}
+
+__global__ void stencil_fill_offd_kernel(grid_desc G, const int32_t * __restrict__ row_ids, long long n_rows,
+                                         const int * __restrict__ rowptr, int32_t * __restrict__ col,
+                                         double * __restrict__ val) {
+	const long long cr = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (cr >= n_rows)
+		return;
+	const long long n_owned = G.row_end - G.row_begin;
+	long long p = rowptr[cr];
+	visit_stencil(G, G.row_begin + row_ids[cr], [&](long long c, double v) {
+		if (c < G.row_begin) {
+			col[p] = static_cast<int32_t>(n_owned + (c - (G.row_begin - G.lower)));
+			val[p] = v;
+			++p;
+		}
+		else if (c >= G.row_end) {
+			col[p] = static_cast<int32_t>(n_owned + G.lower + (c - G.row_end));
+			val[p] = v;
+			++p;
+		}
+	});
+}
+
+__global__ void iota_kernel(int32_t * p, long long n) {
+	const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i < n)
+		p[i] = static_cast<int32_t>(i);
+}
+
+__global__ void colmap_kernel(grid_desc G, long long * colmap) {
+	const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i < G.lower)
+		colmap[i] = G.row_begin - G.lower + i;
+	else if (i < G.lower + G.upper)
+		colmap[i] = G.row_end + (i - G.lower);
+}
+
+struct nonzero_flag {
+	__host__ __device__ bool operator()(int v) const { return v > 0; }
+};
+
+struct to_i64 {
+	__host__ __device__ long long operator()(int v) const { return v; }
+};
+
+template<class In, class Out>
+static void exclusive_scan(fsb_ctx_s * c, In in, Out out, long long n) {
+	void * tmp = nullptr;
+	size_t bytes = 0;
+	FSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, n, c->stream));
+	FSB_CUDA(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
+	FSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, n, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(tmp);
+}
+
+} // namespace fsb
+
+fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t nx, int64_t ny, int64_t nz,
+                                              double diag_shift, double scale) {
+	flush(c);
+	FSB_REQUIRE(kind == 5 || kind == 7 || kind == 27, "stencil: kind must be 5, 7 or 27");
+	FSB_REQUIRE(nx > 0 && ny > 0 && nz > 0, "stencil: empty grid");
+	FSB_REQUIRE(kind != 5 || nz == 1, "stencil: the 5-point operator is 2-D (nz == 1)");
+	const int P = c->nranks, me = c->rank;
+	const int64_t plane = nx * ny;
+	FSB_REQUIRE(P == 1 || nz % P == 0, "stencil: nz must be divisible by the number of ranks (plane-aligned slabs)");
+	auto * A = new fsb_parcsr_s;
+	A->ctx = c;
+	A->n_global = plane * nz;
+	A->row_part.resize(P + 1);
+	for (int q = 0; q <= P; ++q)
+		A->row_part[q] = plane * (nz / P) * q;
+	A->row_begin = A->row_part[me];
+	const int64_t row_end = A->row_part[me + 1];
+	A->n_local = row_end - A->row_begin;
+	FSB_REQUIRE(A->n_local + 2 * plane < (1LL << 31), "stencil: local column space exceeds int32");
+
+	grid_desc G{};
+	G.nx = nx;
+	G.ny = ny;
+	G.nz = nz;
+	G.row_begin = A->row_begin;
+	G.row_end = row_end;
+	G.lower = (P > 1 && me > 0) ? plane : 0;
+	G.upper = (P > 1 && me < P - 1) ? plane : 0;
+	G.kind = kind;
+	const double center = kind == 27 ? 26.0 : (kind == 7 ? 6.0 : 4.0);
+	G.diag = (center + diag_shift) * scale;
+	G.off = -1.0 * scale;
+	A->n_ghost = G.lower + G.upper;
+
+	const long long n = A->n_local;
+	const int T = 256;
+	const int grid = static_cast<int>((n + T - 1) / T);
+	int * cnt_d = dev_alloc<int>(n + 1);
+	int * cnt_o = dev_alloc<int>(n + 1);
+	FSB_CUDA(cudaMemsetAsync(cnt_d + n, 0, sizeof(int), c->stream));
+	FSB_CUDA(cudaMemsetAsync(cnt_o + n, 0, sizeof(int), c->stream));
+	stencil_count_kernel<<<grid, T, 0, c->stream>>>(G, cnt_d, cnt_o);
+	FSB_CUDA(cudaGetLastError());
+
+	// ---- diag block
+	csr_block & D = A->diag;
+	D.n_rows = n;
+	const int width = kind;
+	// nnz upper bound decides the offset width before the scan
+	D.wide = static_cast<long long>(width) * n >= (1LL << 31) - 16;
+	long long nnz_d = 0;
+	if (D.wide) {
+		long long * rp = dev_alloc<long long>(n + 1);
+		exclusive_scan(c, thrust::make_transform_iterator(cnt_d, to_i64{}), rp, n + 1);
+		FSB_CUDA(cudaMemcpy(&nnz_d, rp + n, sizeof(long long), cudaMemcpyDeviceToHost));
+		D.rowptr = rp;
+	}
+	else {
+		int * rp = dev_alloc<int>(n + 1);
+		exclusive_scan(c, cnt_d, rp, n + 1);
+		int last = 0;
+		FSB_CUDA(cudaMemcpy(&last, rp + n, sizeof(int), cudaMemcpyDeviceToHost));
+		nnz_d = last;
+		D.rowptr = rp;
+	}
+	D.nnz = nnz_d;
+	D.col = dev_alloc<int32_t>(nnz_d + 16);
+	D.val = dev_alloc<double>(nnz_d + 16);
+	if (D.wide)
+		stencil_fill_diag_kernel<long long><<<grid, T, 0, c->stream>>>(G, static_cast<long long *>(D.rowptr), D.col, D.val);
+	else
+		stencil_fill_diag_kernel<int><<<grid, T, 0, c->stream>>>(G, static_cast<int *>(D.rowptr), D.col, D.val);
+	FSB_CUDA(cudaGetLastError());
+	D.max_blk_nnz = width; // row width bound for the uniform block builder
+	build_blocks(c, D, nullptr);
+
+	// ---- offd block over the rows that touch a neighbouring slab
+	if (A->n_ghost > 0) {
+		csr_block & O = A->offd;
+		int32_t * iota = dev_alloc<int32_t>(n);
+		iota_kernel<<<grid, T, 0, c->stream>>>(iota, n);
+		int32_t * rows = dev_alloc<int32_t>(n);
+		int * cnt_c = dev_alloc<int>(n + 1);
+		int * d_num = dev_alloc<int>(1);
+		void * tmp = nullptr;
+		size_t bytes = 0, bytes2 = 0;
+		auto flags = thrust::make_transform_iterator(cnt_o, nonzero_flag{});
+		FSB_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, iota, flags, rows, d_num, static_cast<int>(n), c->stream));
+		FSB_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes2, cnt_o, flags, cnt_c, d_num, static_cast<int>(n), c->stream));
+		bytes = std::max(bytes, bytes2);
+		FSB_CUDA(cudaMalloc(&tmp, std::max<size_t>(bytes, 16)));
+		FSB_CUDA(cub::DeviceSelect::Flagged(tmp, bytes, iota, flags, rows, d_num, static_cast<int>(n), c->stream));
+		FSB_CUDA(cub::DeviceSelect::Flagged(tmp, bytes, cnt_o, flags, cnt_c, d_num, static_cast<int>(n), c->stream));
+		int n_rows = 0;
+		FSB_CUDA(cudaMemcpyAsync(&n_rows, d_num, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		FSB_CUDA(cudaStreamSynchronize(c->stream));
+		cudaFree(tmp);
+		cudaFree(iota);
+		cudaFree(d_num);
+		FSB_CUDA(cudaMemsetAsync(cnt_c + n_rows, 0, sizeof(int), c->stream));
+		int * rp = dev_alloc<int>(n_rows + 1);
+		exclusive_scan(c, cnt_c, rp, static_cast<long long>(n_rows) + 1);
+		int nnz_o = 0;
+		FSB_CUDA(cudaMemcpy(&nnz_o, rp + n_rows, sizeof(int), cudaMemcpyDeviceToHost));
+		cudaFree(cnt_c);
+		O.n_rows = n_rows;
+		O.nnz = nnz_o;
+		O.wide = false;
+		O.rowptr = rp;
+		O.row_ids = rows;
+		O.col = dev_alloc<int32_t>(nnz_o + 16);
+		O.val = dev_alloc<double>(nnz_o + 16);
+		if (n_rows > 0) {
+			stencil_fill_offd_kernel<<<(n_rows + T - 1) / T, T, 0, c->stream>>>(G, rows, n_rows, rp, O.col, O.val);
+			FSB_CUDA(cudaGetLastError());
+			const int per_side = kind == 27 ? 9 : 1;
+			O.max_blk_nnz = (A->n_local == plane && G.lower && G.upper) ? 2 * per_side : per_side;
+			build_blocks(c, O, nullptr);
+		}
+		// colmap + analytic halo plan: whole boundary planes, contiguous on both sides
+		A->d_colmap = dev_alloc<int64_t>(A->n_ghost);
+		colmap_kernel<<<static_cast<int>((A->n_ghost + T - 1) / T), T, 0, c->stream>>>(
+			G, reinterpret_cast<long long *>(A->d_colmap));
+		A->colmap.resize(A->n_ghost);
+		FSB_CUDA(cudaMemcpyAsync(A->colmap.data(), A->d_colmap, A->n_ghost * sizeof(int64_t), cudaMemcpyDeviceToHost,
+		                         c->stream));
+		if (G.lower) {
+			neighbour nb{};
+			nb.rank = me - 1;
+			nb.send_count = nb.recv_count = plane;
+			nb.recv_offset = 0;
+			nb.contiguous_start = 0;
+			A->nbrs.push_back(nb);
+		}
+		if (G.upper) {
+			neighbour nb{};
+			nb.rank = me + 1;
+			nb.send_count = nb.recv_count = plane;
+			nb.recv_offset = G.lower;
+			nb.contiguous_start = A->n_local - plane;
+			A->nbrs.push_back(nb);
+		}
+	}
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(cnt_d);
+	cudaFree(cnt_o);
+	return A;
+}
+
+void fsb_parcsr_destroy_impl(fsb_parcsr_s * A) {
+	flush(A->ctx);
+	cudaStreamSynchronize(A->ctx->stream);
+	cudaStreamSynchronize(A->ctx->comm_stream);
+	free_block(A->diag);
+	free_block(A->offd);
+	cudaFree(A->d_colmap);
+	cudaFree(A->d_send_idx);
+	cudaFree(A->d_send_buf);
+	cudaFree(A->d_dinv);
+	delete A;
+}
+
+// ------------------------------------------------------------------ Jacobi
+
+namespace fsb {
+
+// d[r] = 1 / a_rr; rows without a stored diagonal get 1/0 = inf like the reference's `1. / diag`
+template<class OffT>
+__global__ void extract_dinv_kernel(const OffT * __restrict__ rowptr, const int32_t * __restrict__ col,
+                                    const double * __restrict__ val, double * __restrict__ d, long long n) {
+	const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (r >= n)
+		return;
+	double a = 0.0;
+	for (long long p = static_cast<long long>(rowptr[r]); p < static_cast<long long>(rowptr[r + 1]); ++p)
+		if (col[p] == r)
+			a = val[p];
+	d[r] = __ddiv_rn(1.0, a);
+}
+
+void extract_dinv(fsb_parcsr_s * A, double * d) {
+	fsb_ctx_s * c = A->ctx;
+	const long long n = A->n_local;
+	if (n == 0)
+		return;
+	const int T = 256, grid = static_cast<int>((n + T - 1) / T);
+	if (A->diag.wide)
+		extract_dinv_kernel<long long>
+			<<<grid, T, 0, c->stream>>>(static_cast<const long long *>(A->diag.rowptr), A->diag.col, A->diag.val, d, n);
+	else
+		extract_dinv_kernel<int><<<grid, T, 0, c->stream>>>(static_cast<const int *>(A->diag.rowptr), A->diag.col,
+		                                                    A->diag.val, d, n);
+	FSB_CUDA(cudaGetLastError());
+	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+}
+
+// x = omega * dinv * (b - (x - a_rr tmp)) + (1 - omega) * tmp, where on entry x = A tmp (full row sums).
+// Removing the diagonal term afterwards keeps one SpMV kernel for both uses; the reference sums the
+// off-diagonal terms directly (mg/jacobi.hh:73-89), the difference is rounding-level.
+__global__ void jacobi_finish_kernel(double * __restrict__ x, const double * __restrict__ b,
+                                     const double * __restrict__ tmp, const double * __restrict__ dinv, double omega,
+                                     long long n) {
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride) {
+		const double di = dinv[r], t = tmp[r];
+		const double lpu = x[r] - t / di; // (L+U) tmp
+		x[r] = omega * di * (b[r] - lpu) + (1.0 - omega) * t;
+	}
+}
+
+} // namespace fsb
+
+void fsb_parcsr_jacobi_relax_impl(fsb_parcsr_s * A, double omega, int64_t nrelax, fsb_vec_s * b, fsb_vec_s * x,
+                                  fsb_vec_s * tmp) {
+	fsb_ctx_s * c = A->ctx;
+	flush(c);
+	FSB_REQUIRE(x != tmp && b != tmp && x != b, "jacobi_relax: b, x, tmp must be distinct");
+	FSB_REQUIRE(x->n_owned == A->n_local && b->n_owned == A->n_local && tmp->n_owned == A->n_local &&
+	                x->n_ghost >= A->n_ghost && tmp->n_ghost >= A->n_ghost,
+	            "jacobi_relax: vectors do not match the matrix");
+	if (!A->d_dinv) {
+		A->d_dinv = dev_alloc<double>(A->n_local);
+		extract_dinv(A, A->d_dinv);
+	}
+	const bool multi = c->nranks > 1 && !A->nbrs.empty();
+	for (int64_t s = 0; s < nrelax; ++s) {
+		// tmp = x over the whole span incl. ghosts (mg/jacobi.hh:63): refresh ghosts of x, then copy
+		if (multi && !x->halo_valid) {
+			halo_exchange_async(A, x);
+			FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+		}
+		FSB_CUDA(cudaMemcpyAsync(tmp->d, x->d, (x->n_owned + A->n_ghost) * sizeof(double), cudaMemcpyDeviceToDevice,
+		                         c->stream));
+		tmp->halo_valid = true;
+		launch_spmv(c, A->diag, tmp->d, x->d, false, nullptr, nullptr, 0, c->stream);
+		if (A->offd.n_blk > 0)
+			launch_spmv(c, A->offd, tmp->d, x->d, true, nullptr, nullptr, 0, c->stream);
+		const long long n = A->n_local;
+		if (n > 0) {
+			const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, SM_COUNT * 8));
+			jacobi_finish_kernel<<<grid, 256, 0, c->stream>>>(x->d, b->d, tmp->d, A->d_dinv, omega, n);
+			FSB_CUDA(cudaGetLastError());
+			c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+		}
+		x->halo_valid = false;
+	}
+}

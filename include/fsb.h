@@ -1,0 +1,203 @@
+/*
+ * fsb.h -- C ABI of the B200-native flecsolve solve-loop back end ("fsb").
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json:
+ * parallel CSR SpMV, vector operations, global reductions, point-Jacobi.
+ * Every entry point is plain C (opaque handles, pointers, sizes, doubles);
+ * no C++/torch types cross it.  The C++ header layer under
+ * flecsolve_b200/include/flecsolve/ is the only intended caller besides
+ * tests and bench.py (through ctypes).
+ *
+ * Each group cites the reference interface it replaces (paths relative to the
+ * flecsolve source tree).
+ *
+ * Conventions
+ *  - every function returns 0 (FSB_OK) or a positive fsb_status; the message is
+ *    available from fsb_last_error() (thread local).
+ *  - one host thread drives one context; handles are not thread safe.
+ *  - all device work of a context is ordered on the context's stream, in the
+ *    order the calls were made.  Calls may be *deferred*: element-wise
+ *    operations, reductions and SpMV are queued and launched as fused kernels
+ *    when a result is needed (fsb_red_get / fsb_vec_download / fsb_ctx_sync /
+ *    fsb_ctx_flush).  Deferral never changes results element-wise: the fused
+ *    kernels evaluate the queued statements in program order per element.
+ *  - there is no CPU fallback.  Without a usable CUDA device fsb_ctx_create
+ *    fails with FSB_ERR_NOGPU.
+ */
+#ifndef FSB_H
+#define FSB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fsb_ctx_s * fsb_ctx_t;
+typedef struct fsb_vec_s * fsb_vec_t;
+typedef struct fsb_parcsr_s * fsb_parcsr_t;
+typedef int64_t fsb_token_t; /* handle of a pending reduction result */
+
+enum fsb_status {
+	FSB_OK = 0,
+	FSB_ERR_CUDA = 1,
+	FSB_ERR_ARG = 2,
+	FSB_ERR_NCCL = 3,
+	FSB_ERR_NOGPU = 4,
+	FSB_ERR_STATE = 5
+};
+
+enum fsb_option {
+	FSB_OPT_FUSION = 0, /* 1 (default): fuse queued statements; 0: one kernel per call */
+	FSB_OPT_SPMV_ROWS_PER_CTA = 1, /* tuning knob for matrices created afterwards */
+	FSB_OPT_SPMV_THREADS = 2,
+	FSB_OPT_TRACE = 3 /* 1: print every launched group signature to stderr */
+};
+
+enum fsb_stat {
+	FSB_STAT_KERNEL_LAUNCHES = 0, /* kernels of this library launched so far */
+	FSB_STAT_FUSED_STATEMENTS = 1, /* statements that shared a launch with another */
+	FSB_STAT_HALO_EXCHANGES = 2,
+	FSB_STAT_ALLREDUCES = 3,
+	FSB_STAT_HOST_SYNCS = 4,
+	FSB_STAT_UNMATCHED_GROUPS = 5 /* groups that had to be split (no fused kernel) */
+};
+
+const char * fsb_last_error(void);
+int fsb_version(void);
+/* number of visible CUDA devices (0 when none / no driver) */
+int fsb_device_count(void);
+
+/* ---- context -----------------------------------------------------------
+ * Replaces the FleCSI runtime objects the reference path leans on:
+ * flecsi::scheduler (task issue order), one colour per process
+ * (matrices/parcsr.hh:112-119) and the MPI communicator in topo::csr::init
+ * (topo/csr.hh:474-480).  rank/nranks = this process' colour / colour count.
+ * nccl_unique_id: 128 bytes produced by fsb_nccl_unique_id() on rank 0 and
+ * broadcast by the caller (any transport); NULL when nranks == 1.           */
+int fsb_nccl_unique_id(void * out128);
+int fsb_ctx_create(int device, int rank, int nranks, const void * nccl_unique_id, fsb_ctx_t * out);
+int fsb_ctx_destroy(fsb_ctx_t ctx);
+int fsb_ctx_flush(fsb_ctx_t ctx); /* launch everything queued; no host wait */
+int fsb_ctx_sync(fsb_ctx_t ctx); /* flush + wait for the stream */
+void * fsb_ctx_stream(fsb_ctx_t ctx); /* cudaStream_t all kernels are launched on */
+int fsb_ctx_rank(fsb_ctx_t ctx);
+int fsb_ctx_nranks(fsb_ctx_t ctx);
+int fsb_ctx_set_option(fsb_ctx_t ctx, int option, int64_t value);
+int fsb_ctx_get_stat(fsb_ctx_t ctx, int stat, int64_t * out);
+int fsb_ctx_reset_stats(fsb_ctx_t ctx);
+/* overwrite >= bytes of scratch so the L2 holds none of the caller's data */
+int fsb_ctx_flush_l2(fsb_ctx_t ctx);
+
+/* ---- vectors -----------------------------------------------------------
+ * A vector is the device image of one field on the reference's `cols' index
+ * space: n_owned entries followed by n_ghost ghost entries
+ * (topo/csr.hh:420-431, 524-526; vectors/data/topo_view.hh:24-71).          */
+int fsb_vec_create(fsb_ctx_t ctx, int64_t n_owned, int64_t n_ghost, fsb_vec_t * out);
+/* wrap caller-owned device memory of (n_owned + n_ghost) doubles, 16-byte aligned */
+int fsb_vec_wrap(fsb_ctx_t ctx, double * device_ptr, int64_t n_owned, int64_t n_ghost, fsb_vec_t * out);
+int fsb_vec_destroy(fsb_vec_t v);
+int64_t fsb_vec_local_size(fsb_vec_t v); /* vec::ops::topo_view::local_size, operations/topo_view.hh:276-280 */
+int64_t fsb_vec_ghost_size(fsb_vec_t v);
+double * fsb_vec_device_ptr(fsb_vec_t v);
+/* host <-> device copies of owned entries [offset, offset+n) (flushes first) */
+int fsb_vec_upload(fsb_vec_t v, const double * host, int64_t n, int64_t offset);
+int fsb_vec_download(fsb_vec_t v, double * host, int64_t n, int64_t offset);
+
+/* element-wise operations over the owned entries; any operands may alias.
+ * Reference: vec::ops::topo_view dispatch (vectors/operations/topo_view.hh:43-210)
+ * and the task bodies (vectors/operations/topo_tasks.hh:68-214).  The `_self'
+ * alias variants of the reference are all covered by the alias-safe kernels.
+ * Arithmetic is evaluated exactly as written there: products and sums are
+ * rounded separately (no FMA contraction), so results are bit-identical to a
+ * -ffp-contract=off x86-64 build of the reference.                         */
+int fsb_vec_copy(fsb_vec_t z, fsb_vec_t x); /* z = x               (copy, topo_tasks.hh:80-84)  */
+int fsb_vec_set(fsb_vec_t z, double a); /* z = a               (set_to_scalar, :68-70)      */
+int fsb_vec_scale(fsb_vec_t z, double a, fsb_vec_t x); /* z = x * a  (scale/scale_self, :72-78)  */
+int fsb_vec_add(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y); /* z = x + y           (:86-92)   */
+int fsb_vec_sub(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y); /* z = x - y           (:94-108)  */
+int fsb_vec_mul(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y); /* z = x * y           (:110-118) */
+int fsb_vec_div(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y); /* z = x / y           (:120-134) */
+int fsb_vec_recip(fsb_vec_t z, fsb_vec_t x); /* z = 1 / x                     (:136-142) */
+int fsb_vec_linear_sum(fsb_vec_t z, double a, fsb_vec_t x, double b, fsb_vec_t y); /* z = a*x + b*y (:144-172) */
+int fsb_vec_axpy(fsb_vec_t z, double a, fsb_vec_t x, fsb_vec_t y); /* z = a*x + y  (:174-191) */
+int fsb_vec_axpby(fsb_vec_t z, double a, double b, fsb_vec_t x); /* z = a*x + b*z (:193-198) */
+int fsb_vec_abs(fsb_vec_t z, fsb_vec_t x); /* z = |x|                       (:200-206) */
+int fsb_vec_add_scalar(fsb_vec_t z, fsb_vec_t x, double a); /* z = x + a         (:208-214) */
+/* mt19937(seed) + uniform_real_distribution(0,1) drawn sequentially over the
+ * owned entries on the host, same seed on every rank (topo_tasks.hh:305-314) */
+int fsb_vec_set_random(fsb_vec_t z, unsigned seed);
+/* text dump `<prefix>-<rank>', one value per line (topo_tasks.hh:316-323) */
+int fsb_vec_dump(fsb_vec_t x, const char * prefix);
+
+/* global reductions.  Each call queues the reduction and returns a token;
+ * fsb_red_get blocks until the (all-rank) value is on the host -- the
+ * counterpart of flecsi::future::get() on scheduler().reduce<>()
+ * (vectors/operations/topo_view.hh:212-274; bodies topo_tasks.hh:52-66,216-297).
+ * A token may be read more than once until FSB_RED_RING newer tokens exist.   */
+#define FSB_RED_RING 256
+int fsb_vec_dot(fsb_vec_t x, fsb_vec_t y, fsb_token_t * tok); /* sum x*y                       */
+int fsb_vec_sumsq(fsb_vec_t x, fsb_token_t * tok); /* sum x*x  (l2_norm_local; sqrt at get in C++) */
+int fsb_vec_asum(fsb_vec_t x, fsb_token_t * tok); /* sum |x|  (l1_norm_local)                 */
+int fsb_vec_powsum(fsb_vec_t x, int p, fsb_token_t * tok); /* sum pow(x,p) (lp_norm_local)    */
+int fsb_vec_amax(fsb_vec_t x, fsb_token_t * tok); /* max |x|  (inf_norm_local)                */
+int fsb_vec_min(fsb_vec_t x, fsb_token_t * tok); /* min x    (local_min)                      */
+int fsb_vec_max(fsb_vec_t x, fsb_token_t * tok); /* max x    (local_max)                      */
+int fsb_vec_global_size(fsb_vec_t x, int64_t * out); /* sum of local sizes (topo_view.hh:271-274) */
+int fsb_red_get(fsb_ctx_t ctx, fsb_token_t tok, double * out);
+int fsb_red_wait(fsb_ctx_t ctx, fsb_token_t tok);
+
+/* ---- parallel CSR matrix ------------------------------------------------
+ * Device image of mat::parcsr (matrices/parcsr.hh:101-177) on the topology
+ * topo::csr (topo/csr.hh): per rank a `diag' CSR over owned columns and an
+ * `offd' CSR whose column indices are n_owned + (rank of the global column id
+ * in the sorted unique ghost list), plus colmap[ghost] = global id
+ * (topo/csr.hh:482-543 color(), :553-618 init_mats()).
+ *
+ * fsb_parcsr_create does color() + init_mats() + the ghost copy plan
+ * (topo/csr.hh:116-187, 277-304) from this rank's rows in global numbering:
+ *   row_part[nranks+1]  row/column partition offsets (same for rows and
+ *                       columns, as set_block_map gives; matrices/parcsr.hh:170-172)
+ *   rowptr[n_local+1], col[nnz] (global column ids, int64), val[nnz] on the host.
+ * Collective over all ranks of the context (exchanges send lists).          */
+int fsb_parcsr_create(fsb_ctx_t ctx,
+                      int64_t n_global,
+                      const int64_t * row_part,
+                      const int64_t * rowptr,
+                      const int64_t * col,
+                      const double * val,
+                      fsb_parcsr_t * out);
+/* synthetic stencil operators generated on the device:
+ * kind 7: diag 6 / off -1;  kind 27: diag 26 / off -1;  kind 5: 2-D (nz==1) diag 4 / off -1.
+ * Dirichlet truncation, columns ascending, rows g = i + nx*(j + ny*k) split into
+ * equal contiguous blocks (z-slabs; requires nz % nranks == 0 when nranks > 1).
+ * diag_shift is added to the diagonal, scale multiplies every entry.        */
+int fsb_parcsr_create_stencil(fsb_ctx_t ctx, int kind, int64_t nx, int64_t ny, int64_t nz,
+                              double diag_shift, double scale, fsb_parcsr_t * out);
+int fsb_parcsr_destroy(fsb_parcsr_t A);
+int64_t fsb_parcsr_local_rows(fsb_parcsr_t A);
+int64_t fsb_parcsr_global_rows(fsb_parcsr_t A);
+int64_t fsb_parcsr_num_ghosts(fsb_parcsr_t A);
+int64_t fsb_parcsr_row_begin(fsb_parcsr_t A);
+int64_t fsb_parcsr_local_nnz(fsb_parcsr_t A, int which /* 0 diag, 1 offd */);
+/* copy the split representation back to the host (tests: compare with the
+ * oracle's color()/init_mats() restatement).  Any pointer may be NULL.      */
+int fsb_parcsr_download(fsb_parcsr_t A, int which, int64_t * rowptr, int32_t * col, double * val);
+int fsb_parcsr_download_colmap(fsb_parcsr_t A, int64_t * colmap);
+/* y = A x: ghost exchange of x (if stale) overlapped with the diag block, then
+ * the offd block accumulates: y = diag*x_owned + offd*x   (matrices/parcsr.hh:61-91,
+ * matrices/seq.hh:178-194).  Row sums are accumulated in column-index order.  */
+int fsb_parcsr_spmv(fsb_parcsr_t A, fsb_vec_t x, fsb_vec_t y);
+/* d = 1 / diag(A) over owned rows: the vector the reference's Dinv() operator
+ * holds as a diagonal CSR (util/test/mesh.hh:123-140)                        */
+int fsb_parcsr_extract_dinv(fsb_parcsr_t A, fsb_vec_t d);
+/* weighted point-Jacobi sweeps, mg::bound_jacobi::relax (solvers/mg/jacobi.hh:44-93):
+ * nrelax times: tmp = x (incl. ghosts); x[r] = omega/a_rr * (b[r] - sum_{c!=r} a_rc tmp[c]) + (1-omega) tmp[r] */
+int fsb_parcsr_jacobi_relax(fsb_parcsr_t A, double omega, int64_t nrelax, fsb_vec_t b, fsb_vec_t x, fsb_vec_t tmp);
+/* explicit ghost update of x (the copy plan of topo/csr.hh:237-245); normally implicit in spmv */
+int fsb_parcsr_halo_exchange(fsb_parcsr_t A, fsb_vec_t x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,850 @@
+// ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the flecsolve solve-loop path (reference: lanl/flecsolve, paths below are
+// relative to its source tree).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library; nothing under flecsolve_b200/
+// does.  It keeps the reference's data structures and pass structure on purpose:
+//   * 64-bit (std::size_t) row offsets and column indices     matrices/seq.hh:202, parcsr.hh:100
+//   * per colour a `diag' and an `offd' CSR, ghosts numbered after the owned columns in sorted
+//     global-id order                                           topo/csr.hh:482-618
+//   * SpMV = tmp <- offd*x ; y <- diag*x ; y <- y + tmp (3 passes)   matrices/parcsr.hh:61-91
+//   * one pass per vector operation                             vectors/operations/topo_tasks.hh
+//   * three blocking reductions per CG iteration                solvers/cg.hh:98,111,127
+// "Colours" (the reference's MPI ranks) are simulated inside one process; with OpenMP each colour's
+// loops run on its own thread (threads stand in for ranks), which is the CPU timing baseline.
+//
+// PARITY PINNING: the reference itself cannot be built here (needs FleCSI, MPI, Boost; see
+// DESIGN.md).  This file is pinned against (a) the closed-form vector-operation cases of
+// vectors/test/flecsi_vector.cc:99-307 (tests/test_oracle.py), (b) scipy.sparse as an independent
+// SpMV implementation, and (c) where oracle/_ref could be built from the reference's own headers
+// with stub FleCSI headers (oracle/refcheck/), iteration counts of the reference's solver templates.
+//
+// Compile with -ffp-contract=off: the reference's default x86-64 build has no FMA contraction.
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <random>
+#include <unordered_map>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+using idx = std::size_t;
+
+struct Csr {
+	std::vector<idx> rowptr, col;
+	std::vector<double> val;
+	idx rows() const { return rowptr.empty() ? 0 : rowptr.size() - 1; }
+};
+
+// matrices/seq.hh:178-194 compressed_ops::spmv, row-major branch
+template<class X>
+void csr_spmv(const Csr & A, X && x, double * y) {
+	const idx * rowptr = A.rowptr.data();
+	const idx * colind = A.col.data();
+	const double * values = A.val.data();
+	for (idx i = 0; i < A.rows(); ++i) {
+		y[i] = 0.;
+		for (idx off = rowptr[i]; off < rowptr[i + 1]; ++off)
+			y[i] += values[off] * x(colind[off]);
+	}
+}
+
+struct Colour {
+	idx row_beg = 0, row_end = 0; // owned rows == owned columns (row_part == col_part, parcsr.hh:170-172)
+	Csr diag, offd;
+	std::vector<idx> colmap; // ghost i -> global column id (topo/csr.hh:573-577)
+	idx owned() const { return row_end - row_beg; }
+};
+
+struct ParCsr {
+	idx n = 0;
+	int P = 1;
+	std::vector<idx> part; // P+1 offsets
+	std::vector<Colour> c;
+	std::vector<double> tmp; // spmv_tmp field (parcsr.hh:37,46-48), global layout
+};
+
+// flecsi::util::equal_map(n, P): contiguous blocks, the first n % P bins hold one extra element.
+std::vector<idx> equal_map(idx n, int P) {
+	std::vector<idx> part(P + 1, 0);
+	const idx q = n / P, r = n % P;
+	for (int p = 0; p < P; ++p)
+		part[p + 1] = part[p] + q + (static_cast<idx>(p) < r ? 1 : 0);
+	return part;
+}
+
+[[maybe_unused]] int owner_of(const std::vector<idx> & part, idx g) {
+	return static_cast<int>(std::upper_bound(part.begin(), part.end(), g) - part.begin()) - 1;
+}
+
+// topo::csr::color() (topo/csr.hh:482-543) + init_mats() (:553-618) for every colour
+ParCsr * build(idx n, int P, const idx * part_in, const int64_t * rowptr, const int64_t * col, const double * val) {
+	auto * M = new ParCsr;
+	M->n = n;
+	M->P = P;
+	M->part = part_in ? std::vector<idx>(part_in, part_in + P + 1) : equal_map(n, P);
+	M->c.resize(P);
+	M->tmp.assign(n, 0.0);
+#pragma omp parallel for schedule(static, 1)
+	for (int p = 0; p < P; ++p) {
+		Colour & C = M->c[p];
+		C.row_beg = M->part[p];
+		C.row_end = M->part[p + 1];
+		// ghosts: force_unique of the off-colour column ids (:506-524)
+		std::vector<idx> ghosts;
+		for (idx r = C.row_beg; r < C.row_end; ++r)
+			for (int64_t off = rowptr[r]; off < rowptr[r + 1]; ++off) {
+				const idx cid = static_cast<idx>(col[off]);
+				if (cid < C.row_beg || cid >= C.row_end)
+					ghosts.push_back(cid);
+			}
+		std::sort(ghosts.begin(), ghosts.end());
+		ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+		C.colmap = ghosts;
+		std::unordered_map<idx, idx> rcolmap; // reverse map (:573-577)
+		for (idx i = 0; i < ghosts.size(); ++i)
+			rcolmap[ghosts[i]] = i + C.owned();
+		C.diag.rowptr.assign(C.owned() + 1, 0);
+		C.offd.rowptr.assign(C.owned() + 1, 0);
+		for (idx r = 0; r < C.owned(); ++r) {
+			for (int64_t off = rowptr[C.row_beg + r]; off < rowptr[C.row_beg + r + 1]; ++off) {
+				const idx cid = static_cast<idx>(col[off]);
+				if (cid >= C.row_beg && cid < C.row_end) {
+					C.diag.col.push_back(cid - C.row_beg);
+					C.diag.val.push_back(val[off]);
+				}
+				else {
+					C.offd.col.push_back(rcolmap.at(cid));
+					C.offd.val.push_back(val[off]);
+				}
+			}
+			C.diag.rowptr[r + 1] = C.diag.col.size();
+			C.offd.rowptr[r + 1] = C.offd.col.size();
+		}
+	}
+	return M;
+}
+
+// matrices/parcsr.hh:61-91: spmv_remote, spmv_local, y.add(y, tmp).  x, y: global layout.
+// The ghost copy (topo/csr.hh:237-245) delivers x[colmap[g]] into ghost slot g; reading the global
+// array through colmap yields the same values.
+void par_spmv(ParCsr & M, const double * x, double * y) {
+	double * tmp = M.tmp.data();
+#pragma omp parallel for schedule(static, 1)
+	for (int p = 0; p < M.P; ++p) {
+		Colour & C = M.c[p];
+		const idx no = C.owned();
+		const double * xo = x + C.row_beg;
+		const idx * cm = C.colmap.data();
+		csr_spmv(C.offd, [=](idx c) { return c < no ? xo[c] : x[cm[c - no]]; }, tmp + C.row_beg); // spmv_remote
+		csr_spmv(C.diag, [=](idx c) { return xo[c]; }, y + C.row_beg); // spmv_local
+	}
+	// y.add(y, tmpv) -> add_self (vectors/operations/topo_view.hh:78-91, topo_tasks.hh:86-88)
+#pragma omp parallel for schedule(static, 1)
+	for (int p = 0; p < M.P; ++p)
+		for (idx i = M.c[p].row_beg; i < M.c[p].row_end; ++i)
+			y[i] = y[i] + tmp[i];
+}
+
+// ---- vector operations: vectors/operations/topo_tasks.hh, one pass each, colour-parallel ----
+struct Vops {
+	const ParCsr * M;
+	template<class F>
+	void each(F && f) const {
+#pragma omp parallel for schedule(static, 1)
+		for (int p = 0; p < M->P; ++p)
+			for (idx i = M->c[p].row_beg; i < M->c[p].row_end; ++i)
+				f(i);
+	}
+	// scheduler().reduce<task, fold>: per-colour partial, then fold over colours in colour order
+	template<class F>
+	double sum(F && f) const {
+		std::vector<double> part(M->P, 0.0);
+#pragma omp parallel for schedule(static, 1)
+		for (int p = 0; p < M->P; ++p) {
+			double s = 0.0;
+			for (idx i = M->c[p].row_beg; i < M->c[p].row_end; ++i)
+				s += f(i);
+			part[p] = s;
+		}
+		double s = 0.0;
+		for (double v : part)
+			s += v;
+		return s;
+	}
+	void copy(double * z, const double * x) const { each([=](idx i) { z[i] = x[i]; }); } // :80-84
+	void set(double * z, double a) const { each([=](idx i) { z[i] = a; }); } // :68-70
+	void scale(double * z, double a) const { each([=](idx i) { z[i] *= a; }); } // :72-74
+	void scale(double * z, double a, const double * x) const { each([=](idx i) { z[i] = x[i] * a; }); } // :76-78
+	// axpy family (:174-191): z = a*x + y with the alias variants folded into pointer equality
+	void axpy(double * z, double a, const double * x, const double * y) const {
+		each([=](idx i) { z[i] = a * x[i] + y[i]; });
+	}
+	void subtract(double * z, const double * x, const double * y) const { each([=](idx i) { z[i] = x[i] - y[i]; }); }
+	void multiply(double * z, const double * x, const double * y) const { each([=](idx i) { z[i] = x[i] * y[i]; }); }
+	double dot(const double * x, const double * y) const { // scalar_prod :52-66
+		return sum([=](idx i) { return x[i] * y[i]; });
+	}
+	double l2norm(const double * x) const { return std::sqrt(dot(x, x)); } // :237-243 + topo_view.hh:249-251
+};
+
+// ---- operators -----------------------------------------------------------------------------
+struct System {
+	ParCsr * M;
+	const double * dinv; // nullptr: identity preconditioner (operators/shell.hh:83-95: y.copy(x))
+	Vops v() const { return Vops{M}; }
+	void A(const double * x, double * y) const { par_spmv(*M, x, y); }
+	// Dinv(): diagonal CSR applied by SpMV (util/test/mesh.hh:107-140): y = 0 + x*dinv
+	void P(const double * x, double * y) const {
+		if (dinv)
+			v().multiply(y, x, dinv);
+		else
+			v().copy(y, x);
+	}
+	// op::core::residual (operators/core.hh:134-142): apply(x, r); r = b - r
+	void residual(const double * b, const double * x, double * r) const {
+		A(x, r);
+		v().subtract(r, b, r);
+	}
+};
+
+enum stop_reason { converged_atol, converged_rtol, converged_user, diverged_dtol, diverged_iters, diverged_breakdown, unknown };
+
+struct Info { // solvers/solver_settings.hh:61-85 (norm fields are float there)
+	int status = unknown, iters = 0, restarts = 0;
+	float res_norm_initial = 0, res_norm_final = 0, sol_norm_initial = 0, sol_norm_final = 0, rhs_norm = 0;
+};
+
+struct History {
+	double * buf;
+	int cap, n = 0;
+	void push(double r) {
+		if (buf && n < cap)
+			buf[n] = r;
+		++n;
+	}
+};
+
+// solvers/cg.hh:44-139
+Info cg(const System & S, int maxiter, float rtol, bool use_zero_guess, const double * b, double * x, History & H) {
+	Info info;
+	const Vops V = S.v();
+	const idx n = S.M->n;
+	std::vector<double> rv(n), zv(n), pv(n), wv(n);
+	double *r = rv.data(), *z = zv.data(), *p = pv.data(), *w = wv.data();
+	double b_norm = V.l2norm(b);
+	if (b_norm == 0.0)
+		b_norm = 1.0;
+	const double terminate_tol = rtol * b_norm;
+	info.rhs_norm = b_norm;
+	if (use_zero_guess) {
+		info.sol_norm_initial = 0;
+		V.set(x, 0.);
+		V.copy(r, b);
+	}
+	else {
+		info.sol_norm_initial = V.l2norm(x);
+		S.residual(b, x, r);
+	}
+	double current_res = V.l2norm(r);
+	if (current_res < terminate_tol) {
+		info.res_norm_initial = current_res;
+		info.res_norm_final = current_res;
+		info.status = converged_rtol;
+		return info;
+	}
+	S.P(r, z);
+	double rho[2] = {2.0, 0.0};
+	rho[1] = V.dot(z, r);
+	rho[0] = rho[1];
+	V.copy(p, z);
+	for (int iter = 0; iter < maxiter; iter++) {
+		double beta = 1.0;
+		S.A(p, w);
+		double alpha = V.dot(w, p);
+		alpha = rho[1] / alpha;
+		V.axpy(x, alpha, p, x);
+		V.axpy(r, -alpha, w, r);
+		current_res = V.l2norm(r);
+		H.push(current_res); // stands in for user_diagnostic(x, current_res)
+		if (current_res < terminate_tol) {
+			info.iters = iter + 1;
+			info.status = converged_rtol;
+			break;
+		}
+		S.P(r, z);
+		rho[0] = rho[1];
+		rho[1] = V.dot(r, z);
+		beta = rho[1] / rho[0];
+		V.axpy(p, beta, p, z);
+	}
+	info.res_norm_final = current_res;
+	info.sol_norm_final = V.l2norm(x);
+	if (info.iters == 0)
+		info.status = diverged_iters;
+	return info;
+}
+
+// solvers/bicgstab.hh:40-187
+Info bicgstab(const System & S, int maxiter, float rtol, bool use_zero_guess, const double * b, double * x, History & H) {
+	Info info;
+	const Vops V = S.v();
+	const idx n = S.M->n;
+	std::vector<double> w0(n), w1(n), w2(n), w3(n), w4(n), w5(n), w6(n), w7(n);
+	double *res = w0.data(), *r_tilde = w1.data(), *p = w2.data(), *v = w3.data(), *p_hat = w4.data(), *s = w5.data(),
+		   *s_hat = w6.data(), *t = w7.data();
+	double b_norm = V.l2norm(b);
+	if (b_norm == 0.)
+		b_norm = 1.;
+	const double terminate_tol = rtol * b_norm;
+	info.rhs_norm = b_norm;
+	if (use_zero_guess) {
+		info.sol_norm_initial = 0;
+		V.copy(res, b);
+		V.set(x, 0.);
+	}
+	else {
+		info.sol_norm_initial = V.l2norm(x);
+		S.residual(b, x, res);
+	}
+	double res_norm = V.l2norm(res);
+	double r_tilde_norm = res_norm;
+	info.res_norm_initial = res_norm;
+	if (res_norm < terminate_tol) {
+		info.status = converged_rtol;
+		info.res_norm_initial = res_norm;
+		info.res_norm_final = res_norm;
+		return info;
+	}
+	double alpha = 1.0, beta = 0.0, omega = 1.0;
+	double rho[2] = {1.0, 1.0};
+	V.copy(r_tilde, res);
+	V.set(p, 0.);
+	V.set(v, 0.);
+	for (int iter = 0; iter < maxiter; iter++) {
+		rho[1] = V.dot(r_tilde, res);
+		const double angle = std::sqrt(std::fabs(rho[1]));
+		const double eps = std::numeric_limits<double>::epsilon();
+		if (angle < eps * r_tilde_norm) {
+			S.residual(b, x, res);
+			V.copy(r_tilde, res);
+			res_norm = V.l2norm(res);
+			rho[1] = r_tilde_norm = res_norm;
+			V.copy(p, res);
+			++info.restarts;
+			continue;
+		}
+		if (iter == 0) {
+			V.copy(p, res);
+		}
+		else {
+			beta = (rho[1] / rho[0]) * (alpha / omega);
+			V.axpy(p, -omega, v, p);
+			V.axpy(p, beta, p, res);
+		}
+		S.P(p, p_hat);
+		S.A(p_hat, v);
+		alpha = V.dot(r_tilde, v);
+		alpha = rho[1] / alpha;
+		V.axpy(s, -alpha, v, res);
+		const double s_norm = V.l2norm(s);
+		if (s_norm < rtol) { // sic: compares with settings.rtol, bicgstab.hh:136
+			V.axpy(x, alpha, p_hat, x);
+			info.iters = iter;
+			info.status = converged_rtol;
+			break;
+		}
+		S.P(s, s_hat);
+		S.A(s_hat, t);
+		const double t_sqnorm = V.dot(t, t);
+		const double t_dot_s = V.dot(t, s);
+		omega = (t_sqnorm == 0.0) ? 0.0 : t_dot_s / t_sqnorm;
+		V.axpy(x, alpha, p_hat, x);
+		V.axpy(x, omega, s_hat, x);
+		V.axpy(res, -omega, t, s);
+		res_norm = V.l2norm(res);
+		H.push(res_norm);
+		if (res_norm < terminate_tol) {
+			info.status = converged_rtol;
+			info.iters = iter + 1;
+			break;
+		}
+		if (omega == 0.0) {
+			info.iters = iter + 1;
+			info.status = diverged_breakdown;
+			break;
+		}
+		rho[0] = rho[1];
+	}
+	info.res_norm_final = res_norm;
+	info.sol_norm_final = V.l2norm(x);
+	if (info.iters == 0)
+		info.status = diverged_iters;
+	return info;
+}
+
+// solvers/gmres.hh:54-361 (right/left preconditioning, restart)
+struct Gmres {
+	const System & S;
+	int maxiter, max_krylov_dim;
+	float rtol;
+	bool use_zero_guess, right, restart;
+	int dim; // max_dim + 1
+	std::vector<double> hess, cosv, sinv, dw, dy; // column-major (mdcolex): H(i,j) at i + j*dim
+	std::vector<std::vector<double>> basis;
+	double & H(int i, int j) { return hess[static_cast<size_t>(i) + static_cast<size_t>(j) * dim]; }
+
+	void orthogonalize(double * v, int k) { // :266-279 modified Gram-Schmidt
+		const Vops V = S.v();
+		for (int j = 0; j < k; j++) {
+			const double h_jk = V.dot(v, basis[j].data());
+			V.axpy(v, -h_jk, basis[j].data(), v);
+			H(j, k - 1) = h_jk;
+		}
+		H(k, k - 1) = V.l2norm(v);
+	}
+	void apply_givens(int i, int k) { // :281-296
+		const double x = H(i, k), y = H(i + 1, k), c = cosv[i], s = sinv[i];
+		H(i, k) = c * x + s * y;
+		H(i + 1, k) = -s * x + c * y;
+	}
+	void compute_givens(int k) { // :298-331
+		const double f = H(k, k), g = H(k + 1, k);
+		double c, s;
+		if (g == 0.0) {
+			c = 1.0;
+			s = 0.0;
+		}
+		else if (f == 0.0) {
+			c = 0.0;
+			s = (g < 0.0) ? -1.0 : 1.0;
+		}
+		else {
+			double r = std::sqrt(f * f + g * g);
+			r = 1.0 / r;
+			c = std::fabs(f) * r;
+			s = std::copysign(g * r, f);
+		}
+		cosv[k] = c;
+		sinv[k] = s;
+	}
+	void back_solve(int nr) { // :333-347
+		dy[nr] = dw[nr] / H(nr, nr);
+		for (int k = nr - 1; k >= 0; k--) {
+			dy[k] = dw[k];
+			for (int i = k + 1; i <= nr; i++)
+				dy[k] -= H(k, i) * dy[i];
+			dy[k] = dy[k] / H(k, k);
+		}
+	}
+	void correct(int nr, double * z, double * v, double * x) { // :245-263
+		const Vops V = S.v();
+		if (right) {
+			V.set(z, 0.0);
+			for (int i = 0; i <= nr; i++)
+				V.axpy(z, dy[i], basis[i].data(), z);
+			S.P(z, v);
+			V.axpy(x, 1.0, v, x);
+		}
+		else {
+			for (int i = 0; i <= nr; i++)
+				V.axpy(x, dy[i], basis[i].data(), x);
+		}
+	}
+
+	Info run(const double * b, double * x, History & Hs) {
+		Info info;
+		const Vops V = S.v();
+		const idx n = S.M->n;
+		if (max_krylov_dim < 0)
+			max_krylov_dim = maxiter; // settings::validate :394-404
+		const int max_dim = std::min(max_krylov_dim, maxiter);
+		dim = max_dim + 1;
+		hess.assign(static_cast<size_t>(dim) * dim, 0.0);
+		cosv.assign(dim, 0.0);
+		sinv.assign(dim, 0.0);
+		dw.assign(dim, 0.0);
+		dy.assign(dim, 0.0);
+		basis.assign(dim, std::vector<double>(n));
+		std::vector<double> resv(n), zv(n), vv(n);
+		double *res = resv.data(), *z = zv.data(), *v = vv.data();
+
+		double b_norm = V.l2norm(b);
+		info.rhs_norm = b_norm;
+		if (b_norm < std::numeric_limits<double>::epsilon())
+			b_norm = 1.0;
+		const double terminate_tol = rtol * b_norm;
+		if (use_zero_guess)
+			V.set(x, 0.);
+		if (!right) {
+			if (use_zero_guess)
+				V.copy(basis[0].data(), b);
+			else
+				S.residual(b, x, basis[0].data());
+			S.P(basis[0].data(), res);
+		}
+		else {
+			if (use_zero_guess)
+				V.copy(res, b);
+			else
+				S.residual(b, x, res);
+		}
+		const double beta = V.l2norm(res);
+		info.res_norm_initial = beta;
+		if (beta < terminate_tol) {
+			info.res_norm_final = beta;
+			info.status = converged_rtol;
+			return info;
+		}
+		V.scale(res, 1.0 / beta);
+		V.copy(basis[0].data(), res);
+		dw[0] = beta;
+		double v_norm = beta;
+		int k = 0;
+		for (int iter = 0; iter < maxiter; iter++) {
+			if (right) {
+				S.P(basis[k].data(), z);
+				S.A(z, v);
+			}
+			else {
+				S.A(basis[k].data(), z);
+				S.P(z, v);
+			}
+			orthogonalize(v, k + 1);
+			v_norm = H(k + 1, k);
+			if (v_norm != 0.0)
+				V.scale(v, 1.0 / v_norm);
+			V.copy(basis[k + 1].data(), v);
+			for (int i = 0; i < k; i++)
+				apply_givens(i, k);
+			if (v_norm != 0.0) {
+				compute_givens(k);
+				apply_givens(k, k);
+				H(k + 1, k) = 0.0;
+				const double xx = dw[k], c = cosv[k], s = sinv[k];
+				dw[k] = c * xx;
+				dw[k + 1] = -s * xx;
+			}
+			v_norm = std::fabs(dw[k + 1]);
+			++k;
+			Hs.push(v_norm);
+			if (v_norm < terminate_tol) {
+				info.status = converged_rtol;
+				info.iters = iter + 1;
+				break;
+			}
+			if (k == max_krylov_dim && iter != maxiter - 1) {
+				back_solve(k - 1);
+				correct(k - 1, z, v, x);
+				if (!right) {
+					S.residual(b, x, basis[0].data());
+					S.P(basis[0].data(), res);
+				}
+				else
+					S.residual(b, x, res);
+				const double betar = V.l2norm(res);
+				V.scale(res, 1.0 / betar);
+				V.copy(basis[0].data(), res);
+				dw[0] = betar;
+				++info.restarts;
+				k = 0;
+			}
+		}
+		if (k > 0) {
+			back_solve(k - 1);
+			correct(k - 1, z, v, x);
+		}
+		info.res_norm_final = v_norm;
+		info.sol_norm_final = V.l2norm(x);
+		if (info.iters == 0)
+			info.status = diverged_iters;
+		return info;
+	}
+};
+
+// solvers/mg/jacobi.hh:58-93, one colour at a time; x, b, tmp in global layout
+void jacobi_relax(ParCsr & M, double omega, idx nrelax, const double * b, double * x) {
+	std::vector<double> tmp(M.n);
+	for (idx s = 0; s < nrelax; ++s) {
+		std::copy(x, x + M.n, tmp.begin()); // std::copy of the whole span incl. ghosts (:63)
+#pragma omp parallel for schedule(static, 1)
+		for (int p = 0; p < M.P; ++p) {
+			const Colour & C = M.c[p];
+			const idx no = C.owned();
+			for (idx r = 0; r < no; ++r) {
+				double diag = 0, lpu_x = 0;
+				for (idx off = C.diag.rowptr[r]; off < C.diag.rowptr[r + 1]; ++off) {
+					const idx c = C.diag.col[off];
+					if (C.row_beg + r == C.row_beg + c) // global_id(row) == global_id(col)
+						diag = C.diag.val[off];
+					else
+						lpu_x += C.diag.val[off] * tmp[C.row_beg + c];
+				}
+				for (idx off = C.offd.rowptr[r]; off < C.offd.rowptr[r + 1]; ++off)
+					lpu_x += C.offd.val[off] * tmp[C.colmap[C.offd.col[off] - no]];
+				const double dinv = 1. / diag;
+				x[C.row_beg + r] = omega * dinv * (b[C.row_beg + r] - lpu_x) + (1 - omega) * tmp[C.row_beg + r];
+			}
+		}
+	}
+}
+
+// synthetic operators of SURVEY.md section 8d: rows g = i + nx*(j + ny*k), Dirichlet truncation,
+// columns ascending.  kind 5 / 7 / 27.
+template<class F>
+void visit_stencil(int kind, int64_t nx, int64_t ny, int64_t nz, int64_t g, double dv, double ov, F && f) {
+	const int64_t i = g % nx, j = (g / nx) % ny, k = g / (nx * ny);
+	if (kind == 27) {
+		for (int dk = -1; dk <= 1; ++dk)
+			for (int dj = -1; dj <= 1; ++dj)
+				for (int di = -1; di <= 1; ++di) {
+					const int64_t ii = i + di, jj = j + dj, kk = k + dk;
+					if (ii < 0 || ii >= nx || jj < 0 || jj >= ny || kk < 0 || kk >= nz)
+						continue;
+					f(ii + nx * (jj + ny * kk), (di == 0 && dj == 0 && dk == 0) ? dv : ov);
+				}
+		return;
+	}
+	if (kind == 7 && k > 0)
+		f(g - nx * ny, ov);
+	if (j > 0)
+		f(g - nx, ov);
+	if (i > 0)
+		f(g - 1, ov);
+	f(g, dv);
+	if (i < nx - 1)
+		f(g + 1, ov);
+	if (j < ny - 1)
+		f(g + nx, ov);
+	if (kind == 7 && k < nz - 1)
+		f(g + nx * ny, ov);
+}
+
+} // namespace
+
+extern "C" {
+
+struct orc_info {
+	int status, iters, restarts;
+	float res_norm_initial, res_norm_final, sol_norm_initial, sol_norm_final, rhs_norm;
+	int history_len;
+};
+
+static void fill(orc_info * out, const Info & i, const History & H) {
+	out->status = i.status;
+	out->iters = i.iters;
+	out->restarts = i.restarts;
+	out->res_norm_initial = i.res_norm_initial;
+	out->res_norm_final = i.res_norm_final;
+	out->sol_norm_initial = i.sol_norm_initial;
+	out->sol_norm_final = i.sol_norm_final;
+	out->rhs_norm = i.rhs_norm;
+	out->history_len = H.n;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+	return omp_get_max_threads();
+#else
+	return 1;
+#endif
+}
+
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+	omp_set_num_threads(n);
+#else
+	(void)n;
+#endif
+}
+
+// number of stencil nonzeros / fill a global CSR (int64 indices) for the generators
+int64_t orc_stencil_nnz(int kind, int64_t nx, int64_t ny, int64_t nz) {
+	if (kind == 27)
+		return (3 * nx - 2) * (3 * ny - 2) * (3 * nz - 2);
+	if (kind == 7)
+		return 7 * nx * ny * nz - 2 * (nx * ny + ny * nz + nx * nz);
+	return 5 * nx * ny - 2 * (nx + ny);
+}
+
+void orc_stencil_fill(int kind, int64_t nx, int64_t ny, int64_t nz, double diag_shift, double scale, int64_t * rowptr,
+                      int64_t * col, double * val) {
+	const int64_t n = nx * ny * nz;
+	const double center = kind == 27 ? 26.0 : (kind == 7 ? 6.0 : 4.0);
+	const double dv = (center + diag_shift) * scale, ov = -1.0 * scale;
+	rowptr[0] = 0;
+	for (int64_t g = 0; g < n; ++g) {
+		int64_t c = 0;
+		visit_stencil(kind, nx, ny, nz, g, dv, ov, [&](int64_t, double) { ++c; });
+		rowptr[g + 1] = rowptr[g] + c;
+	}
+#pragma omp parallel for schedule(static)
+	for (int64_t g = 0; g < n; ++g) {
+		int64_t p = rowptr[g];
+		visit_stencil(kind, nx, ny, nz, g, dv, ov, [&](int64_t cc, double v) {
+			col[p] = cc;
+			val[p] = v;
+			++p;
+		});
+	}
+}
+
+// serial CSR SpMV with the reference's index type (matrices/seq.hh:178-194)
+void orc_csr_spmv(int64_t n, const int64_t * rowptr, const int64_t * col, const double * val, const double * x,
+                  double * y) {
+	for (int64_t i = 0; i < n; ++i) {
+		y[i] = 0.;
+		for (int64_t off = rowptr[i]; off < rowptr[i + 1]; ++off)
+			y[i] += val[off] * x[col[off]];
+	}
+}
+
+void * orc_parcsr_create(int64_t n, int colours, const int64_t * part, const int64_t * rowptr, const int64_t * col,
+                         const double * val) {
+	std::vector<idx> p;
+	if (part)
+		p.assign(part, part + colours + 1);
+	return build(static_cast<idx>(n), colours, part ? p.data() : nullptr, rowptr, col, val);
+}
+
+void orc_parcsr_destroy(void * M) { delete static_cast<ParCsr *>(M); }
+
+void orc_parcsr_partition(void * Mv, int64_t * part) {
+	auto * M = static_cast<ParCsr *>(Mv);
+	for (int p = 0; p <= M->P; ++p)
+		part[p] = static_cast<int64_t>(M->part[p]);
+}
+
+// sizes of colour p: {n_owned, n_ghost, nnz_diag, nnz_offd}
+void orc_parcsr_sizes(void * Mv, int p, int64_t * out) {
+	const Colour & C = static_cast<ParCsr *>(Mv)->c[p];
+	out[0] = C.owned();
+	out[1] = C.colmap.size();
+	out[2] = C.diag.col.size();
+	out[3] = C.offd.col.size();
+}
+
+// copy out colour p's blocks (which: 0 diag, 1 offd); any pointer may be null
+void orc_parcsr_block(void * Mv, int p, int which, int64_t * rowptr, int64_t * col, double * val, int64_t * colmap) {
+	const Colour & C = static_cast<ParCsr *>(Mv)->c[p];
+	const Csr & B = which == 0 ? C.diag : C.offd;
+	if (rowptr)
+		for (size_t i = 0; i < B.rowptr.size(); ++i)
+			rowptr[i] = static_cast<int64_t>(B.rowptr[i]);
+	if (col)
+		for (size_t i = 0; i < B.col.size(); ++i)
+			col[i] = static_cast<int64_t>(B.col[i]);
+	if (val)
+		std::copy(B.val.begin(), B.val.end(), val);
+	if (colmap)
+		for (size_t i = 0; i < C.colmap.size(); ++i)
+			colmap[i] = static_cast<int64_t>(C.colmap[i]);
+}
+
+void orc_parcsr_spmv(void * M, const double * x, double * y) { par_spmv(*static_cast<ParCsr *>(M), x, y); }
+
+void orc_parcsr_dinv(void * Mv, double * d) { // util/test/mesh.hh:123-140
+	auto * M = static_cast<ParCsr *>(Mv);
+	for (const Colour & C : M->c)
+		for (idx r = 0; r < C.owned(); ++r) {
+			double a = 0.0;
+			for (idx off = C.diag.rowptr[r]; off < C.diag.rowptr[r + 1]; ++off)
+				if (C.diag.col[off] == r)
+					a = C.diag.val[off];
+			d[C.row_beg + r] = 1.0 / a;
+		}
+}
+
+void orc_jacobi_relax(void * M, double omega, int64_t nrelax, const double * b, double * x) {
+	jacobi_relax(*static_cast<ParCsr *>(M), omega, static_cast<idx>(nrelax), b, x);
+}
+
+double orc_dot(void * M, const double * x, const double * y) { return Vops{static_cast<ParCsr *>(M)}.dot(x, y); }
+
+// set_random per colour: mt19937(seed), uniform(0,1), sequential over local dofs, same seed on every
+// colour (vectors/operations/topo_tasks.hh:305-314)
+void orc_set_random(void * Mv, double * x, unsigned seed) {
+	auto * M = static_cast<ParCsr *>(Mv);
+	for (const Colour & C : M->c) {
+		std::mt19937 gen(seed);
+		std::uniform_real_distribution<double> dis(0., 1.);
+		for (idx i = C.row_beg; i < C.row_end; ++i)
+			x[i] = dis(gen);
+	}
+}
+
+void orc_cg(void * M, const double * dinv, int maxiter, float rtol, int use_zero_guess, const double * b, double * x,
+            orc_info * out, double * history, int history_cap) {
+	System S{static_cast<ParCsr *>(M), dinv};
+	History H{history, history_cap};
+	fill(out, cg(S, maxiter, rtol, use_zero_guess != 0, b, x, H), H);
+}
+
+void orc_bicgstab(void * M, const double * dinv, int maxiter, float rtol, int use_zero_guess, const double * b,
+                  double * x, orc_info * out, double * history, int history_cap) {
+	System S{static_cast<ParCsr *>(M), dinv};
+	History H{history, history_cap};
+	fill(out, bicgstab(S, maxiter, rtol, use_zero_guess != 0, b, x, H), H);
+}
+
+void orc_gmres(void * M, const double * dinv, int maxiter, float rtol, int use_zero_guess, int max_krylov_dim,
+               int right_precond, int restart, const double * b, double * x, orc_info * out, double * history,
+               int history_cap) {
+	System S{static_cast<ParCsr *>(M), dinv};
+	History H{history, history_cap};
+	Gmres g{S, maxiter, max_krylov_dim, rtol, use_zero_guess != 0, right_precond != 0, restart != 0};
+	fill(out, g.run(b, x, H), H);
+}
+
+// ---- closed-form vector operation restatements for tests (global arrays of length n) ----
+// op codes mirror include/fsb.h's element-wise list; a, b scalars; x, y operands; z destination.
+void orc_vec_op(int op, int64_t n, double * z, const double * x, const double * y, double a, double b) {
+	for (int64_t i = 0; i < n; ++i) {
+		switch (op) {
+		case 0: z[i] = x[i]; break; // copy                      topo_tasks.hh:80-84
+		case 1: z[i] = a; break; // set_to_scalar                 :68-70
+		case 2: z[i] = x[i] * a; break; // scale                  :72-78
+		case 3: z[i] = x[i] + y[i]; break; // add                 :86-92
+		case 4: z[i] = x[i] - y[i]; break; // subtract            :94-108
+		case 5: z[i] = x[i] * y[i]; break; // multiply            :110-118
+		case 6: z[i] = x[i] / y[i]; break; // divide              :120-134
+		case 7: z[i] = 1.0 / x[i]; break; // reciprocal           :136-142
+		case 8: z[i] = a * x[i] + b * y[i]; break; // linear_sum  :144-172
+		case 9: z[i] = a * x[i] + y[i]; break; // axpy            :174-191
+		case 10: z[i] = a * x[i] + b * z[i]; break; // axpby      :193-198
+		case 11: z[i] = std::abs(x[i]); break; // abs             :200-206
+		case 12: z[i] = x[i] + a; break; // add_scalar            :208-214
+		}
+	}
+}
+
+// reductions over one colour (sequential): 0 dot, 1 l1, 2 inf-norm, 3 min, 4 max, 5 pow-sum (p = a)
+double orc_vec_reduce(int op, int64_t n, const double * x, const double * y, double a) {
+	double r = 0.0;
+	if (op == 3)
+		r = std::numeric_limits<double>::max();
+	if (op == 4)
+		r = std::numeric_limits<double>::lowest();
+	for (int64_t i = 0; i < n; ++i) {
+		switch (op) {
+		case 0: r += x[i] * y[i]; break; // scalar_prod           :52-66
+		case 1: r += std::abs(x[i]); break; // l1_norm_local      :228-235
+		case 2: r = std::max(r, std::abs(x[i])); break; // inf    :291-297
+		case 3: r = std::min(r, x[i]); break; // local_min        :245-267
+		case 4: r = std::max(r, x[i]); break; // local_max
+		case 5: r += std::pow(x[i], static_cast<int>(a)); break; // lp_norm_local :216-226
+		}
+	}
+	return r;
+}
+
+} // extern "C"
