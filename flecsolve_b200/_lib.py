@@ -31,13 +31,29 @@ def declared_symbols() -> list[str]:
     return sorted(set(re.findall(r"\b(fsb_[a-z0-9_]+)\s*\(", src)))
 
 
+def _preload_nccl() -> None:
+    """libfsb.so needs libnccl.so.2.  torch bundles a newer one than the system's; whichever is
+    loaded first wins for the whole process (same soname), and torch cannot run on the older
+    one -- so load torch's copy first when it exists."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+    except Exception:
+        pass
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise FsbError(-1, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)")
-        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _preload_nccl()
+        _lib = C.CDLL(LIB_PATH)
         _declare(_lib)
     return _lib
 
@@ -71,6 +87,8 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_ctx_get_stat", C.c_int, _p, C.c_int, _pi64)
     f("fsb_ctx_reset_stats", C.c_int, _p)
     f("fsb_ctx_flush_l2", C.c_int, _p)
+    f("fsb_ctx_event_record", C.c_int, _p, C.c_int)
+    f("fsb_ctx_event_elapsed_ms", C.c_int, _p, C.c_int, C.c_int, _pd)
     f("fsb_vec_create", C.c_int, _p, _i64, _i64, C.POINTER(_p))
     f("fsb_vec_wrap", C.c_int, _p, _p, _i64, _i64, C.POINTER(_p))
     f("fsb_vec_destroy", C.c_int, _p)
@@ -158,6 +176,14 @@ class Context:
 
     def flush_l2(self):
         check(lib().fsb_ctx_flush_l2(self.h))
+
+    def event_record(self, slot: int):
+        check(lib().fsb_ctx_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        out = _dbl()
+        check(lib().fsb_ctx_event_elapsed_ms(self.h, a, b, C.byref(out)))
+        return out.value
 
     @property
     def stream(self) -> int:

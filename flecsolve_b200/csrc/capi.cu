@@ -134,6 +134,9 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 		for (auto e : c->token_event)
 			if (e)
 				cudaEventDestroy(e);
+		for (auto e : c->timers)
+			if (e)
+				cudaEventDestroy(e);
 		cudaFree(c->d_partials);
 		cudaFree(c->d_counter);
 		cudaFree(c->d_results);
@@ -210,6 +213,26 @@ int fsb_ctx_flush_l2(fsb_ctx_t c) {
 			c->flush_bytes = bytes;
 		}
 		FSB_CUDA(cudaMemsetAsync(c->d_flush, 1, c->flush_bytes, c->stream));
+	});
+}
+
+int fsb_ctx_event_record(fsb_ctx_t c, int slot) {
+	return guarded([&] {
+		FSB_REQUIRE(c && slot >= 0 && slot < 16, "event slot out of range");
+		flush(c);
+		if (!c->timers[slot])
+			FSB_CUDA(cudaEventCreate(&c->timers[slot]));
+		FSB_CUDA(cudaEventRecord(c->timers[slot], c->stream));
+	});
+}
+
+int fsb_ctx_event_elapsed_ms(fsb_ctx_t c, int a, int b, double * ms) {
+	return guarded([&] {
+		FSB_REQUIRE(c && ms && a >= 0 && a < 16 && b >= 0 && b < 16 && c->timers[a] && c->timers[b], "bad event slots");
+		FSB_CUDA(cudaEventSynchronize(c->timers[b]));
+		float t = 0;
+		FSB_CUDA(cudaEventElapsedTime(&t, c->timers[a], c->timers[b]));
+		*ms = t;
 	});
 }
 

@@ -98,6 +98,8 @@ struct fsb_ctx_s {
 	int spmv_rows_per_cta = 0; // 0 = auto
 	int spmv_threads = 0;
 
+	cudaEvent_t timers[16] = {};
+
 	// L2 flush scratch
 	void * d_flush = nullptr;
 	size_t flush_bytes = 0;
@@ -127,6 +129,7 @@ struct csr_block {
 	double * val = nullptr; // [nnz padded]
 	// row-block work descriptors for the streaming kernel
 	int32_t * blk_row = nullptr; // [n_blk+1] first row of each CTA's row block
+	void * blk_desc = nullptr; // [n_blk] per-block descriptors (spmv.cu)
 	int n_blk = 0;
 	int max_blk_nnz = 0; // max nnz staged by one CTA (smem sizing)
 	int max_blk_rows = 0;
@@ -168,7 +171,7 @@ int64_t new_token(fsb_ctx_s * c, int nccl_op);
 // kernels (declared here, defined in their .cu)
 void launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
                  const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s);
-int spmv_partial_count(const csr_block & B);
+int spmv_partial_count(const fsb_ctx_s * c, const csr_block & B);
 void finalize_reduction(fsb_ctx_s * c, int n_partials, int64_t token, int op_kind);
 void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x);
 

@@ -35,6 +35,7 @@ static void free_block(csr_block & B) {
 	cudaFree(B.col);
 	cudaFree(B.val);
 	cudaFree(B.blk_row);
+	cudaFree(B.blk_desc);
 	cudaFree(B.row_ids);
 	B = csr_block{};
 }
@@ -47,11 +48,11 @@ static void upload_block(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t
 	B.nnz = rowptr.empty() ? 0 : rowptr.back();
 	B.wide = B.nnz >= (1LL << 31) - 16;
 	if (B.wide) {
-		B.rowptr = dev_upload<int64_t>(c, rowptr);
+		B.rowptr = dev_upload<int64_t>(c, rowptr, 8);
 	}
 	else {
 		std::vector<int32_t> rp32(rowptr.begin(), rowptr.end());
-		B.rowptr = dev_upload<int32_t>(c, rp32);
+		B.rowptr = dev_upload<int32_t>(c, rp32, 8);
 		FSB_CUDA(cudaStreamSynchronize(c->stream)); // rp32 is a temporary
 	}
 	B.col = dev_upload<int32_t>(c, col, 16);
@@ -219,14 +220,14 @@ void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot) {
 		fsb_vec_s * other = dot->x == y ? dot->y : dot->x;
 		u = other->d; // other == y gives sum y^2
 	}
-	const int np_diag = u ? spmv_partial_count(A->diag) : 0;
+	const int np_diag = u ? spmv_partial_count(c, A->diag) : 0;
 	launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream);
 	int np_offd = 0;
 	if (A->offd.n_blk > 0) {
 		if (!waited)
 			FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
 		waited = true;
-		np_offd = u ? spmv_partial_count(A->offd) : 0;
+		np_offd = u ? spmv_partial_count(c, A->offd) : 0;
 		launch_spmv(c, A->offd, x->d, y->d, true, u, c->d_partials, np_diag, c->stream);
 	}
 	if (!waited) // ghosts were requested but no row uses them: still order the streams
@@ -491,13 +492,13 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 	D.wide = static_cast<long long>(width) * n >= (1LL << 31) - 16;
 	long long nnz_d = 0;
 	if (D.wide) {
-		long long * rp = dev_alloc<long long>(n + 1);
+		long long * rp = dev_alloc<long long>(n + 1 + 8);
 		exclusive_scan(c, thrust::make_transform_iterator(cnt_d, to_i64{}), rp, n + 1);
 		FSB_CUDA(cudaMemcpy(&nnz_d, rp + n, sizeof(long long), cudaMemcpyDeviceToHost));
 		D.rowptr = rp;
 	}
 	else {
-		int * rp = dev_alloc<int>(n + 1);
+		int * rp = dev_alloc<int>(n + 1 + 8);
 		exclusive_scan(c, cnt_d, rp, n + 1);
 		int last = 0;
 		FSB_CUDA(cudaMemcpy(&last, rp + n, sizeof(int), cudaMemcpyDeviceToHost));
@@ -539,7 +540,7 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 		cudaFree(iota);
 		cudaFree(d_num);
 		FSB_CUDA(cudaMemsetAsync(cnt_c + n_rows, 0, sizeof(int), c->stream));
-		int * rp = dev_alloc<int>(n_rows + 1);
+		int * rp = dev_alloc<int>(n_rows + 1 + 8);
 		exclusive_scan(c, cnt_c, rp, static_cast<long long>(n_rows) + 1);
 		int nnz_o = 0;
 		FSB_CUDA(cudaMemcpy(&nnz_o, rp + n_rows, sizeof(int), cudaMemcpyDeviceToHost));

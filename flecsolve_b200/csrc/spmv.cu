@@ -10,31 +10,42 @@
 //    contiguous in CSR, so one elected thread pulls them into shared memory with two
 //    1-D bulk TMA copies (cp.async.bulk ... mbarrier::complete_tx) -- fully coalesced
 //    128-byte HBM bursts regardless of row length, no per-thread load instructions.
-//  * NSTAGE-deep ring of shared-memory stages per CTA: the copy of row block i+NSTAGE-1
-//    is in flight while block i is being multiplied; CTAs are persistent and walk row
-//    blocks with a grid stride, so the number of reduction partials is bounded.
+//  * NSTAGE-deep ring of shared-memory stages per CTA: the copies of row blocks
+//    i+1 .. i+NSTAGE-1 are in flight while block i is being multiplied; CTAs are persistent
+//    and walk row blocks with a grid stride, so the number of reduction partials is bounded.
 //  * Rows are assigned thread-per-row with consecutive lanes on consecutive rows:
 //    stencil/banded gathers x[col] then touch 2-3 L1 lines per warp instruction, and the
 //    strided shared-memory reads of val/col are conflict-free for odd row lengths.
+//    Gathers are issued in groups of GATHER independent loads before the in-order sum.
 //    x itself is served by L1/L2 (reuse distance of a 3-D stencil is two grid planes).
 //  * Row blocks with few, long rows switch to warp-per-row; a row longer than a stage
 //    is streamed straight from global memory by the whole CTA.
 //  * Optional fused epilogue: per-CTA partial of sum_i y_i * u_i (CG's p.Ap, cg.hh:98)
 //    and accumulate mode y += A x for the off-process block (parcsr.hh:61-68).
-#include <cub/cub.cuh>
+#include <cstdlib>
 
 #include "ew_kernels.cuh"
 #include "fsb_internal.h"
 
 namespace fsb {
 
-constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_MAX_THREADS = 544; // 512 consumer threads + one producer warp
+constexpr int GATHER = 16;
+
+// one row block = the unit of work of a pipeline stage
+struct blk_desc {
+	long long z0; // first nonzero
+	int r0; // first row
+	int nrows;
+	int nnz;
+	int pad;
+};
 
 struct spmv_args {
 	const void * rowptr;
 	const int32_t * col;
 	const double * val;
-	const int32_t * blk_row; // [n_blk + 1]
+	const blk_desc * desc; // [n_blk]
 	const int32_t * row_ids; // compressed-row list or nullptr
 	const double * x;
 	double * y;
@@ -42,6 +53,7 @@ struct spmv_args {
 	double * partials; // one per CTA
 	int n_blk;
 	int cap; // nnz capacity of one stage (multiple of 4, includes alignment slack)
+	int rcap; // row-offset capacity of one stage
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) {
@@ -52,6 +64,9 @@ __device__ __forceinline__ void mbar_init(uint64_t * bar, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
 	asm volatile(
@@ -73,125 +88,184 @@ __device__ __forceinline__ void tma_load_1d(void * dst, const void * src, uint32
 	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
 	             : "memory");
 }
+// barrier among the consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync(int nconsumers) {
+	asm volatile("bar.sync 1, %0;" ::"r"(nconsumers) : "memory");
+}
 
+// Warp-specialised: warp 0 is the producer (one lane issues descriptor loads and bulk copies and
+// runs up to NSTAGE row blocks ahead, throttled by the `empty` barriers); all other warps are
+// consumers (wait `full`, multiply thread-per-row out of shared memory, release the stage).
 template<class OffT, int NSTAGE, bool ACC, bool DOT, bool ROWLIST>
-__global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(const __grid_constant__ spmv_args a) {
+__global__ void __launch_bounds__(SPMV_MAX_THREADS) spmv_stream_kernel(const __grid_constant__ spmv_args a) {
 	extern __shared__ __align__(128) unsigned char smem[];
-	__shared__ uint64_t bar[NSTAGE];
+	__shared__ uint64_t full[NSTAGE], empty[NSTAGE];
+	__shared__ blk_desc sdesc[NSTAGE];
 	__shared__ double scratch[32];
-	// stage layout: NSTAGE x [cap doubles] then NSTAGE x [cap int32]
-	double * s_val = reinterpret_cast<double *>(smem);
-	int32_t * s_col = reinterpret_cast<int32_t *>(smem + static_cast<size_t>(NSTAGE) * a.cap * sizeof(double));
+	constexpr int E = 16 / sizeof(OffT); // row offsets per 16 bytes
+	const size_t stage_bytes = static_cast<size_t>(a.cap) * 12 + static_cast<size_t>(a.rcap) * sizeof(OffT);
 	const OffT * __restrict__ rowptr = static_cast<const OffT *>(a.rowptr);
 	const double * __restrict__ x = a.x;
 	const int tid = threadIdx.x;
+	const int nconsumers = blockDim.x - 32;
+	const int first = blockIdx.x, step = gridDim.x;
 
 	if (tid == 0) {
-		for (int s = 0; s < NSTAGE; ++s)
-			mbar_init(&bar[s], 1);
+		for (int s = 0; s < NSTAGE; ++s) {
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], nconsumers / 32);
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();
 
-	// issue the bulk copies of row block `blk` into stage `s`; returns nothing (thread 0 only)
-	auto issue = [&](int blk, int s) {
-		const int r0 = a.blk_row[blk], r1 = a.blk_row[blk + 1];
-		const long long z0 = static_cast<long long>(rowptr[r0]), z1 = static_cast<long long>(rowptr[r1]);
-		const long long za = z0 & ~3LL; // 16-byte aligned start for the int32 stream
-		const long long cnt = ((z1 + 3) & ~3LL) - za;
-		if (cnt > 0 && cnt <= a.cap) {
-			mbar_expect_tx(&bar[s], static_cast<uint32_t>(cnt * 12));
-			tma_load_1d(s_val + static_cast<size_t>(s) * a.cap, a.val + za, static_cast<uint32_t>(cnt * 8), &bar[s]);
-			tma_load_1d(s_col + static_cast<size_t>(s) * a.cap, a.col + za, static_cast<uint32_t>(cnt * 4), &bar[s]);
-		}
-		else {
-			mbar_expect_tx(&bar[s], 0); // empty or oversize block: nothing staged, complete the phase
-		}
-	};
+	double dot_acc = 0.0;
 
-	const int first = blockIdx.x, step = gridDim.x;
-	if (tid == 0) {
-#pragma unroll
-		for (int s = 0; s < NSTAGE - 1; ++s) {
-			const int blk = first + s * step;
-			if (blk < a.n_blk)
-				issue(blk, s);
+	if (tid < 32) {
+		// ------------------------------------------------ producer
+		// The whole warp fetches block descriptors 32 iterations at a time (lane l holds the
+		// descriptor of iteration base + l, the next batch is already in flight) so their DRAM
+		// latency never sits between a freed stage and the next bulk copy; lane 0 issues.
+		const int lane = tid;
+		const int niter = first < a.n_blk ? (a.n_blk - first + step - 1) / step : 0;
+		auto fetch = [&](int iter) {
+			blk_desc d{};
+			if (iter < niter)
+				d = a.desc[first + static_cast<long long>(iter) * step];
+			return d;
+		};
+		blk_desc cur = fetch(lane);
+		for (int base = 0; base < niter; base += 32) {
+			const blk_desc nxt = fetch(base + 32 + lane);
+			const int jmax = min(32, niter - base);
+			for (int j = 0; j < jmax; ++j) {
+				blk_desc d;
+				d.z0 = __shfl_sync(0xffffffffu, cur.z0, j);
+				d.r0 = __shfl_sync(0xffffffffu, cur.r0, j);
+				d.nrows = __shfl_sync(0xffffffffu, cur.nrows, j);
+				d.nnz = __shfl_sync(0xffffffffu, cur.nnz, j);
+				d.pad = 0;
+				if (lane == 0) {
+					const int it = base + j;
+					const int s = it % NSTAGE;
+					if (it >= NSTAGE)
+						mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+					sdesc[s] = d;
+					unsigned char * sbase = smem + s * stage_bytes;
+					const long long za = d.z0 & ~3LL; // 16-byte aligned start of the int32 stream
+					const long long cnt = ((d.z0 + d.nnz + 3) & ~3LL) - za;
+					const long long ra = d.r0 & ~static_cast<long long>(E - 1);
+					const long long rcnt = ((d.r0 + d.nrows + 1 + E - 1) & ~static_cast<long long>(E - 1)) - ra;
+					const bool staged = cnt > 0 && cnt <= a.cap;
+					uint32_t bytes = static_cast<uint32_t>(rcnt * sizeof(OffT));
+					if (staged)
+						bytes += static_cast<uint32_t>(cnt * 12);
+					mbar_expect_tx(&full[s], bytes); // also publishes sdesc[s] to the waiters
+					if (staged) {
+						tma_load_1d(sbase, a.val + za, static_cast<uint32_t>(cnt * 8), &full[s]);
+						tma_load_1d(sbase + static_cast<size_t>(a.cap) * 8, a.col + za, static_cast<uint32_t>(cnt * 4),
+						            &full[s]);
+					}
+					tma_load_1d(sbase + static_cast<size_t>(a.cap) * 12, rowptr + ra,
+					            static_cast<uint32_t>(rcnt * sizeof(OffT)), &full[s]);
+				}
+				__syncwarp();
+			}
+			cur = nxt;
 		}
 	}
+	else {
+		// ------------------------------------------------ consumers
+		const int ctid = tid - 32;
+		// write one row result; the dot partial of an accumulate pass only counts what this pass added
+		auto emit = [&](int r, double sum) {
+			const int yr = ROWLIST ? a.row_ids[r] : r;
+			double out = sum;
+			if constexpr (ACC) {
+				const double old = a.y[yr];
+				out = __dadd_rn(old, sum);
+				if constexpr (DOT)
+					dot_acc += (a.u == a.y) ? (out * out - old * old) : sum * a.u[yr];
+			}
+			else if constexpr (DOT) {
+				dot_acc = fma(out, a.u == a.y ? out : a.u[yr], dot_acc);
+			}
+			a.y[yr] = out;
+		};
 
-	double dot_acc = 0.0;
-	// write one row result; the dot partial of an accumulate pass only counts what this pass added
-	auto emit = [&](int r, double sum) {
-		const int yr = ROWLIST ? a.row_ids[r] : r;
-		double out = sum;
-		if constexpr (ACC) {
-			const double old = a.y[yr];
-			out = __dadd_rn(old, sum);
-			if constexpr (DOT)
-				dot_acc += (a.u == a.y) ? (out * out - old * old) : sum * a.u[yr];
-		}
-		else if constexpr (DOT) {
-			dot_acc = fma(out, a.u == a.y ? out : a.u[yr], dot_acc);
-		}
-		a.y[yr] = out;
-	};
-	int it = 0;
-	for (int blk = first; blk < a.n_blk; blk += step, ++it) {
-		const int s = it % NSTAGE;
-		const uint32_t parity = (it / NSTAGE) & 1;
-		if (tid == 0) { // prefetch NSTAGE-1 blocks ahead into the stage freed last iteration
-			const int pre = blk + (NSTAGE - 1) * step;
-			if (pre < a.n_blk)
-				issue(pre, (it + NSTAGE - 1) % NSTAGE);
-		}
-		const int r0 = a.blk_row[blk], r1 = a.blk_row[blk + 1];
-		const long long z0 = static_cast<long long>(rowptr[r0]), z1 = static_cast<long long>(rowptr[r1]);
-		const long long za = z0 & ~3LL;
-		const long long cnt = ((z1 + 3) & ~3LL) - za;
-		const int nrows = r1 - r0;
-		mbar_wait(&bar[s], parity);
-		const double * sv = s_val + static_cast<size_t>(s) * a.cap;
-		const int32_t * sc = s_col + static_cast<size_t>(s) * a.cap;
+		int it = 0;
+		for (int blk = first; blk < a.n_blk; blk += step, ++it) {
+			const int s = it % NSTAGE;
+			mbar_wait(&full[s], (it / NSTAGE) & 1);
+			const blk_desc d = sdesc[s];
+			const unsigned char * base = smem + s * stage_bytes;
+			const double * sv = reinterpret_cast<const double *>(base);
+			const int32_t * sc = reinterpret_cast<const int32_t *>(base + static_cast<size_t>(a.cap) * 8);
+			const OffT * srp = reinterpret_cast<const OffT *>(base + static_cast<size_t>(a.cap) * 12);
+			const long long za = d.z0 & ~3LL;
+			const int roff = d.r0 & (E - 1); // srp[roff + i] = rowptr[r0 + i]
+			const long long cnt = ((d.z0 + d.nnz + 3) & ~3LL) - za;
+			const int r0 = d.r0, nrows = d.nrows;
 
-		if (cnt > a.cap) {
-			// a single row longer than a stage: CTA-wide strided pass over global memory
-			for (int r = r0; r < r1; ++r) {
-				const long long p0 = static_cast<long long>(rowptr[r]), p1 = static_cast<long long>(rowptr[r + 1]);
-				double sum = 0.0;
-				for (long long p = p0 + tid; p < p1; p += SPMV_THREADS)
-					sum = fma(a.val[p], __ldg(&x[a.col[p]]), sum);
-				sum = block_fold<0>(sum, scratch);
-				if (tid == 0)
-					emit(r, sum);
+			if (cnt > a.cap) {
+				// a single row longer than a stage: all consumers stream it from global memory
+				for (int i = 0; i < nrows; ++i) {
+					const long long q0 = static_cast<long long>(srp[roff + i]), q1 = static_cast<long long>(srp[roff + i + 1]);
+					double sum = 0.0;
+					for (long long p = q0 + ctid; p < q1; p += nconsumers)
+						sum = fma(a.val[p], __ldg(&x[a.col[p]]), sum);
+					sum = warp_fold<0>(sum);
+					consumer_sync(nconsumers);
+					if ((ctid & 31) == 0)
+						scratch[ctid >> 5] = sum;
+					consumer_sync(nconsumers);
+					if (ctid == 0) {
+						double t = 0.0;
+						for (int w = 0; w < nconsumers / 32; ++w)
+							t += scratch[w];
+						emit(r0 + i, t);
+					}
+				}
 			}
-		}
-		else if (nrows * 8 >= SPMV_THREADS || nrows >= cnt) {
-			// thread per row, consecutive lanes on consecutive rows; in-order accumulation
-			for (int r = r0 + tid; r < r1; r += SPMV_THREADS) {
-				const int p0 = static_cast<int>(static_cast<long long>(rowptr[r]) - za);
-				const int p1 = static_cast<int>(static_cast<long long>(rowptr[r + 1]) - za);
-				double sum = 0.0;
-				for (int p = p0; p < p1; ++p)
-					sum = __dadd_rn(sum, __dmul_rn(sv[p], __ldg(&x[sc[p]])));
-				emit(r, sum);
+			else if (nrows * 8 >= nconsumers || nrows >= cnt) {
+				// thread per row, consecutive lanes on consecutive rows; in-order accumulation
+				for (int i = ctid; i < nrows; i += nconsumers) {
+					const int p0 = static_cast<int>(static_cast<long long>(srp[roff + i]) - za);
+					const int p1 = static_cast<int>(static_cast<long long>(srp[roff + i + 1]) - za);
+					double sum = 0.0;
+					for (int p = p0; p < p1; p += GATHER) {
+						double prod[GATHER];
+#pragma unroll
+						for (int k = 0; k < GATHER; ++k)
+							if (p + k < p1)
+								prod[k] = __dmul_rn(sv[p + k], __ldg(&x[sc[p + k]]));
+#pragma unroll
+						for (int k = 0; k < GATHER; ++k)
+							if (p + k < p1)
+								sum = __dadd_rn(sum, prod[k]);
+					}
+					emit(r0 + i, sum);
+				}
 			}
-		}
-		else {
-			// few long rows: warp per row, lanes stride the staged row, shuffle tree
-			const int lane = tid & 31, warp = tid >> 5;
-			for (int r = r0 + warp; r < r1; r += SPMV_THREADS / 32) {
-				const int p0 = static_cast<int>(static_cast<long long>(rowptr[r]) - za);
-				const int p1 = static_cast<int>(static_cast<long long>(rowptr[r + 1]) - za);
-				double sum = 0.0;
-				for (int p = p0 + lane; p < p1; p += 32)
-					sum = fma(sv[p], __ldg(&x[sc[p]]), sum);
-				sum = warp_fold<0>(sum);
-				if (lane == 0)
-					emit(r, sum);
+			else {
+				// few long rows: warp per row, lanes stride the staged row, shuffle tree
+				const int lane = ctid & 31, warp = ctid >> 5;
+				for (int i = warp; i < nrows; i += nconsumers / 32) {
+					const int q0 = static_cast<int>(static_cast<long long>(srp[roff + i]) - za);
+					const int q1 = static_cast<int>(static_cast<long long>(srp[roff + i + 1]) - za);
+					double sum = 0.0;
+					for (int p = q0 + lane; p < q1; p += 32)
+						sum = fma(sv[p], __ldg(&x[sc[p]]), sum);
+					sum = warp_fold<0>(sum);
+					if (lane == 0)
+						emit(r0 + i, sum);
+				}
 			}
+			__syncwarp();
+			if ((ctid & 31) == 0)
+				mbar_arrive(&empty[s]); // this warp is done reading stage s
 		}
-		__syncthreads(); // stage s may be overwritten by the prefetch issued next iteration
 	}
 
 	if constexpr (DOT) {
@@ -199,6 +273,29 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(const __grid_
 		if (tid == 0)
 			a.partials[blockIdx.x] = dot_acc;
 	}
+}
+
+__global__ void build_desc_kernel(const void * rowptr, bool wide, const int32_t * blk_row, int n_blk, blk_desc * out) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_blk)
+		return;
+	const int r0 = blk_row[b], r1 = blk_row[b + 1];
+	long long z0, z1;
+	if (wide) {
+		z0 = static_cast<const long long *>(rowptr)[r0];
+		z1 = static_cast<const long long *>(rowptr)[r1];
+	}
+	else {
+		z0 = static_cast<const int *>(rowptr)[r0];
+		z1 = static_cast<const int *>(rowptr)[r1];
+	}
+	blk_desc d;
+	d.z0 = z0;
+	d.r0 = r0;
+	d.nrows = r1 - r0;
+	d.nnz = static_cast<int>(z1 - z0);
+	d.pad = 0;
+	out[b] = d;
 }
 
 // one CTA: fold `n` partials in fixed order and publish like the element-wise epilogue
@@ -219,35 +316,45 @@ __global__ void __launch_bounds__(256) fold_partials_kernel(const double * parti
 }
 
 struct spmv_config {
-	int nstage;
-	int cap;
+	int nstage, threads, cap, rcap, grid;
 	size_t smem;
-	int grid;
 };
 
-static spmv_config configure(const csr_block & B) {
+static int env_int(const char * name, int dflt) {
+	const char * v = std::getenv(name);
+	return v ? std::atoi(v) : dflt;
+}
+
+static spmv_config configure(const fsb_ctx_s * c, const csr_block & B) {
+	static const int env_stages = env_int("FSB_SPMV_STAGES", 0);
+	static const int env_threads = env_int("FSB_SPMV_THREADS", 0);
+	static const int env_ctas = env_int("FSB_SPMV_CTAS_PER_SM", 0);
 	spmv_config k;
 	k.cap = ((B.max_blk_nnz + 8 + 3) / 4) * 4; // + alignment slack on both ends
 	if (k.cap < 64)
 		k.cap = 64;
-	const size_t stage_bytes = static_cast<size_t>(k.cap) * 12;
-	// aim for ~4 stages resident per SM in total: 2 CTAs x 2 stages when they fit
-	k.nstage = 2;
-	if (stage_bytes * 2 > 110 * 1024)
-		k.nstage = 1;
+	k.rcap = ((B.max_blk_rows + 1 + 8 + 3) / 4) * 4;
+	const size_t stage_bytes = static_cast<size_t>(k.cap) * 12 + static_cast<size_t>(k.rcap) * (B.wide ? 8 : 4);
+	// consumer threads: one per row of a block, at most 512
+	int consumers = env_threads > 0 ? env_threads : (c->spmv_threads > 0 ? c->spmv_threads : 512);
+	consumers = std::min(consumers, 512);
+	while (consumers > 64 && consumers / 2 >= B.max_blk_rows)
+		consumers /= 2;
+	k.threads = consumers + 32;
+	const size_t budget = 220 * 1024;
+	k.nstage = env_stages > 0 ? std::min(env_stages, 4) : 2;
+	while (k.nstage > 1 && stage_bytes * k.nstage > budget)
+		--k.nstage;
 	k.smem = stage_bytes * k.nstage;
-	int ctas_per_sm = static_cast<int>((220 * 1024) / (k.smem + 1024));
-	if (ctas_per_sm < 1)
-		ctas_per_sm = 1;
-	if (ctas_per_sm > 4)
-		ctas_per_sm = 4;
-	k.grid = std::min(B.n_blk, SM_COUNT * ctas_per_sm);
-	if (k.grid < 1)
-		k.grid = 1;
+	int ctas_per_sm = static_cast<int>(budget / (k.smem + 2048));
+	ctas_per_sm = std::max(1, std::min(ctas_per_sm, 2048 / k.threads));
+	if (env_ctas > 0)
+		ctas_per_sm = std::min(ctas_per_sm, env_ctas);
+	k.grid = std::max(1, std::min(B.n_blk, SM_COUNT * ctas_per_sm));
 	return k;
 }
 
-int spmv_partial_count(const csr_block & B) { return B.n_blk > 0 ? configure(B).grid : 0; }
+int spmv_partial_count(const fsb_ctx_s * c, const csr_block & B) { return B.n_blk > 0 ? configure(c, B).grid : 0; }
 
 template<class OffT, int NSTAGE, bool ACC, bool DOT, bool ROWLIST>
 static void launch_variant(const spmv_args & a, const spmv_config & k, cudaStream_t s) {
@@ -257,7 +364,7 @@ static void launch_variant(const spmv_args & a, const spmv_config & k, cudaStrea
 		FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
 		attr_set = true;
 	}
-	kern<<<k.grid, SPMV_THREADS, k.smem, s>>>(a);
+	kern<<<k.grid, k.threads, k.smem, s>>>(a);
 	FSB_CUDA(cudaGetLastError());
 }
 
@@ -283,19 +390,29 @@ static void launch_flags(const spmv_args & a, const spmv_config & k, bool acc, b
 	}
 }
 
+template<class OffT>
+static void launch_stages(const spmv_args & a, const spmv_config & k, bool acc, bool dot, bool rowlist, cudaStream_t s) {
+	switch (k.nstage) {
+	case 1: launch_flags<OffT, 1>(a, k, acc, dot, rowlist, s); break;
+	case 2: launch_flags<OffT, 2>(a, k, acc, dot, rowlist, s); break;
+	case 3: launch_flags<OffT, 3>(a, k, acc, dot, rowlist, s); break;
+	default: launch_flags<OffT, 4>(a, k, acc, dot, rowlist, s); break;
+	}
+}
+
 // y (+)= B x on stream s.  When dot_u != nullptr, CTA b writes its partial of sum y_i u_i
 // to d_partials[partial_offset + b].
 void launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
                  const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s) {
 	if (B.n_blk == 0)
 		return;
-	const spmv_config k = configure(B);
+	const spmv_config k = configure(c, B);
 	FSB_REQUIRE(k.smem <= 225 * 1024, "spmv: row block does not fit shared memory");
 	spmv_args a{};
 	a.rowptr = B.rowptr;
 	a.col = B.col;
 	a.val = B.val;
-	a.blk_row = B.blk_row;
+	a.desc = static_cast<const blk_desc *>(B.blk_desc);
 	a.row_ids = B.row_ids;
 	a.x = x;
 	a.y = y;
@@ -303,20 +420,13 @@ void launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * 
 	a.partials = d_partials ? d_partials + partial_offset : nullptr;
 	a.n_blk = B.n_blk;
 	a.cap = k.cap;
+	a.rcap = k.rcap;
 	const bool rowlist = B.row_ids != nullptr;
 	const bool dot = dot_u != nullptr;
-	if (B.wide) {
-		if (k.nstage == 2)
-			launch_flags<long long, 2>(a, k, accumulate, dot, rowlist, s);
-		else
-			launch_flags<long long, 1>(a, k, accumulate, dot, rowlist, s);
-	}
-	else {
-		if (k.nstage == 2)
-			launch_flags<int, 2>(a, k, accumulate, dot, rowlist, s);
-		else
-			launch_flags<int, 1>(a, k, accumulate, dot, rowlist, s);
-	}
+	if (B.wide)
+		launch_stages<long long>(a, k, accumulate, dot, rowlist, s);
+	else
+		launch_stages<int>(a, k, accumulate, dot, rowlist, s);
 	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
 }
 
@@ -335,11 +445,12 @@ void finalize_reduction(fsb_ctx_s * c, int n_partials, int64_t token, int /*op_k
 	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
 }
 
-// Row-block work descriptors.  host_rowptr == nullptr: uniform blocks of `rows_per_blk` rows
-// (caller guarantees they fit); otherwise greedy packing by nnz.
+// Row-block work descriptors.  host_rowptr == nullptr: uniform blocks (the caller left the row
+// width bound in B.max_blk_nnz); otherwise greedy packing by nnz.
 void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * host_rowptr) {
 	constexpr int CAP = 4096 - 8; // nnz staged per row block (48 KB per stage)
 	constexpr int ROWS_MAX = 512;
+	static const int env_rows = env_int("FSB_SPMV_ROWS", 0);
 	std::vector<int32_t> blk;
 	int max_nnz = 0, max_rows = 0;
 	if (B.n_rows == 0) {
@@ -367,16 +478,17 @@ void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * hos
 		blk.push_back(static_cast<int32_t>(B.n_rows));
 	}
 	else {
-		// uniform: caller stored the row width bound in max_blk_nnz (per row).  Aim for
-		// thread-per-row with every thread busy (multiples of 256 rows) within <= 96 KB a stage.
+		// Aim for thread-per-row with every thread busy (multiples of 256 rows), <= 96 KB a stage.
 		const int width = std::max(1, B.max_blk_nnz);
-		int rows = (4096 / width) / SPMV_THREADS * SPMV_THREADS;
-		if (rows < SPMV_THREADS)
-			rows = SPMV_THREADS;
+		int rows = (4096 / width) / 256 * 256;
+		if (rows < 256)
+			rows = 256;
 		if (rows * width > 8192)
 			rows = std::max(1, 8192 / width);
 		if (c->spmv_rows_per_cta > 0)
 			rows = c->spmv_rows_per_cta;
+		if (env_rows > 0)
+			rows = env_rows;
 		if (rows > 32)
 			rows = rows / 32 * 32;
 		for (int64_t r = 0; r < B.n_rows; r += rows)
@@ -390,6 +502,10 @@ void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * hos
 	B.max_blk_rows = max_rows;
 	FSB_CUDA(cudaMalloc(&B.blk_row, blk.size() * sizeof(int32_t)));
 	FSB_CUDA(cudaMemcpyAsync(B.blk_row, blk.data(), blk.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+	FSB_CUDA(cudaMalloc(&B.blk_desc, static_cast<size_t>(B.n_blk) * sizeof(blk_desc)));
+	build_desc_kernel<<<(B.n_blk + 255) / 256, 256, 0, c->stream>>>(B.rowptr, B.wide, B.blk_row, B.n_blk,
+	                                                               static_cast<blk_desc *>(B.blk_desc));
+	FSB_CUDA(cudaGetLastError());
 	FSB_CUDA(cudaStreamSynchronize(c->stream));
 }
 

@@ -1,0 +1,390 @@
+// libfsb_host.so: C entry points that run the flecsolve-shaped C++ host layer
+// (flecsolve_b200/include/flecsolve/...) over device vectors.  This is what a flecsolve
+// application does -- build an operator, make vectors and work vectors from field definitions,
+// bind a solver, call it -- compiled once so tests and bench.py can drive it through ctypes.
+// All arithmetic happens behind include/fsb.h; nothing here touches vector data on the host
+// except the explicit host-buffer copies of fsbh_solve.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "flecsolve/matrices/parcsr.hh"
+#include "flecsolve/operators/shell.hh"
+#include "flecsolve/solvers/bicgstab.hh"
+#include "flecsolve/solvers/cg.hh"
+#include "flecsolve/solvers/gmres.hh"
+#include "flecsolve/solvers/mg/jacobi.hh"
+#include "flecsolve/time-integrators/operator_adapter.hh"
+#include "flecsolve/vectors/multi.hh"
+
+using namespace flecsolve;
+
+namespace {
+
+using parcsr = mat::parcsr<double>;
+using csr_topo = parcsr::topo_t;
+using vec_def = csr_topo::vec_def<csr_topo::cols>;
+
+// field definitions of this "application" (static, like the reference's examples and tests)
+const vec_def bd, xd, diag_work_d;
+const vec_def b2d, x2d; // second component for the multi-vector driver
+
+thread_local std::string g_error;
+
+template<class F>
+int guarded(F && f) noexcept {
+	try {
+		f();
+		return 0;
+	}
+	catch (const device::error & e) {
+		g_error = e.what();
+		return e.code;
+	}
+	catch (const std::exception & e) {
+		g_error = e.what();
+		return 100;
+	}
+}
+
+struct session {
+	device::context ctx;
+	op::core<parcsr> A;
+	decltype(vec::make(bd(std::declval<csr_topo::topology &>()))) b, x;
+	// preconditioners are built once per session (their fields live on the topology)
+	std::unique_ptr<op::core<op::diagonal_inverse<double, std::size_t>>> dinv;
+
+	session(fsb_ctx_t c, fsb_parcsr_t a)
+		: ctx(c), A(ctx, a, false), b(vec::make(bd(A.data.topo()))), x(vec::make(xd(A.data.topo()))) {}
+};
+
+// per-iteration hook: residual history + CUDA-event marks for the timing window
+struct recorder {
+	fsb_ctx_t ctx;
+	double * history;
+	int cap;
+	int ev_start, ev_stop; // iteration numbers (1-based count of completed iterations) or -1
+	int count = 0;
+
+	template<class V>
+	bool operator()(const V &, double rnorm) {
+		if (history && count < cap)
+			history[count] = rnorm;
+		++count;
+		if (count == ev_start)
+			fsb_ctx_event_record(ctx, 0);
+		if (count == ev_stop)
+			fsb_ctx_event_record(ctx, 1);
+		return false;
+	}
+};
+
+}
+
+extern "C" {
+struct fsbh_info {
+	int status, iters, restarts;
+	float res_norm_initial, res_norm_final, sol_norm_initial, sol_norm_final, rhs_norm;
+	int callbacks; // times the diagnostic ran
+};
+
+struct fsbh_options {
+	int solver; // 0 cg, 1 gmres, 2 bicgstab, 3 fcg
+	int precond; // 0 identity (op::I), 1 diagonal inverse, 2 weighted Jacobi relaxation
+	float omega; // precond 2
+	int nrelax; // precond 2
+	int maxiter;
+	float rtol, atol;
+	int use_zero_guess;
+	int max_krylov_dim, restart, pre_side_left; // gmres
+	int ev_start, ev_stop; // record CUDA events 0 / 1 after this many iterations (-1: never)
+};
+
+}
+
+namespace {
+
+enum class var { first, second };
+
+// policy applying a parallel CSR matrix to vectors of any variable tag
+struct matrix_rhs : op::base<> {
+	const op::core<parcsr> * A;
+	explicit matrix_rhs(const op::core<parcsr> * a) : A(a) {}
+	template<class D, class R>
+	void apply(const D & x, R & y) const {
+		A->mult(x, y);
+	}
+};
+
+void fill(fsbh_info * out, const solve_info & i, int callbacks) {
+	out->status = static_cast<int>(i.status);
+	out->iters = i.iters;
+	out->restarts = i.restarts;
+	out->res_norm_initial = i.res_norm_initial;
+	out->res_norm_final = i.res_norm_final;
+	out->sol_norm_initial = i.sol_norm_initial;
+	out->sol_norm_final = i.sol_norm_final;
+	out->rhs_norm = i.rhs_norm;
+	out->callbacks = callbacks;
+}
+
+template<class S, class P>
+solve_info run_solver(session & S_, const fsbh_options & o, P precond_handle, recorder & rec) {
+	auto & A = S_.A;
+	auto & b = S_.b;
+	auto & x = S_.x;
+	(void)sizeof(S);
+	if (o.solver == 0) {
+		auto slv = cg::solver(cg::settings{o.maxiter, o.rtol, o.atol, o.use_zero_guess != 0},
+		                      cg::make_work(x))(op::ref(A), precond_handle, std::ref(rec));
+		return slv(b, x);
+	}
+	if (o.solver == 3) {
+		auto slv = fcg::solver(fcg::settings{o.maxiter, o.rtol, o.atol, o.use_zero_guess != 0},
+		                       fcg::make_work(x))(op::ref(A), precond_handle, std::ref(rec));
+		return slv(b, x);
+	}
+	if (o.solver == 2) {
+		bicgstab::settings st{{o.maxiter, o.rtol, o.atol, o.use_zero_guess != 0}};
+		auto slv = bicgstab::solver(st, bicgstab::make_work(x))(op::ref(A), precond_handle, std::ref(rec));
+		return slv(b, x);
+	}
+	gmres::settings st{{o.maxiter, o.rtol, o.atol, o.use_zero_guess != 0},
+	                   o.max_krylov_dim,
+	                   o.pre_side_left ? gmres::precond_side::left : gmres::precond_side::right,
+	                   o.restart != 0};
+	auto slv = gmres::solver(st, gmres::make_work(x))(op::ref(A), precond_handle, std::ref(rec));
+	return slv(b, x);
+}
+
+}
+
+extern "C" {
+
+const char * fsbh_last_error(void) { return g_error.c_str(); }
+
+int fsbh_session_create(fsb_ctx_t ctx, fsb_parcsr_t A, void ** out) {
+	return guarded([&] { *out = new session(ctx, A); });
+}
+
+int fsbh_session_destroy(void * s) {
+	return guarded([&] { delete static_cast<session *>(s); });
+}
+
+fsb_vec_t fsbh_session_b(void * s) { return static_cast<session *>(s)->b.data.handle(); }
+fsb_vec_t fsbh_session_x(void * s) { return static_cast<session *>(s)->x.data.handle(); }
+
+// Solve A x = b.  b_host / x_host may be null: then the session's device vectors (fsbh_session_b/x)
+// are used as they are.  Otherwise b is uploaded, x is uploaded (initial guess) and downloaded.
+int fsbh_solve(void * sv, const fsbh_options * o, const double * b_host, double * x_host, fsbh_info * info,
+               double * history, int history_cap) {
+	return guarded([&] {
+		session & S = *static_cast<session *>(sv);
+		const std::int64_t n = fsb_vec_local_size(S.b.data.handle());
+		if (b_host)
+			device::check(fsb_vec_upload(S.b.data.handle(), b_host, n, 0));
+		if (x_host && !o->use_zero_guess)
+			device::check(fsb_vec_upload(S.x.data.handle(), x_host, n, 0));
+		recorder rec{S.ctx.handle(), history, history_cap, o->ev_start, o->ev_stop};
+		solve_info si;
+		if (o->precond == 1) {
+			if (!S.dinv)
+				S.dinv = std::make_unique<op::core<op::diagonal_inverse<double, std::size_t>>>(S.A);
+			si = run_solver<int>(S, *o, op::ref(*S.dinv), rec);
+		}
+		else if (o->precond == 2) {
+			auto P = mg::jacobi{{o->omega, static_cast<std::size_t>(o->nrelax)}}(op::ref(S.A));
+			// relaxation does not zero its output first (mg/jacobi.hh:58-93); as a preconditioner it
+			// is applied to a zeroed vector like the multigrid cycles do
+			auto Pz = op::make_shell([&P](const auto & r, auto & z) {
+				z.set_scalar(0.0);
+				P.apply(r, z);
+			});
+			si = run_solver<int>(S, *o, op::ref(Pz), rec);
+		}
+		else {
+			si = run_solver<int>(S, *o, op::I, rec);
+		}
+		if (x_host)
+			device::check(fsb_vec_download(S.x.data.handle(), x_host, n, 0));
+		else
+			S.ctx.sync();
+		fill(info, si, rec.count);
+	});
+}
+
+// y = (I - gamma A) x through time_integrator::operator_adapter (host buffers in/out)
+int fsbh_adapter_apply(void * sv, double gamma, const double * x_host, double * y_host) {
+	return guarded([&] {
+		session & S = *static_cast<session *>(sv);
+		const std::int64_t n = fsb_vec_local_size(S.b.data.handle());
+		device::check(fsb_vec_upload(S.x.data.handle(), x_host, n, 0));
+		op::core<time_integrator::operator_adapter<matrix_rhs>> F(&S.A);
+		F.set_scaling(gamma);
+		F.apply(S.x, S.b);
+		device::check(fsb_vec_download(S.b.data.handle(), y_host, n, 0));
+	});
+}
+
+// CG on a two-component vec::multi with the block-diagonal operator diag(A, A2): the shape of the
+// reference's cgmulti test (solvers/test/cgmulti.cc:28-77) and of examples/equilibrium_diffusion.
+// solver: 0 cg, 2 bicgstab.  Host buffers b = [b0 | b1], x = [x0 | x1].
+int fsbh_solve_multi2(fsb_ctx_t ctx_h, fsb_parcsr_t A0h, fsb_parcsr_t A1h, const fsbh_options * o, const double * b_host,
+                      double * x_host, fsbh_info * info, double * history, int history_cap) {
+	return guarded([&] {
+		device::context ctx(ctx_h);
+		op::core<parcsr> A0(ctx, A0h, false), A1(ctx, A1h, false);
+		auto b0 = vec::make(variable<var::first>, bd(A0.data.topo()));
+		auto x0 = vec::make(variable<var::first>, xd(A0.data.topo()));
+		auto b1 = vec::make(variable<var::second>, b2d(A1.data.topo()));
+		auto x1 = vec::make(variable<var::second>, x2d(A1.data.topo()));
+		const std::int64_t n0 = fsb_vec_local_size(b0.data.handle()), n1 = fsb_vec_local_size(b1.data.handle());
+		device::check(fsb_vec_upload(b0.data.handle(), b_host, n0, 0));
+		device::check(fsb_vec_upload(b1.data.handle(), b_host + n0, n1, 0));
+		device::check(fsb_vec_upload(x0.data.handle(), x_host, n0, 0));
+		device::check(fsb_vec_upload(x1.data.handle(), x_host + n0, n1, 0));
+		vec::multi b(b0, b1), x(x0, x1);
+
+		auto blockdiag = op::make_shell(
+			[&](const auto & xin, auto & yout) {
+				A0.mult(xin.subset(variable<var::first>), yout.subset(variable<var::first>));
+				A1.mult(xin.subset(variable<var::second>), yout.subset(variable<var::second>));
+			},
+			multivariable<var::first, var::second>, multivariable<var::first, var::second>);
+
+		recorder rec{ctx_h, history, history_cap, -1, -1};
+		solve_info si;
+		if (o->solver == 2) {
+			bicgstab::settings st{{o->maxiter, o->rtol, o->atol, o->use_zero_guess != 0}};
+			auto slv = bicgstab::solver(st, bicgstab::make_work(x))(
+				op::ref(blockdiag),
+				op::make_identity(multivariable<var::first, var::second>, multivariable<var::first, var::second>),
+				std::ref(rec));
+			si = slv(b, x);
+		}
+		else {
+			auto slv = cg::solver(cg::settings{o->maxiter, o->rtol, o->atol, o->use_zero_guess != 0}, cg::make_work(x))(
+				op::ref(blockdiag),
+				op::make_identity(multivariable<var::first, var::second>, multivariable<var::first, var::second>),
+				std::ref(rec));
+			si = slv(b, x);
+		}
+		device::check(fsb_vec_download(x0.data.handle(), x_host, n0, 0));
+		device::check(fsb_vec_download(x1.data.handle(), x_host + n0, n1, 0));
+		fill(info, si, rec.count);
+	});
+}
+
+// CG bound to ONE variable of a two-component multi-vector: slv(bm, xm) must pick the component
+// through subset() and iterate exactly like the single-vector solve (solvers/test/cgmulti.cc:63-76).
+// Both components live on A's topology; b = [b_first | b_second], x likewise; `which` selects.
+int fsbh_solve_subset(fsb_ctx_t ctx_h, fsb_parcsr_t Ah, int which, const fsbh_options * o, const double * b_host,
+                      double * x_host, fsbh_info * info) {
+	return guarded([&] {
+		device::context ctx(ctx_h);
+		op::core<parcsr> A(ctx, Ah, false);
+		auto b0 = vec::make(variable<var::first>, bd(A.data.topo()));
+		auto x0 = vec::make(variable<var::first>, xd(A.data.topo()));
+		auto b1 = vec::make(variable<var::second>, b2d(A.data.topo()));
+		auto x1 = vec::make(variable<var::second>, x2d(A.data.topo()));
+		const std::int64_t n = fsb_vec_local_size(b0.data.handle());
+		device::check(fsb_vec_upload(b0.data.handle(), b_host, n, 0));
+		device::check(fsb_vec_upload(b1.data.handle(), b_host + n, n, 0));
+		device::check(fsb_vec_upload(x0.data.handle(), x_host, n, 0));
+		device::check(fsb_vec_upload(x1.data.handle(), x_host + n, n, 0));
+		auto bm = vec::make(b0, b1);
+		auto xm = vec::make(x0, x1);
+		const cg::settings st{o->maxiter, o->rtol, o->atol, o->use_zero_guess != 0};
+		solve_info si;
+		auto run = [&](auto tag) {
+			auto op1 = op::make_shell([&A](const auto & xin, auto & yout) { A.mult(xin, yout); }, tag, tag);
+			auto slv = cg::solver(st, cg::make_work(bm.subset(tag)))(op::ref(op1));
+			si = slv(bm, xm);
+		};
+		if (which == 0)
+			run(variable<var::first>);
+		else
+			run(variable<var::second>);
+		device::check(fsb_vec_download(x0.data.handle(), x_host, n, 0));
+		device::check(fsb_vec_download(x1.data.handle(), x_host + n, n, 0));
+		fill(info, si, 0);
+	});
+}
+
+// The vector-operation sequence of the reference's unit test (vectors/test/flecsi_vector.cc:324-392)
+// on device vectors of global size n with x = gid, y = 2 gid, z = 3 gid.  err[k] = sum_i |got - expected|
+// for each checked operation (order: add, subtract, multiply, add_scalar, divide, scale, reciprocal,
+// linear_sum, axpy, axpby, abs), then min, max, dot error, l1 error, l2 error.
+int fsbh_vector_selftest(void * sv, double * err16) {
+	return guarded([&] {
+		session & S = *static_cast<session *>(sv);
+		auto & topo = S.A.data.topo();
+		static const vec_def xd_, yd_, zd_, tmpd_;
+		auto [x, y, z, tmp] = vec::make(topo)(xd_, yd_, zd_, tmpd_);
+		const std::int64_t n = fsb_vec_local_size(x.data.handle());
+		const std::int64_t g0 = topo.meta().rows.beg;
+		std::vector<double> hx(n), hy(n), hz(n), got(n);
+		for (std::int64_t i = 0; i < n; ++i) {
+			const double gid = static_cast<double>(g0 + i);
+			hx[i] = gid;
+			hy[i] = 2 * gid;
+			hz[i] = 3 * gid;
+		}
+		device::check(fsb_vec_upload(x.data.handle(), hx.data(), n, 0));
+		device::check(fsb_vec_upload(y.data.handle(), hy.data(), n, 0));
+		device::check(fsb_vec_upload(z.data.handle(), hz.data(), n, 0));
+		int k = 0;
+		auto check = [&](auto & v, auto expect) {
+			device::check(fsb_vec_download(v.data.handle(), got.data(), n, 0));
+			double e = 0;
+			for (std::int64_t i = 0; i < n; ++i)
+				e += std::abs(expect(static_cast<double>(g0 + i)) - got[i]);
+			err16[k++] = e;
+		};
+		auto X = [](double g) { return g; };
+		auto Y = [](double g) { return 2 * g; };
+		auto Z = [](double g) { return 3 * g; };
+		tmp.add(x, z);
+		check(tmp, [&](double g) { return X(g) + Z(g); });
+		tmp.subtract(x, z);
+		check(tmp, [&](double g) { return X(g) - Z(g); });
+		tmp.multiply(x, z);
+		check(tmp, [&](double g) { return X(g) * Z(g); });
+		x.add_scalar(x, 1);
+		check(x, [&](double g) { return X(g) + 1; });
+		tmp.divide(y, x);
+		check(tmp, [&](double g) { return Y(g) / (X(g) + 1); });
+		x.add_scalar(x, -1);
+		tmp.scale(2, x);
+		check(tmp, [&](double g) { return X(g) * 2; });
+		y.add_scalar(y, 1);
+		tmp.reciprocal(y);
+		check(tmp, [&](double g) { return 1.0 / (Y(g) + 1); });
+		y.add_scalar(y, -1);
+		tmp.linear_sum(8, y, 9, z);
+		check(tmp, [&](double g) { return Y(g) * 8 + Z(g) * 9; });
+		tmp.axpy(7, x, y);
+		check(tmp, [&](double g) { return X(g) * 7 + Y(g); });
+		tmp.copy(y);
+		tmp.axpby(4, 11, z);
+		check(tmp, [&](double g) { return Z(g) * 4 + Y(g) * 11; });
+		tmp.add_scalar(y, -4);
+		tmp.abs(tmp);
+		check(tmp, [&](double g) { return std::abs(Y(g) - 4); });
+		tmp.add_scalar(y, -7);
+		err16[k++] = tmp.min().get(); // -7 on the rank owning gid 0
+		err16[k++] = z.max().get(); // 3 (n_global - 1)
+		const double N = static_cast<double>(x.global_size().get());
+		x.set_scalar(1.5);
+		y.set_scalar(3.8);
+		err16[k++] = std::abs(x.dot(y).get() - N * 1.5 * 3.8);
+		x.set_scalar(-3.141719);
+		err16[k++] = std::abs(x.l1norm().get() - N * 3.141719);
+		err16[k++] = std::abs(x.l2norm().get() - std::sqrt(N * 3.141719 * 3.141719));
+	});
+}
+
+} // extern "C"

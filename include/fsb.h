@@ -88,6 +88,10 @@ int fsb_ctx_get_stat(fsb_ctx_t ctx, int stat, int64_t * out);
 int fsb_ctx_reset_stats(fsb_ctx_t ctx);
 /* overwrite >= bytes of scratch so the L2 holds none of the caller's data */
 int fsb_ctx_flush_l2(fsb_ctx_t ctx);
+/* CUDA-event timing on the context's stream (the stream the kernels run on): record flushes the
+ * queue, then records event `slot` (0..15); elapsed blocks until both events completed.          */
+int fsb_ctx_event_record(fsb_ctx_t ctx, int slot);
+int fsb_ctx_event_elapsed_ms(fsb_ctx_t ctx, int slot_start, int slot_stop, double * ms);
 
 /* ---- vectors -----------------------------------------------------------
  * A vector is the device image of one field on the reference's `cols' index

@@ -326,7 +326,7 @@ Info bicgstab(const System & S, int maxiter, float rtol, bool use_zero_guess, co
 		return info;
 	}
 	double alpha = 1.0, beta = 0.0, omega = 1.0;
-	double rho[2] = {1.0, 1.0};
+	double rho[2] = {2.0, 1.0}; // std::vector<real> rho{2, 1.0} is the list {2.0, 1.0}
 	V.copy(r_tilde, res);
 	V.set(p, 0.);
 	V.set(v, 0.);
