@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Headline benchmark: fp64 Jacobi-preconditioned CG on the synthetic 7-point 3-D Poisson system
+256^3 (BASELINE.json configs[1]), row-sharded over N GPUs (z-slabs, strong scaling).
+
+  python bench.py --gpus N --steps K --warmup W            this repo (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N ...            the reference's CPU path (oracle restatement)
+
+A "step" is one CG iteration.  Rank 0 prints ONE JSON line; see README/DESIGN.md for the fields.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (stencil kind, nx, ny, nz, preconditioner)
+    "poisson7_256": (7, 256, 256, 256, "dinv"),
+    "poisson27_512": (27, 512, 512, 512, "dinv"),
+    "poisson27_256": (27, 256, 256, 256, "dinv"),
+    "poisson7_128": (7, 128, 128, 128, "dinv"),
+    "poisson5_2d_256": (5, 256, 256, 1, None),
+}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def x_true(g0: int, n: int) -> np.ndarray:
+    """x_true(g) = 1 + (h mod 1000)/1000, h = (uint32)(g * 2654435761)."""
+    g = np.arange(g0, g0 + n, dtype=np.uint64)
+    h = (g * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)
+    return 1.0 + (h % np.uint64(1000)).astype(np.float64) / 1000.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            # "under load": the upper half of the samples (the timed region keeps the GPU busy)
+            s = sorted(sm)
+            out.update(sm_mhz=float(np.median(s[len(s) // 2:])), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def pinned(n: int) -> np.ndarray:
+    import torch
+    return torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+
+
+def run_ours(args):
+    from flecsolve_b200 import _lib as F
+    from flecsolve_b200 import dist as D
+    from flecsolve_b200 import host as H
+
+    world = D.init(D.world_from_env())
+    if world.size != args.gpus:
+        if world.size == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    kind, nx, ny, nz, precond = WORKLOADS[args.workload]
+    ctx = D.make_context(world)
+    t0 = time.time()
+    A = F.ParCSR.stencil(ctx, kind, nx, ny, nz)
+    ctx.sync()
+    n_local, n_global = A.local_rows, A.global_rows
+    nnz_local = A.nnz(0) + A.nnz(1)
+    nnz_global = int(D.sum_over_ranks(world, nnz_local))
+    S = H.Session(ctx, A)
+    # b = A x_true computed on the device; x0 = 0
+    xt = A.vector(x_true(A.row_begin, n_local))
+    A.spmv(xt, S.b)
+    ctx.sync()
+    xt.destroy()
+    setup_s = time.time() - t0
+
+    W, K = args.warmup, args.steps
+    ctx.set_option("profile", 1)
+
+    # ---- device-resident timing: iterations W+1 .. W+K of one solve, CUDA events on the library's stream
+    def timed_solve():
+        S.x.zero()
+        ctx.sync()
+        ctx.profile_read()
+        D.barrier(world)
+        _, info, _ = S.solve(solver="cg", precond=precond, maxiter=W + K, rtol=0.0, ev_start=W, ev_stop=W + K)
+        ctx.sync()
+        D.barrier(world)
+        ms = ctx.event_elapsed_ms(0, 1)
+        spmv_ms, spmv_n = ctx.profile_read()
+        return ms, info, spmv_ms, spmv_n
+
+    timed_solve()  # cold pass: allocations, occupancy queries, NCCL channels
+    sampler = ClockSampler(world.local_rank).start() if world.is_root else None
+    ms, info, spmv_ms, spmv_n = timed_solve()
+    clocks = sampler.stop() if sampler else {}
+    ms = D.max_over_ranks(world, ms)
+    ms_per_step = ms / K
+    value = 1000.0 / ms_per_step
+
+    # ---- end to end: full solve to rtol 1e-9 through the host-buffer call (H2D b, x0; D2H x)
+    ctx.set_option("profile", 0)
+    b_host, x_host = pinned(n_local), pinned(n_local)
+    b_host[:] = S.b.download()
+    e2e_iters, e2e_s = 0, 0.0
+    for rep in range(2):  # first rep warms the pinned buffers / page tables
+        x_host[:] = 0.0
+        ctx.sync()
+        D.barrier(world)
+        t1 = time.perf_counter()
+        x_out, einfo, _ = S.solve(b_host, x_host, solver="cg", precond=precond, maxiter=5000, rtol=1e-9)
+        dt = time.perf_counter() - t1
+        e2e_s = D.max_over_ranks(world, dt)
+        e2e_iters = einfo.iters
+    err = float(np.abs(x_out - x_true(A.row_begin, n_local)).max())
+    err = D.max_over_ranks(world, err)
+    e2e_value = e2e_iters / e2e_s if e2e_s > 0 and e2e_iters > 0 else 0.0
+
+    peak, peak_src = measured_peak_gbs()
+    N, nnz = n_local, nnz_local
+    off = 8 if nnz >= 2 ** 31 - 16 else 4
+    spmv_bytes = 12 * nnz + off * (N + 1) + 16 * N + 8 * A.num_ghosts
+    iter_bytes = 12 * nnz + off * N + (108 - 4) * N + 8 * A.num_ghosts  # 12 nnz + 108 N (int32 offsets)
+    spmv_avg_ms = spmv_ms / max(spmv_n, 1)
+    spmv_gbs = spmv_bytes / spmv_avg_ms / 1e6 if spmv_avg_ms > 0 else 0.0
+    iter_gbs = iter_bytes / ms_per_step / 1e6
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_spmv_ncu_summary.json")
+    if os.path.exists(tp) and args.workload == "poisson7_256" and world.size == 1:
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    line = {
+        "metric": "cg_iterations_per_second",
+        "value": value,
+        "unit": "iterations/s",
+        "n_gpus": world.size,
+        "steps": K,
+        "warmup": W,
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {kind}-point Poisson {nx}x{ny}x{nz}, parallel CSR (fp64 values, int32 columns), "
+                        f"{'Jacobi (1/diag)' if precond else 'un'}preconditioned CG, b = A x_true, x0 = 0",
+            "rows": n_global, "nnz": nnz_global, "partition": f"{world.size} z-slab(s) of {n_local} rows",
+            "l2_policy": "inputs larger than L2 (per-iteration working set %.2f GB >> 126 MB)" % (iter_bytes / 1e9),
+            "timed": f"iterations {W + 1}..{W + K} of one solve (rtol 0), CUDA events on the library stream, max over ranks",
+        },
+        "roofline": {
+            "bound": "hbm", "kernel": "spmv_stream_kernel (y = A p fused with p.Ap)",
+            "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak, "traffic": traffic,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
+            "launches_timed": spmv_n, "share_of_step": spmv_avg_ms / ms_per_step if ms_per_step > 0 else None,
+            "iteration": {"algorithmic_bytes": iter_bytes, "achieved": iter_gbs, "frac": iter_gbs / peak,
+                          "frac_of_nominal_8TBs": iter_gbs / 8000.0},
+        },
+        "e2e": {
+            "value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": 16 * n_local / max(e2e_iters, 1),
+            "d2h_bytes_per_step": 8 * n_local / max(e2e_iters, 1), "iterations": e2e_iters, "seconds": e2e_s,
+            "what": "fsbh_solve with pinned host b, x0 in and x out, rtol 1e-9f, wall clock around the call",
+            "max_abs_error_vs_x_true": err,
+        },
+        "gpu_launches": int(info.window_launches),
+        "clocks": clocks,
+        "setup_seconds": setup_s,
+    }
+    if world.is_root and world.size == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.workload, sample_iters=args.cpu_iters)
+    S.close()
+    A.destroy()
+    ctx.close()
+    if world.is_root:
+        print(json.dumps(line), flush=True)
+    D.finalize(world)
+
+
+def cpu_baseline(workload: str, sample_iters: int, warm: int = 2) -> dict:
+    """The reference's CPU path (oracle restatement: size_t indices, diag/offd split + add pass,
+    one pass per vector op, 3 blocking reductions per iteration) on the host cores of this box."""
+    import oracle as O
+    kind, nx, ny, nz, precond = WORKLOADS[workload]
+    threads = O.max_threads()
+    rp, col, val = O.stencil_csr(kind, nx, ny, nz)
+    M = O.ParCSR(rp, col, val, colours=threads)  # one colour per thread, like one MPI rank per core
+    n = len(rp) - 1
+    b = M.spmv(x_true(0, n))
+    dinv = M.dinv() if precond else None
+    M.cg(b, dinv=dinv, maxiter=warm, rtol=0.0)  # page in
+    t0 = time.perf_counter()
+    _, info, _ = M.cg(b, dinv=dinv, maxiter=sample_iters, rtol=0.0)
+    dt = time.perf_counter() - t0
+    return {"value": sample_iters / dt, "unit": "iterations/s", "cores": threads, "kind": "port",
+            "sample": f"first {sample_iters} CG iterations of the same system (x0 = 0), {threads} OpenMP threads = colours, "
+                      f"{dt:.1f} s", "seconds": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path is not buildable here
+    (needs FleCSI/MPI/Boost), so this times its line-faithful restatement under oracle/."""
+    from flecsolve_b200 import dist as D
+    world = D.world_from_env()
+    if world.rank != 0:
+        return
+    iters = max(1, min(args.steps, args.cpu_iters_cap))
+    base = cpu_baseline(args.workload, sample_iters=iters, warm=max(1, min(args.warmup, 3)))
+    kind, nx, ny, nz, precond = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference",
+        "metric": "cg_iterations_per_second", "value": base["value"], "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": iters, "warmup": min(args.warmup, 3), "ms_per_step": 1000.0 / base["value"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {kind}-point Poisson {nx}x{ny}x{nz}, reference CPU path restated "
+                               f"(oracle/oracle.cpp), {'Jacobi' if precond else 'un'}preconditioned CG"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="poisson7_256", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-iters", type=int, default=40, help="CG iterations of the CPU baseline sample")
+    ap.add_argument("--cpu-iters-cap", type=int, default=60)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,7 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_ctx_flush_l2", C.c_int, _p)
     f("fsb_ctx_event_record", C.c_int, _p, C.c_int)
     f("fsb_ctx_event_elapsed_ms", C.c_int, _p, C.c_int, C.c_int, _pd)
+    f("fsb_ctx_profile_read", C.c_int, _p, _pd, _pi64)
     f("fsb_vec_create", C.c_int, _p, _i64, _i64, C.POINTER(_p))
     f("fsb_vec_wrap", C.c_int, _p, _p, _i64, _i64, C.POINTER(_p))
     f("fsb_vec_destroy", C.c_int, _p)
@@ -146,7 +147,7 @@ def device_count() -> int:
 
 STAT = {"launches": 0, "fused_statements": 1, "halo_exchanges": 2, "allreduces": 3, "host_syncs": 4,
         "unmatched_groups": 5}
-OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3}
+OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3, "profile": 4}
 
 
 class Context:
@@ -184,6 +185,12 @@ class Context:
         out = _dbl()
         check(lib().fsb_ctx_event_elapsed_ms(self.h, a, b, C.byref(out)))
         return out.value
+
+    def profile_read(self):
+        """(total SpMV kernel ms, launches) since the last read; needs set_option('profile', 1)."""
+        ms, cnt = _dbl(), _i64()
+        check(lib().fsb_ctx_profile_read(self.h, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     @property
     def stream(self) -> int:

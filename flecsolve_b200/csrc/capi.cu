@@ -137,6 +137,8 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 		for (auto e : c->timers)
 			if (e)
 				cudaEventDestroy(e);
+		for (auto e : c->prof_events)
+			cudaEventDestroy(e);
 		cudaFree(c->d_partials);
 		cudaFree(c->d_counter);
 		cudaFree(c->d_results);
@@ -183,6 +185,9 @@ int fsb_ctx_set_option(fsb_ctx_t c, int option, int64_t value) {
 			break;
 		case FSB_OPT_TRACE:
 			c->trace = value != 0;
+			break;
+		case FSB_OPT_PROFILE:
+			c->profile = value != 0;
 			break;
 		default:
 			throw fsb::error(FSB_ERR_ARG, "unknown option");
@@ -233,6 +238,23 @@ int fsb_ctx_event_elapsed_ms(fsb_ctx_t c, int a, int b, double * ms) {
 		float t = 0;
 		FSB_CUDA(cudaEventElapsedTime(&t, c->timers[a], c->timers[b]));
 		*ms = t;
+	});
+}
+
+int fsb_ctx_profile_read(fsb_ctx_t c, double * spmv_ms, int64_t * spmv_launches) {
+	return guarded([&] {
+		FSB_REQUIRE(c && spmv_ms && spmv_launches, "bad arguments");
+		flush(c);
+		double total = 0;
+		for (size_t k = 0; k + 1 < c->prof_used; k += 2) {
+			FSB_CUDA(cudaEventSynchronize(c->prof_events[k + 1]));
+			float t = 0;
+			FSB_CUDA(cudaEventElapsedTime(&t, c->prof_events[k], c->prof_events[k + 1]));
+			total += t;
+		}
+		*spmv_ms = total;
+		*spmv_launches = static_cast<int64_t>(c->prof_used / 2);
+		c->prof_used = 0;
 	});
 }
 

@@ -99,6 +99,9 @@ struct fsb_ctx_s {
 	int spmv_threads = 0;
 
 	cudaEvent_t timers[16] = {};
+	bool profile = false;
+	std::vector<cudaEvent_t> prof_events; // pairs: [2k] start, [2k+1] stop
+	size_t prof_used = 0;
 
 	// L2 flush scratch
 	void * d_flush = nullptr;
@@ -169,9 +172,8 @@ void flush(fsb_ctx_s * c);
 int64_t new_token(fsb_ctx_s * c, int nccl_op);
 
 // kernels (declared here, defined in their .cu)
-void launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
-                 const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s);
-int spmv_partial_count(const fsb_ctx_s * c, const csr_block & B);
+int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
+                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s);
 void finalize_reduction(fsb_ctx_s * c, int n_partials, int64_t token, int op_kind);
 void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x);
 

@@ -220,15 +220,13 @@ void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot) {
 		fsb_vec_s * other = dot->x == y ? dot->y : dot->x;
 		u = other->d; // other == y gives sum y^2
 	}
-	const int np_diag = u ? spmv_partial_count(c, A->diag) : 0;
-	launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream);
+	const int np_diag = launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream);
 	int np_offd = 0;
 	if (A->offd.n_blk > 0) {
 		if (!waited)
 			FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
 		waited = true;
-		np_offd = u ? spmv_partial_count(c, A->offd) : 0;
-		launch_spmv(c, A->offd, x->d, y->d, true, u, c->d_partials, np_diag, c->stream);
+		np_offd = launch_spmv(c, A->offd, x->d, y->d, true, u, c->d_partials, np_diag, c->stream);
 	}
 	if (!waited) // ghosts were requested but no row uses them: still order the streams
 		FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));

@@ -30,7 +30,7 @@
 namespace fsb {
 
 constexpr int SPMV_MAX_THREADS = 544; // 512 consumer threads + one producer warp
-constexpr int GATHER = 16;
+constexpr int GATHER = 8;
 
 // one row block = the unit of work of a pipeline stage
 struct blk_desc {
@@ -97,7 +97,7 @@ __device__ __forceinline__ void consumer_sync(int nconsumers) {
 // runs up to NSTAGE row blocks ahead, throttled by the `empty` barriers); all other warps are
 // consumers (wait `full`, multiply thread-per-row out of shared memory, release the stage).
 template<class OffT, int NSTAGE, bool ACC, bool DOT, bool ROWLIST>
-__global__ void __launch_bounds__(SPMV_MAX_THREADS) spmv_stream_kernel(const __grid_constant__ spmv_args a) {
+__global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const __grid_constant__ spmv_args a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint64_t full[NSTAGE], empty[NSTAGE];
 	__shared__ blk_desc sdesc[NSTAGE];
@@ -228,8 +228,9 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS) spmv_stream_kernel(const __g
 					}
 				}
 			}
-			else if (nrows * 8 >= nconsumers || nrows >= cnt) {
-				// thread per row, consecutive lanes on consecutive rows; in-order accumulation
+			else if (cnt <= static_cast<long long>(nrows) * 64) {
+				// short rows (average <= 64 entries): thread per row, consecutive lanes on consecutive
+				// rows; in-order accumulation
 				for (int i = ctid; i < nrows; i += nconsumers) {
 					const int p0 = static_cast<int>(static_cast<long long>(srp[roff + i]) - za);
 					const int p1 = static_cast<int>(static_cast<long long>(srp[roff + i + 1]) - za);
@@ -341,71 +342,86 @@ static spmv_config configure(const fsb_ctx_s * c, const csr_block & B) {
 	while (consumers > 64 && consumers / 2 >= B.max_blk_rows)
 		consumers /= 2;
 	k.threads = consumers + 32;
+	// Measured on B200 (profiles/r1_spmv_sweep.txt): throughput follows the number of resident
+	// consumer threads (>= 1024 per SM saturates HBM); a second stage only pays when it does not
+	// cost resident CTAs.
 	const size_t budget = 220 * 1024;
-	k.nstage = env_stages > 0 ? std::min(env_stages, 4) : 2;
+	const size_t ctas_for_1024 = (1024 + consumers - 1) / consumers;
+	k.nstage = (2 * stage_bytes * ctas_for_1024 <= budget) ? 2 : 1;
+	if (env_stages > 0)
+		k.nstage = std::min(env_stages, 4);
 	while (k.nstage > 1 && stage_bytes * k.nstage > budget)
 		--k.nstage;
 	k.smem = stage_bytes * k.nstage;
-	int ctas_per_sm = static_cast<int>(budget / (k.smem + 2048));
-	ctas_per_sm = std::max(1, std::min(ctas_per_sm, 2048 / k.threads));
-	if (env_ctas > 0)
-		ctas_per_sm = std::min(ctas_per_sm, env_ctas);
-	k.grid = std::max(1, std::min(B.n_blk, SM_COUNT * ctas_per_sm));
+	k.grid = env_ctas; // optional cap on resident CTAs per SM; the launcher asks the occupancy API
 	return k;
 }
 
-int spmv_partial_count(const fsb_ctx_s * c, const csr_block & B) { return B.n_blk > 0 ? configure(c, B).grid : 0; }
-
 template<class OffT, int NSTAGE, bool ACC, bool DOT, bool ROWLIST>
-static void launch_variant(const spmv_args & a, const spmv_config & k, cudaStream_t s) {
+static int launch_variant(const spmv_args & a, const spmv_config & k, cudaStream_t s) {
 	auto kern = spmv_stream_kernel<OffT, NSTAGE, ACC, DOT, ROWLIST>;
-	static bool attr_set = false;
-	if (!attr_set) {
+	// resident CTAs per SM for this (threads, smem): persistent grid = exactly one wave
+	static int cached_threads = -1, cached_ctas = 0;
+	static size_t cached_smem = 0;
+	if (cached_threads != k.threads || cached_smem != k.smem) {
 		FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-		attr_set = true;
+		int nb = 0;
+		FSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, k.threads, k.smem));
+		FSB_REQUIRE(nb >= 1, "spmv: kernel does not fit on an SM");
+		cached_threads = k.threads;
+		cached_smem = k.smem;
+		cached_ctas = nb;
+		if (std::getenv("FSB_SPMV_DEBUG"))
+			fprintf(stderr, "[fsb] spmv config: threads %d stages %d smem %zu B cap %d -> %d CTAs/SM\n", k.threads, NSTAGE,
+			        k.smem, k.cap, nb);
 	}
-	kern<<<k.grid, k.threads, k.smem, s>>>(a);
+	int ctas = cached_ctas;
+	if (k.grid > 0)
+		ctas = std::min(ctas, k.grid);
+	const int grid = std::max(1, std::min(a.n_blk, SM_COUNT * ctas));
+	kern<<<grid, k.threads, k.smem, s>>>(a);
 	FSB_CUDA(cudaGetLastError());
+	return grid;
 }
 
 template<class OffT, int NSTAGE>
-static void launch_flags(const spmv_args & a, const spmv_config & k, bool acc, bool dot, bool rowlist, cudaStream_t s) {
+static int launch_flags(const spmv_args & a, const spmv_config & k, bool acc, bool dot, bool rowlist, cudaStream_t s) {
 	if (rowlist) { // off-process block: always accumulates
 		if (dot)
-			launch_variant<OffT, NSTAGE, true, true, true>(a, k, s);
+			return launch_variant<OffT, NSTAGE, true, true, true>(a, k, s);
 		else
-			launch_variant<OffT, NSTAGE, true, false, true>(a, k, s);
+			return launch_variant<OffT, NSTAGE, true, false, true>(a, k, s);
 	}
 	else if (acc) {
 		if (dot)
-			launch_variant<OffT, NSTAGE, true, true, false>(a, k, s);
+			return launch_variant<OffT, NSTAGE, true, true, false>(a, k, s);
 		else
-			launch_variant<OffT, NSTAGE, true, false, false>(a, k, s);
+			return launch_variant<OffT, NSTAGE, true, false, false>(a, k, s);
 	}
 	else {
 		if (dot)
-			launch_variant<OffT, NSTAGE, false, true, false>(a, k, s);
+			return launch_variant<OffT, NSTAGE, false, true, false>(a, k, s);
 		else
-			launch_variant<OffT, NSTAGE, false, false, false>(a, k, s);
+			return launch_variant<OffT, NSTAGE, false, false, false>(a, k, s);
 	}
 }
 
 template<class OffT>
-static void launch_stages(const spmv_args & a, const spmv_config & k, bool acc, bool dot, bool rowlist, cudaStream_t s) {
+static int launch_stages(const spmv_args & a, const spmv_config & k, bool acc, bool dot, bool rowlist, cudaStream_t s) {
 	switch (k.nstage) {
-	case 1: launch_flags<OffT, 1>(a, k, acc, dot, rowlist, s); break;
-	case 2: launch_flags<OffT, 2>(a, k, acc, dot, rowlist, s); break;
-	case 3: launch_flags<OffT, 3>(a, k, acc, dot, rowlist, s); break;
-	default: launch_flags<OffT, 4>(a, k, acc, dot, rowlist, s); break;
+	case 1: return launch_flags<OffT, 1>(a, k, acc, dot, rowlist, s);
+	case 2: return launch_flags<OffT, 2>(a, k, acc, dot, rowlist, s);
+	case 3: return launch_flags<OffT, 3>(a, k, acc, dot, rowlist, s);
+	default: return launch_flags<OffT, 4>(a, k, acc, dot, rowlist, s);
 	}
 }
 
 // y (+)= B x on stream s.  When dot_u != nullptr, CTA b writes its partial of sum y_i u_i
-// to d_partials[partial_offset + b].
-void launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
-                 const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s) {
+// to d_partials[partial_offset + b].  Returns the number of CTAs launched (= partials written).
+int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
+                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s) {
 	if (B.n_blk == 0)
-		return;
+		return 0;
 	const spmv_config k = configure(c, B);
 	FSB_REQUIRE(k.smem <= 225 * 1024, "spmv: row block does not fit shared memory");
 	spmv_args a{};
@@ -423,11 +439,23 @@ void launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * 
 	a.rcap = k.rcap;
 	const bool rowlist = B.row_ids != nullptr;
 	const bool dot = dot_u != nullptr;
-	if (B.wide)
-		launch_stages<long long>(a, k, accumulate, dot, rowlist, s);
-	else
-		launch_stages<int>(a, k, accumulate, dot, rowlist, s);
 	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+	const bool prof = c->profile && s == c->stream;
+	if (prof) {
+		while (c->prof_events.size() < c->prof_used + 2) {
+			cudaEvent_t e;
+			FSB_CUDA(cudaEventCreate(&e));
+			c->prof_events.push_back(e);
+		}
+		FSB_CUDA(cudaEventRecord(c->prof_events[c->prof_used], s));
+	}
+	const int grid = B.wide ? launch_stages<long long>(a, k, accumulate, dot, rowlist, s)
+	                        : launch_stages<int>(a, k, accumulate, dot, rowlist, s);
+	if (prof) {
+		FSB_CUDA(cudaEventRecord(c->prof_events[c->prof_used + 1], s));
+		c->prof_used += 2;
+	}
+	return grid;
 }
 
 // fold the SpMV partials [0, n) into the reduction slot of `token`
@@ -478,13 +506,14 @@ void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * hos
 		blk.push_back(static_cast<int32_t>(B.n_rows));
 	}
 	else {
-		// Aim for thread-per-row with every thread busy (multiples of 256 rows), <= 96 KB a stage.
+		// one thread per row, about 44 KB of matrix stream per stage, at most 512 rows
 		const int width = std::max(1, B.max_blk_nnz);
-		int rows = (4096 / width) / 256 * 256;
-		if (rows < 256)
-			rows = 256;
-		if (rows * width > 8192)
-			rows = std::max(1, 8192 / width);
+		int rows = (44 * 1024) / (width * 12);
+		rows = std::max(32, std::min(512, rows));
+		int pow2 = 32;
+		while (pow2 * 2 <= rows)
+			pow2 *= 2;
+		rows = pow2;
 		if (c->spmv_rows_per_cta > 0)
 			rows = c->spmv_rows_per_cta;
 		if (env_rows > 0)

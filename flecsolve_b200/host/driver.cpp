@@ -68,16 +68,21 @@ struct recorder {
 	int cap;
 	int ev_start, ev_stop; // iteration numbers (1-based count of completed iterations) or -1
 	int count = 0;
+	std::int64_t launches_start = 0, launches_stop = 0;
 
 	template<class V>
 	bool operator()(const V &, double rnorm) {
 		if (history && count < cap)
 			history[count] = rnorm;
 		++count;
-		if (count == ev_start)
+		if (count == ev_start) {
 			fsb_ctx_event_record(ctx, 0);
-		if (count == ev_stop)
+			fsb_ctx_get_stat(ctx, FSB_STAT_KERNEL_LAUNCHES, &launches_start);
+		}
+		if (count == ev_stop) {
 			fsb_ctx_event_record(ctx, 1);
+			fsb_ctx_get_stat(ctx, FSB_STAT_KERNEL_LAUNCHES, &launches_stop);
+		}
 		return false;
 	}
 };
@@ -89,6 +94,7 @@ struct fsbh_info {
 	int status, iters, restarts;
 	float res_norm_initial, res_norm_final, sol_norm_initial, sol_norm_final, rhs_norm;
 	int callbacks; // times the diagnostic ran
+	int window_launches; // kernels launched between the two event marks
 };
 
 struct fsbh_options {
@@ -119,7 +125,8 @@ struct matrix_rhs : op::base<> {
 	}
 };
 
-void fill(fsbh_info * out, const solve_info & i, int callbacks) {
+void fill(fsbh_info * out, const solve_info & i, int callbacks, std::int64_t window_launches = 0) {
+	out->window_launches = static_cast<int>(window_launches);
 	out->status = static_cast<int>(i.status);
 	out->iters = i.iters;
 	out->restarts = i.restarts;
@@ -212,7 +219,7 @@ int fsbh_solve(void * sv, const fsbh_options * o, const double * b_host, double 
 			device::check(fsb_vec_download(S.x.data.handle(), x_host, n, 0));
 		else
 			S.ctx.sync();
-		fill(info, si, rec.count);
+		fill(info, si, rec.count, rec.launches_stop - rec.launches_start);
 	});
 }
 

@@ -60,6 +60,12 @@ struct diagonal_inverse : base<std::nullptr_t, ivar, ovar> {
 	using vec_t = decltype(vec::make(std::declval<typename topo_t::template vec_def<topo_t::cols> &>()(
 		std::declval<typename topo_t::topology &>())));
 
+private:
+	// one definition per operator object (several matrices may each carry their own 1/diag);
+	// declared before `dinv`, which is built from it
+	typename topo_t::template vec_def<topo_t::cols> def_;
+
+public:
 	explicit diagonal_inverse(const op::core<mat::parcsr<scalar, size>> & A)
 		: dinv(vec::make(def_(A.data.topo()))) {
 		device::check(fsb_parcsr_extract_dinv(A.data.handle(), dinv.data.handle()));
@@ -71,10 +77,6 @@ struct diagonal_inverse : base<std::nullptr_t, ivar, ovar> {
 	}
 
 	vec_t dinv;
-
-private:
-	// one definition per operator object: several matrices may carry their own 1/diag
-	typename topo_t::template vec_def<topo_t::cols> def_;
 };
 
 template<class scalar, class size>

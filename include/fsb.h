@@ -51,7 +51,8 @@ enum fsb_option {
 	FSB_OPT_FUSION = 0, /* 1 (default): fuse queued statements; 0: one kernel per call */
 	FSB_OPT_SPMV_ROWS_PER_CTA = 1, /* tuning knob for matrices created afterwards */
 	FSB_OPT_SPMV_THREADS = 2,
-	FSB_OPT_TRACE = 3 /* 1: print every launched group signature to stderr */
+	FSB_OPT_TRACE = 3, /* 1: print every launched group signature to stderr */
+	FSB_OPT_PROFILE = 4 /* 1: bracket every SpMV kernel with CUDA events (fsb_ctx_profile_read) */
 };
 
 enum fsb_stat {
@@ -92,6 +93,9 @@ int fsb_ctx_flush_l2(fsb_ctx_t ctx);
  * queue, then records event `slot` (0..15); elapsed blocks until both events completed.          */
 int fsb_ctx_event_record(fsb_ctx_t ctx, int slot);
 int fsb_ctx_event_elapsed_ms(fsb_ctx_t ctx, int slot_start, int slot_stop, double * ms);
+/* with FSB_OPT_PROFILE on: total device time and count of the SpMV kernels launched since the last
+ * read (waits for them); used by bench.py for the roofline of the dominant kernel                 */
+int fsb_ctx_profile_read(fsb_ctx_t ctx, double * spmv_ms, int64_t * spmv_launches);
 
 /* ---- vectors -----------------------------------------------------------
  * A vector is the device image of one field on the reference's `cols' index

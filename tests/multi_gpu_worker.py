@@ -1,0 +1,106 @@
+"""Worker for tests/test_multi_gpu.py: run under torchrun with one rank per GPU.  Every rank
+checks its slice of the results against the serial oracle and exits non-zero on mismatch."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import oracle as O  # noqa: E402
+from flecsolve_b200 import _lib as F  # noqa: E402
+from flecsolve_b200 import dist as D  # noqa: E402
+from flecsolve_b200 import host as H  # noqa: E402
+
+
+def main():
+    world = D.init(D.world_from_env())
+    ctx = D.make_context(world)
+    P, me = world.size, world.rank
+    rng = np.random.default_rng(0)
+
+    # ---- general (host) path: 27-point operator with perturbed values, rows not divisible by P
+    dims = (7, 6, 5 if P == 1 else 11)
+    rp, col, val = O.stencil_csr(27, *dims)
+    val = val * rng.uniform(0.5, 1.5, val.size)
+    n = len(rp) - 1
+    part = D.equal_map(n, P)
+    lo, hi = part[me], part[me + 1]
+    A = F.ParCSR.from_csr(ctx, n, part, rp[lo:hi + 1] - rp[lo], col[rp[lo]:rp[hi]], val[rp[lo]:rp[hi]])
+    M = O.ParCSR(rp, col, val, colours=P)
+    # split representation equals the oracle's colour `me` (topo/csr.hh color()/init_mats())
+    for which in (0, 1):
+        orp, ocol, oval, ocm = M.block(me, which)
+        drp, dcol, dval = A.download(which)
+        assert np.array_equal(drp, orp) and np.array_equal(dcol, ocol) and np.array_equal(dval, oval), ("split", which)
+    assert np.array_equal(A.colmap(), M.block(me, 1)[3])
+    x = rng.standard_normal(n)
+    xv, yv = A.vector(x[lo:hi]), A.vector()
+    A.spmv(xv, yv)
+    ref = M.spmv(x)  # oracle does (diag.x) + (offd.x) per colour like parcsr.hh:61-68
+    got = yv.download()
+    assert np.array_equal(got, ref[lo:hi]), ("spmv", np.abs(got - ref[lo:hi]).max())
+    # reductions across ranks
+    d = xv.dot(yv)
+    assert abs(d - x @ ref) <= 1e-12 * np.abs(x * ref).sum()
+    assert xv.global_size() == n
+    assert xv.max() == x.max() and xv.min() == x.min() and xv.inf_norm() == np.abs(x).max()
+    # fused spmv + dot on several ranks
+    A.spmv(xv, yv)
+    t = yv.dot_token(xv)
+    assert abs(ctx.get(t) - x @ ref) <= 1e-12 * np.abs(x * ref).sum()
+    # solver parity on the distributed matrix
+    S = H.Session(ctx, A)
+    b = M.spmv(np.linspace(1, 2, n))
+    for solver, fn in (("cg", M.cg), ("bicgstab", M.bicgstab)):
+        xo, oinfo, _ = fn(b, dinv=M.dinv(), rtol=1e-9, maxiter=500)
+        xs, info, _ = S.solve(b[lo:hi], np.zeros(hi - lo), solver=solver, precond="dinv", rtol=1e-9, maxiter=500)
+        assert info.reason == oinfo.reason == "converged_rtol", (solver, info.reason, oinfo.reason)
+        assert abs(info.iters - oinfo.iters) <= max(1, 0.05 * oinfo.iters), (solver, info.iters, oinfo.iters)
+        assert np.abs(xs - xo[lo:hi]).max() <= 1e-6
+    # weighted Jacobi sweeps need ghost values of x
+    x0 = rng.standard_normal(n)
+    w = float(np.float32(2 / 3))
+    bv, xj, tv = A.vector(b[lo:hi]), A.vector(x0[lo:hi]), A.vector()
+    A.jacobi_relax(w, 3, bv, xj, tv)
+    refj = M.jacobi_relax(w, 3, b, x0)
+    assert np.abs(xj.download() - refj[lo:hi]).max() <= 1e-12 * np.abs(refj).max()
+    S.close()
+    A.destroy()
+
+    # ---- device generator path: plane-aligned z-slabs
+    nn = 16
+    rp, col, val = O.stencil_csr(7, nn, nn, nn * P if P > 1 else nn)
+    n = len(rp) - 1
+    M = O.ParCSR(rp, col, val, colours=P)
+    B = F.ParCSR.stencil(ctx, 7, nn, nn, nn * P if P > 1 else nn)
+    lo, hi = B.row_begin, B.row_begin + B.local_rows
+    assert [lo, hi] == list(M.partition()[me:me + 2])
+    for which in (0, 1):
+        orp, ocol, oval, ocm = M.block(me, which)
+        drp, dcol, dval = B.download(which)
+        assert np.array_equal(drp, orp) and np.array_equal(dcol, ocol) and np.array_equal(dval, oval), ("gen", which)
+    assert np.array_equal(B.colmap(), M.block(me, 1)[3])
+    x = rng.standard_normal(n)
+    xv, yv = B.vector(x[lo:hi]), B.vector()
+    B.spmv(xv, yv)
+    assert np.array_equal(yv.download(), M.spmv(x)[lo:hi])
+    S = H.Session(ctx, B)
+    b = M.spmv(np.linspace(1, 2, n))
+    xo, oinfo, ohist = M.cg(b, dinv=M.dinv(), rtol=1e-9, maxiter=1000, history_cap=1000)
+    xs, info, hist = S.solve(b[lo:hi], np.zeros(hi - lo), solver="cg", precond="dinv", rtol=1e-9, maxiter=1000,
+                             history_cap=1000)
+    assert info.reason == "converged_rtol" and abs(info.iters - oinfo.iters) <= max(1, 0.02 * oinfo.iters)
+    m = min(len(hist), len(ohist), 30)
+    assert np.allclose(hist[:m], ohist[:m], rtol=1e-8)
+    assert ctx.stat("halo_exchanges") > 0 or P == 1
+    S.close()
+    B.destroy()
+    ctx.close()
+    D.finalize(world)
+    print(f"rank {me}/{P}: multi-gpu checks passed", flush=True)
+
+
+if __name__ == "__main__":
+    main()

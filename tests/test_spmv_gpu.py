@@ -1,0 +1,169 @@
+"""Device SpMV through the C ABI vs the oracle's restatement of matrices/seq.hh:178-194."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle as O
+from flecsolve_b200 import _lib as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_spmv(ctx, n, rp, col, val, x):
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    xv, yv = A.vector(x), A.vector()
+    A.spmv(xv, yv)
+    y = yv.download()
+    xv.destroy(); yv.destroy()
+    return A, y
+
+
+@pytest.mark.parametrize("kind,dims", [(5, (64, 64, 1)), (5, (33, 21, 1)), (7, (17, 13, 11)), (7, (32, 32, 32)),
+                                       (27, (9, 10, 11)), (27, (24, 24, 24))])
+def test_stencil_bit_exact(ctx, kind, dims):
+    rp, col, val = O.stencil_csr(kind, *dims)
+    n = len(rp) - 1
+    rng = np.random.default_rng(kind)
+    x = rng.standard_normal(n)
+    ref = O.csr_spmv(rp, col, val, x)
+    A, y = _device_spmv(ctx, n, rp, col, val, x)
+    assert np.array_equal(y, ref)  # same accumulation order, no FMA contraction
+    assert np.abs(y - sp.csr_matrix((val, col, rp)) @ x).max() <= 1e-12 * np.abs(ref).max()
+    # the device generator builds the identical matrix
+    B = F.ParCSR.stencil(ctx, kind, *dims)
+    rp2, col2, val2 = B.download(0)
+    assert np.array_equal(rp2, rp) and np.array_equal(col2, col) and np.array_equal(val2, val)
+    xv, yv = B.vector(x), B.vector()
+    B.spmv(xv, yv)
+    assert np.array_equal(yv.download(), ref)
+    xv.destroy(); yv.destroy(); A.destroy(); B.destroy()
+
+
+def _random_csr(n, rng, density_rows):
+    """rows with 0..k entries incl. empty rows, unsorted columns, repeated structure"""
+    counts = density_rows(rng, n)
+    rp = np.zeros(n + 1, dtype=np.int64)
+    rp[1:] = np.cumsum(counts)
+    col = rng.integers(0, n, rp[-1])
+    val = rng.standard_normal(rp[-1])
+    return rp, col, val
+
+
+@pytest.mark.parametrize("case", ["ragged", "empty_rows", "long_rows", "one_huge_row", "all_empty", "single"])
+def test_irregular_matrices(ctx, case):
+    rng = np.random.default_rng(11)
+    if case == "ragged":
+        n = 5000
+        rp, col, val = _random_csr(n, rng, lambda r, n: r.integers(0, 40, n))
+    elif case == "empty_rows":
+        n = 3000
+        rp, col, val = _random_csr(n, rng, lambda r, n: r.integers(0, 3, n) * (r.random(n) < 0.3))
+    elif case == "long_rows":  # few rows, hundreds of entries: warp-per-row path
+        n = 700
+        rp, col, val = _random_csr(n, rng, lambda r, n: r.integers(300, 600, n))
+    elif case == "one_huge_row":  # a row longer than a shared-memory stage
+        n = 2000
+        rp, col, val = _random_csr(n, rng, lambda r, n: np.where(np.arange(n) == 777, 20000, r.integers(0, 9, n)))
+    elif case == "all_empty":
+        n = 100
+        rp, col, val = np.zeros(n + 1, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)
+    else:
+        n = 1
+        rp, col, val = np.array([0, 1]), np.array([0]), np.array([2.5])
+    x = rng.standard_normal(n)
+    ref = O.csr_spmv(rp, col, val, x)
+    A, y = _device_spmv(ctx, n, rp, col, val, x)
+    scale = np.abs(ref).max() if ref.size and np.abs(ref).max() > 0 else 1.0
+    rowabs = np.zeros(n)
+    if val.size:
+        np.add.at(rowabs, np.repeat(np.arange(n), np.diff(rp)), np.abs(val * x[col]))
+    assert np.all(np.abs(y - ref) <= 1e-12 * np.maximum(rowabs, scale * 1e-3)), np.abs(y - ref).max()
+    if case in ("ragged", "empty_rows", "all_empty", "single"):
+        assert np.array_equal(y, ref)  # thread-per-row path keeps the reference order
+    A.destroy()
+
+
+def test_fused_dot_matches_separate(ctx):
+    rp, col, val = O.stencil_csr(7, 20, 19, 18)
+    n = len(rp) - 1
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(n)
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    xv, yv, uv = A.vector(x), A.vector(), A.vector(rng.standard_normal(n))
+    ref = O.csr_spmv(rp, col, val, x)
+    for other, expect in ((xv, ref @ x), (uv, ref @ uv.download()), (yv, ref @ ref)):
+        ctx.reset_stats()
+        A.spmv(xv, yv)
+        t = yv.dot_token(other)
+        got = ctx.get(t)
+        assert abs(got - expect) <= 1e-13 * np.abs(ref).sum() * max(np.abs(x).max(), np.abs(ref).max())
+        assert ctx.stat("launches") == 2  # spmv(+dot) and the one-CTA fold
+        assert np.array_equal(yv.download(), ref)
+    for v in (xv, yv, uv):
+        v.destroy()
+    A.destroy()
+
+
+def test_spmv_rejects_aliasing_and_size_mismatch(ctx):
+    rp, col, val = O.stencil_csr(5, 8, 8)
+    A = F.ParCSR.from_csr(ctx, 64, [0, 64], rp, col, val)
+    x = A.vector()
+    with pytest.raises(F.FsbError):
+        A.spmv(x, x)
+    bad = ctx.vector(63)
+    with pytest.raises(F.FsbError):
+        A.spmv(x, bad)
+    x.destroy(); bad.destroy(); A.destroy()
+
+
+def test_dinv_and_jacobi_relax(ctx):
+    rp, col, val = O.stencil_csr(27, 7, 8, 9)
+    n = len(rp) - 1
+    rng = np.random.default_rng(4)
+    val = val * rng.uniform(0.5, 1.5, val.size)
+    M = O.ParCSR(rp, col, val, colours=1)
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    d = A.vector()
+    A.extract_dinv(d)
+    assert np.array_equal(d.download(), M.dinv())  # 1/a_rr exactly
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    w = float(np.float32(2 / 3))
+    bv, xv, tv = A.vector(b), A.vector(x0), A.vector()
+    A.jacobi_relax(w, 4, bv, xv, tv)
+    ref = M.jacobi_relax(w, 4, b, x0)
+    assert np.abs(xv.download() - ref).max() <= 1e-13 * np.abs(ref).max()
+    for v in (d, bv, xv, tv):
+        v.destroy()
+    A.destroy()
+
+
+def test_large_stencil_properties(ctx):
+    """256^3 7-point (BASELINE config 2): size-independent checks."""
+    nn = 256
+    A = F.ParCSR.stencil(ctx, 7, nn, nn, nn)
+    n = A.local_rows
+    assert n == nn ** 3 and A.nnz(0) == 7 * n - 6 * nn * nn
+    ones, y = A.vector(), A.vector()
+    ones.set_scalar(1.0)
+    A.spmv(ones, y)
+    got = y.download().reshape(nn, nn, nn)
+    # row sum = 6 - number of neighbours = number of faces on the boundary
+    idx = np.arange(nn)
+    edge = ((idx == 0) | (idx == nn - 1)).astype(np.float64)
+    expect = edge[:, None, None] + edge[None, :, None] + edge[None, None, :]
+    assert np.array_equal(got, expect)
+    # linearity on random vectors: A(a u + b v) == a A u + b A v to rounding
+    rng = np.random.default_rng(0)
+    u, v = A.vector(rng.standard_normal(n)), A.vector(rng.standard_normal(n))
+    w, Au, Av, Aw = A.vector(), A.vector(), A.vector(), A.vector()
+    w.linear_sum(0.3, u, -1.7, v)
+    A.spmv(u, Au); A.spmv(v, Av); A.spmv(w, Aw)
+    Au.linear_sum(0.3, Au, -1.7, Av)
+    Aw.subtract(Aw, Au)
+    assert Aw.inf_norm() <= 1e-13 * 12 * 5
+    # symmetry: u.Av == v.Au
+    A.spmv(u, Au); A.spmv(v, Av)
+    assert abs(u.dot(Av) - v.dot(Au)) <= 1e-12 * n
+    for t in (ones, y, u, v, w, Au, Av, Aw):
+        t.destroy()
+    A.destroy()
