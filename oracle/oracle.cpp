@@ -13,11 +13,16 @@
 // "Colours" (the reference's MPI ranks) are simulated inside one process; with OpenMP each colour's
 // loops run on its own thread (threads stand in for ranks), which is the CPU timing baseline.
 //
-// PARITY PINNING: the reference itself cannot be built here (needs FleCSI, MPI, Boost; see
-// DESIGN.md).  This file is pinned against (a) the closed-form vector-operation cases of
-// vectors/test/flecsi_vector.cc:99-307 (tests/test_oracle.py), (b) scipy.sparse as an independent
-// SpMV implementation, and (c) where oracle/_ref could be built from the reference's own headers
-// with stub FleCSI headers (oracle/refcheck/), iteration counts of the reference's solver templates.
+// PARITY PINNING: the reference as a whole cannot be built here (needs FleCSI, MPI, Boost; see
+// DESIGN.md), but its serial path can: oracle/refcheck/ compiles the reference's OWN headers
+// (matrices/seq.hh, vectors/seq.hh, solvers/{cg,gmres,bicgstab}.hh, from /root/reference, against
+// stub FleCSI/Boost headers) into oracle/_ref/refcheck, and tests/golden/reference_solvers.json
+// holds its outputs.  This file reproduces them BIT FOR BIT: SpMV results, every residual norm of
+// every iteration, final iterates and solve_info (tests/test_golden_reference.py).  In addition:
+// the closed-form vector-operation cases of vectors/test/flecsi_vector.cc:99-307 and scipy.sparse
+// as an independent SpMV (tests/test_oracle.py).  What stays unpinned: the multi-colour split
+// against a real FleCSI run (checked structurally and against the serial result only) and the
+// reference's SuiteSparse iteration-count goldens (matrix files not available offline).
 //
 // Compile with -ffp-contract=off: the reference's default x86-64 build has no FMA contraction.
 #include <algorithm>

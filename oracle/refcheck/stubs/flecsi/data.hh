@@ -1,0 +1,2 @@
+#pragma once
+#include "stub_core.hh"

@@ -228,3 +228,31 @@ def test_config2_small_scale_iteration_parity(ctx):
     m = min(len(hist), len(ohist), 100)
     assert np.allclose(hist[:m], ohist[:m], rtol=1e-7)
     S.close(); A.destroy()
+
+
+# ---- against golden vectors generated by the reference's own solver templates (tests/golden/)
+from tests import golden_util as G  # noqa: E402
+
+
+@pytest.mark.parametrize("entry", G.load(), ids=lambda e: "-".join(map(str, e["case"][:4])).replace(" ", ""))
+def test_device_matches_reference_golden(ctx, entry):
+    (rp, col, val), M, b, x0, solver, precond, kw = G.problem(entry["case"])
+    n = len(rp) - 1
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    info = entry["info"]
+    if solver == "spmv":
+        xv, yv = A.vector(x0), A.vector()
+        A.spmv(xv, yv)
+        assert G.sha(yv.download()) == entry["x_sha256"]  # bit-identical to the reference's serial SpMV
+        xv.destroy(); yv.destroy(); A.destroy()
+        return
+    S = H.Session(ctx, A)
+    x, dinfo, hist = S.solve(b, x0, solver=solver, precond="dinv" if precond else None, history_cap=2000, **kw)
+    assert dinfo.status == info["status"]
+    tol = 0.02 if solver != "bicgstab" else 0.1
+    assert abs(dinfo.iters - info["iters"]) <= max(1, tol * info["iters"]), (dinfo.iters, info["iters"])
+    ref_hist = G.history(entry)
+    m = min(len(hist), len(ref_hist), 25)
+    assert np.allclose(hist[:m], ref_hist[:m], rtol=1e-7)
+    assert abs(np.linalg.norm(x) - float.fromhex(entry["x_norm2"])) <= 1e-6 * float.fromhex(entry["x_norm2"])
+    S.close(); A.destroy()
