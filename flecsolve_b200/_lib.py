@@ -90,6 +90,7 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_ctx_event_record", C.c_int, _p, C.c_int)
     f("fsb_ctx_event_elapsed_ms", C.c_int, _p, C.c_int, C.c_int, _pd)
     f("fsb_ctx_profile_read", C.c_int, _p, _pd, _pi64)
+    f("fsb_ctx_profile_read_split", C.c_int, _p, _pd, _pi64)
     f("fsb_vec_create", C.c_int, _p, _i64, _i64, C.POINTER(_p))
     f("fsb_vec_wrap", C.c_int, _p, _p, _i64, _i64, C.POINTER(_p))
     f("fsb_vec_destroy", C.c_int, _p)
@@ -185,6 +186,13 @@ class Context:
         out = _dbl()
         check(lib().fsb_ctx_event_elapsed_ms(self.h, a, b, C.byref(out)))
         return out.value
+
+    def profile_read_split(self):
+        """((diag ms, offd ms), (diag launches, offd launches)) since the last read."""
+        ms = (C.c_double * 2)()
+        cnt = (C.c_int64 * 2)()
+        check(lib().fsb_ctx_profile_read_split(self.h, ms, cnt))
+        return (ms[0], ms[1]), (cnt[0], cnt[1])
 
     def profile_read(self):
         """(total SpMV kernel ms, launches) since the last read; needs set_option('profile', 1)."""

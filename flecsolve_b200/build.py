@@ -67,7 +67,7 @@ def host_lib_path() -> str:
 
 def build_lib(force: bool = False, verbose_ptxas: bool = False) -> str:
     out = lib_path()
-    srcs = [os.path.join(CSRC, f) for f in ("capi.cu", "fuser.cu", "spmv.cu", "parcsr.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("capi.cu", "fuser.cu", "spmv.cu", "parcsr.cu", "halo.cu")]
     deps = _walk(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "fsb.h")]
     if force or _newer(out, deps):
         flags = list(NVCC_FLAGS)

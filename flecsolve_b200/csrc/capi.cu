@@ -7,6 +7,7 @@
 #include <fstream>
 #include <random>
 
+#include "ew_kernels.cuh"
 #include "fsb_internal.h"
 
 using namespace fsb;
@@ -41,6 +42,72 @@ static int guarded(F && body) noexcept {
 		set_last_error("unknown error");
 		return FSB_ERR_STATE;
 	}
+}
+
+// Map every rank's reduction mailbox into this process (cudaIpc) so the kernels can all-reduce
+// scalars with plain stores/loads over NVLink.  Any failure leaves d_xrank null => NCCL path.
+static void setup_peer_reductions(fsb_ctx_s * c) {
+	static_assert(XRANK_RING == FSB_RED_RING, "mailbox ring must match the token ring");
+	const int P = c->nranks;
+	if (P > XRANK_MAX)
+		return;
+	const size_t bytes = sizeof(double) * 2 * XRANK_RING * P;
+	FSB_CUDA(cudaMalloc(&c->d_mailbox, bytes));
+	FSB_CUDA(cudaMemset(c->d_mailbox, 0, bytes));
+	cudaIpcMemHandle_t mine;
+	bool ok = cudaIpcGetMemHandle(&mine, c->d_mailbox) == cudaSuccess;
+	// all-gather the handles (and whether every rank got one) with NCCL
+	struct packet {
+		cudaIpcMemHandle_t h;
+		long long ok;
+	};
+	std::vector<packet> all(P);
+	packet * d_all = nullptr;
+	FSB_CUDA(cudaMalloc(&d_all, sizeof(packet) * P));
+	packet me{mine, ok ? 1 : 0};
+	FSB_CUDA(cudaMemcpy(d_all + c->rank, &me, sizeof(packet), cudaMemcpyHostToDevice));
+	FSB_NCCL(ncclAllGather(d_all + c->rank, d_all, sizeof(packet), ncclChar, c->nccl, c->stream));
+	FSB_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(packet) * P, cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(d_all);
+	for (int q = 0; q < P; ++q)
+		ok = ok && all[q].ok;
+	xrank_info info{};
+	info.me = c->rank;
+	info.nranks = P;
+	for (int q = 0; q < P && ok; ++q) {
+		if (q == c->rank) {
+			info.mailbox[q] = c->d_mailbox;
+			continue;
+		}
+		void * p = nullptr;
+		if (cudaIpcOpenMemHandle(&p, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+			cudaGetLastError();
+			ok = false;
+			break;
+		}
+		c->peer_mailbox[q] = p;
+		info.mailbox[q] = static_cast<double *>(p);
+	}
+	// every rank must agree, otherwise some would wait on mailboxes nobody writes
+	long long * d_ok = nullptr;
+	FSB_CUDA(cudaMalloc(&d_ok, sizeof(long long)));
+	long long v = ok ? 1 : 0;
+	FSB_CUDA(cudaMemcpy(d_ok, &v, sizeof(v), cudaMemcpyHostToDevice));
+	FSB_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt64, ncclMin, c->nccl, c->stream));
+	FSB_CUDA(cudaMemcpyAsync(&v, d_ok, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(d_ok);
+	if (!v) {
+		if (c->rank == 0)
+			fprintf(stderr, "[fsb] peer-memory reductions unavailable (cudaIpc failed); using ncclAllReduce\n");
+		return;
+	}
+	FSB_CUDA(cudaHostAlloc(&c->h_xrank_error, sizeof(int), cudaHostAllocMapped));
+	*c->h_xrank_error = 0;
+	FSB_CUDA(cudaHostGetDevicePointer(&info.error_flag, c->h_xrank_error, 0));
+	FSB_CUDA(cudaMalloc(&c->d_xrank, sizeof(xrank_info)));
+	FSB_CUDA(cudaMemcpy(c->d_xrank, &info, sizeof(info), cudaMemcpyHostToDevice));
 }
 
 extern "C" {
@@ -95,6 +162,8 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 		FSB_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * MAXR * MAX_RED_BLOCKS));
 		FSB_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned)));
 		FSB_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned)));
+		FSB_CUDA(cudaMalloc(&c->d_sched, 2 * sizeof(unsigned)));
+		FSB_CUDA(cudaMemset(c->d_sched, 0, 2 * sizeof(unsigned)));
 		FSB_CUDA(cudaMalloc(&c->d_results, sizeof(double) * FSB_RED_RING));
 		FSB_CUDA(cudaHostAlloc(&c->h_results, sizeof(double) * FSB_RED_RING, cudaHostAllocMapped));
 		FSB_CUDA(cudaHostAlloc(&c->h_flags, sizeof(int64_t) * FSB_RED_RING, cudaHostAllocMapped));
@@ -112,6 +181,8 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 			for (auto & e : c->token_event)
 				FSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		}
+		if (nranks > 1 && !(std::getenv("FSB_P2P_REDUCE") && std::atoi(std::getenv("FSB_P2P_REDUCE")) == 0))
+			setup_peer_reductions(c);
 		if (const char * t = std::getenv("FSB_TRACE"))
 			c->trace = std::atoi(t) != 0;
 		if (const char * t = std::getenv("FSB_FUSION"))
@@ -127,6 +198,13 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 		flush(c);
 		cudaStreamSynchronize(c->stream);
 		cudaStreamSynchronize(c->comm_stream);
+		for (void * p : c->peer_mailbox)
+			if (p)
+				cudaIpcCloseMemHandle(p);
+		cudaFree(c->d_mailbox);
+		cudaFree(c->d_xrank);
+		if (c->h_xrank_error)
+			cudaFreeHost(c->h_xrank_error);
 		if (c->nccl_halo_comm)
 			ncclCommDestroy(c->nccl_halo_comm);
 		if (c->nccl)
@@ -141,6 +219,7 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 			cudaEventDestroy(e);
 		cudaFree(c->d_partials);
 		cudaFree(c->d_counter);
+		cudaFree(c->d_sched);
 		cudaFree(c->d_results);
 		cudaFree(c->d_flush);
 		cudaFreeHost(c->h_results);
@@ -241,21 +320,33 @@ int fsb_ctx_event_elapsed_ms(fsb_ctx_t c, int a, int b, double * ms) {
 	});
 }
 
-int fsb_ctx_profile_read(fsb_ctx_t c, double * spmv_ms, int64_t * spmv_launches) {
+int fsb_ctx_profile_read_split(fsb_ctx_t c, double * ms2, int64_t * launches2) {
 	return guarded([&] {
-		FSB_REQUIRE(c && spmv_ms && spmv_launches, "bad arguments");
+		FSB_REQUIRE(c && ms2 && launches2, "bad arguments");
 		flush(c);
-		double total = 0;
+		ms2[0] = ms2[1] = 0;
+		launches2[0] = launches2[1] = 0;
 		for (size_t k = 0; k + 1 < c->prof_used; k += 2) {
 			FSB_CUDA(cudaEventSynchronize(c->prof_events[k + 1]));
 			float t = 0;
 			FSB_CUDA(cudaEventElapsedTime(&t, c->prof_events[k], c->prof_events[k + 1]));
-			total += t;
+			const int tag = c->prof_tag[k / 2] ? 1 : 0;
+			ms2[tag] += t;
+			launches2[tag]++;
 		}
-		*spmv_ms = total;
-		*spmv_launches = static_cast<int64_t>(c->prof_used / 2);
 		c->prof_used = 0;
 	});
+}
+
+int fsb_ctx_profile_read(fsb_ctx_t c, double * spmv_ms, int64_t * spmv_launches) {
+	double ms2[2];
+	int64_t n2[2];
+	const int rc = fsb_ctx_profile_read_split(c, ms2, n2);
+	if (rc == FSB_OK && spmv_ms && spmv_launches) {
+		*spmv_ms = ms2[0] + ms2[1];
+		*spmv_launches = n2[0] + n2[1];
+	}
+	return rc;
 }
 
 // ------------------------------------------------------------------ vectors
@@ -501,7 +592,7 @@ static void wait_token(fsb_ctx_t c, fsb_token_t tok) {
 	FSB_REQUIRE(tok + FSB_RED_RING > c->next_token - 1, "reduction token expired");
 	flush(c);
 	const int slot = static_cast<int>(tok % FSB_RED_RING);
-	if (c->nranks > 1) {
+	if (c->nranks > 1 && !c->d_xrank) {
 		FSB_CUDA(cudaEventSynchronize(c->token_event[slot]));
 	}
 	else {
@@ -518,6 +609,8 @@ static void wait_token(fsb_ctx_t c, fsb_token_t tok) {
 					throw fsb::error(FSB_ERR_STATE, "reduction result never arrived");
 			}
 		}
+		if (c->h_xrank_error && *(volatile int *)c->h_xrank_error)
+			throw fsb::error(FSB_ERR_STATE, "cross-rank reduction timed out waiting for a peer");
 	}
 	c->stats[FSB_STAT_HOST_SYNCS]++;
 }

@@ -22,6 +22,18 @@ struct red_out {
 	long long token;
 };
 
+// Cross-rank all-reduce of one scalar over NVLink peer memory, executed by the CTA that finishes
+// a reduction: every rank stores its partial (then the token) into slot [token % ring][me] of every
+// rank's mailbox, waits for the P tokens in its own mailbox and folds the P values in rank order --
+// the same bits on every rank, no NCCL launch, no extra kernel.  Mailboxes are cudaIpc-mapped.
+constexpr int XRANK_MAX = 8;
+constexpr int XRANK_RING = 256; // == FSB_RED_RING
+struct xrank_info {
+	int me, nranks;
+	double * mailbox[XRANK_MAX]; // [ring][nranks]{value, token}
+	int * error_flag; // mapped host int: set when a peer never showed up
+};
+
 struct ew_args {
 	double * v[MAXV];
 	double s[MAXSC];
@@ -29,6 +41,7 @@ struct ew_args {
 	double * partials; // [MAXR][MAX_RED_BLOCKS]
 	unsigned * counter;
 	int partial_stride;
+	const xrank_info * xr; // nullptr on one rank
 	red_out r[MAXR];
 };
 
@@ -75,6 +88,55 @@ __device__ __forceinline__ double block_fold(double v, double * scratch) {
 		v = warp_fold<FOLD>(v);
 	}
 	return v;
+}
+
+// all threads of the CTA call this; `local` is valid in thread 0; result valid in thread 0
+template<int FOLD>
+__device__ __forceinline__ double xrank_allreduce(const xrank_info * xr, double local, long long token, double * scratch) {
+	const int P = xr->nranks, me = xr->me;
+	const size_t slot = static_cast<size_t>(token % XRANK_RING);
+	__syncthreads();
+	if (threadIdx.x == 0)
+		scratch[0] = local;
+	__syncthreads();
+	local = scratch[0];
+	__syncthreads();
+	if (threadIdx.x < P) {
+		const int q = threadIdx.x;
+		volatile double * dst = xr->mailbox[q] + (slot * P + me) * 2;
+		dst[0] = local;
+		__threadfence_system();
+		reinterpret_cast<volatile long long *>(dst)[1] = token;
+		volatile double * src = xr->mailbox[me] + (slot * P + q) * 2;
+		const long long t0 = clock64();
+		bool ok = true;
+		while (reinterpret_cast<volatile long long *>(src)[1] != token) {
+			if (clock64() - t0 > 20000000000LL) { // ~10 s: a peer is gone
+				ok = false;
+				break;
+			}
+		}
+		__threadfence_system();
+		scratch[q] = ok ? src[0] : __longlong_as_double(0x7ff8000000000000LL);
+		if (!ok)
+			*reinterpret_cast<volatile int *>(xr->error_flag) = 1;
+	}
+	__syncthreads();
+	double r = fold_identity<FOLD>();
+	if (threadIdx.x == 0)
+		for (int q = 0; q < P; ++q)
+			r = fold<FOLD>(r, scratch[q]);
+	return r;
+}
+
+// publish a finished reduction: device slot, then mapped host value + token (thread 0 only)
+__device__ __forceinline__ void publish(const red_out & r, double t) {
+	*r.d_value = t;
+	if (r.h_value) {
+		*reinterpret_cast<volatile double *>(r.h_value) = t;
+		__threadfence_system();
+		*reinterpret_cast<volatile long long *>(r.h_flag) = r.token;
+	}
 }
 
 template<class PT, int I>
@@ -194,14 +256,10 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_const
 					 for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += blockDim.x)
 						 t = fold<F>(t, __ldcg(&a.partials[R * a.partial_stride + b]));
 					 t = block_fold<F>(t, scratch);
-					 if (threadIdx.x == 0) {
-						 *a.r[R].d_value = t;
-						 if (a.r[R].h_value) {
-							 *reinterpret_cast<volatile double *>(a.r[R].h_value) = t;
-							 __threadfence_system();
-							 *reinterpret_cast<volatile long long *>(a.r[R].h_flag) = a.r[R].token;
-						 }
-					 }
+					 if (a.xr)
+						 t = xrank_allreduce<F>(a.xr, t, a.r[R].token, scratch);
+					 if (threadIdx.x == 0)
+						 publish(a.r[R], t);
 				 }()),
 				 ...);
 			}(std::make_index_sequence<P.nr>{});

@@ -14,6 +14,10 @@
 #include "program.h"
 
 namespace fsb {
+struct xrank_info;
+}
+
+namespace fsb {
 
 struct error : std::runtime_error {
 	int code;
@@ -82,12 +86,18 @@ struct fsb_ctx_s {
 	// reductions
 	double * d_partials = nullptr; // [MAX_RED][MAX_RED_BLOCKS]
 	unsigned * d_counter = nullptr;
+	unsigned * d_sched = nullptr; // SpMV dynamic scheduler words {next block, finished CTAs}
 	double * d_results = nullptr; // [FSB_RED_RING]
 	double * h_results = nullptr; // pinned+mapped [FSB_RED_RING]
 	double * h_results_dev = nullptr; // device alias of h_results
 	int64_t * h_flags = nullptr; // pinned+mapped [FSB_RED_RING]
 	int64_t * h_flags_dev = nullptr;
 	int64_t next_token = 1;
+	// cross-rank reductions over peer memory (nranks > 1, when cudaIpc mapping succeeded)
+	double * d_mailbox = nullptr; // this rank's mailbox [ring][nranks]{value, token}
+	void * peer_mailbox[8] = {};
+	fsb::xrank_info * d_xrank = nullptr; // device copy handed to kernels; nullptr => NCCL path
+	int * h_xrank_error = nullptr; // mapped host flag
 	std::vector<int> token_op; // per ring slot: nccl op kind of the reduction
 	std::vector<cudaEvent_t> token_event; // multi-rank path
 
@@ -101,6 +111,7 @@ struct fsb_ctx_s {
 	cudaEvent_t timers[16] = {};
 	bool profile = false;
 	std::vector<cudaEvent_t> prof_events; // pairs: [2k] start, [2k+1] stop
+	std::vector<char> prof_tag; // per pair: 0 diag block, 1 offd block
 	size_t prof_used = 0;
 
 	// L2 flush scratch
@@ -116,7 +127,8 @@ struct fsb_vec_s {
 	double * d = nullptr;
 	int64_t n_owned = 0, n_ghost = 0;
 	bool owns = true;
-	bool halo_valid = false;
+	bool halo_valid = false; // ghost entries hold the owners' current values ...
+	const void * halo_for = nullptr; // ... in the ghost numbering of this matrix
 	uint64_t id = 0;
 };
 
@@ -162,6 +174,13 @@ struct fsb_parcsr_s {
 	int64_t send_total = 0;
 	bool need_pack = false;
 	double * d_dinv = nullptr; // lazily computed 1/diag (jacobi relax)
+	// ghost exchange over peer memory (halo.cu); null => NCCL send/recv
+	void * halo_p2p = nullptr; // device halo_dev
+	unsigned char * halo_block = nullptr; // flags + double-buffered landing area (IPC-exported)
+	unsigned * halo_counters = nullptr;
+	std::vector<void *> halo_opened; // peers' blocks mapped here
+	long long halo_epoch = 0;
+	int halo_push_ctas = 1, halo_unpack_ctas = 1;
 };
 
 namespace fsb {
@@ -173,12 +192,16 @@ int64_t new_token(fsb_ctx_s * c, int nccl_op);
 
 // kernels (declared here, defined in their .cu)
 int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
-                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s);
+                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s, int64_t fold_token = 0);
 void finalize_reduction(fsb_ctx_s * c, int n_partials, int64_t token, int op_kind);
 void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x);
 
 void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * host_rowptr);
 void extract_dinv(fsb_parcsr_s * A, double * d);
+void halo_p2p_setup(fsb_parcsr_s * A, const std::vector<int64_t> & dest_off);
+void halo_p2p_destroy(fsb_parcsr_s * A);
+void halo_p2p_push(fsb_parcsr_s * A, fsb_vec_s * x);
+void halo_p2p_unpack(fsb_parcsr_s * A, fsb_vec_s * x);
 void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot);
 
 } // namespace fsb

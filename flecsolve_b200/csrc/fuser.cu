@@ -17,10 +17,19 @@ namespace fsb {
 
 // ---------------------------------------------------------------- registry
 
-using launcher_t = void (*)(const ew_args &, int grid, cudaStream_t);
+using launcher_t = void (*)(const ew_args &, int want_ctas, cudaStream_t);
 
+// grid: enough CTAs for the data, at most one resident wave (occupancy API, cached per program)
 template<class PT>
-static void launch_program(const ew_args & a, int grid, cudaStream_t s) {
+static void launch_program(const ew_args & a, int want, cudaStream_t s) {
+	static int resident = 0;
+	if (resident == 0) {
+		int nb = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ew_program_kernel<PT>, EW_BLOCK, 0) != cudaSuccess || nb < 1)
+			nb = 4;
+		resident = nb * SM_COUNT;
+	}
+	const int grid = want < resident ? want : resident;
 	ew_program_kernel<PT><<<grid, EW_BLOCK, 0, s>>>(a);
 }
 
@@ -231,6 +240,7 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 	a.partials = c->d_partials;
 	a.counter = c->d_counter;
 	a.partial_stride = MAX_RED_BLOCKS;
+	a.xr = c->d_xrank;
 	for (int i = 0; i < len; ++i) {
 		const stmt & s = cr.p.st[i];
 		if (s.a >= 0)
@@ -242,7 +252,7 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 			red_out & r = a.r[s.z];
 			r.d_value = c->d_results + slot;
 			r.token = q[i].token;
-			if (c->nranks == 1) {
+			if (c->nranks == 1 || c->d_xrank) {
 				r.h_value = c->h_results_dev + slot;
 				r.h_flag = reinterpret_cast<long long *>(c->h_flags_dev + slot);
 			}
@@ -257,7 +267,7 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 
 // After a kernel that produced intra-rank reduction values: finish across ranks.
 static void publish_multi_rank(fsb_ctx_s * c, const pending * q, int len) {
-	if (c->nranks == 1)
+	if (c->nranks == 1 || c->d_xrank) // the producing kernel already reduced across ranks
 		return;
 	for (int i = 0; i < len; ++i) {
 		if (q[i].kind != pending::RED)
@@ -314,12 +324,10 @@ void flush(fsb_ctx_s * c) {
 		if (c->trace)
 			fprintf(stderr, "[fsb] launch: %s%s\n", describe(&q[i], len).c_str(),
 			        len < j - i ? ("   <-- split from: " + describe(&q[i], j - i)).c_str() : "");
-		if (n > 0) {
+		if (n > 0 || (g.nr > 0 && c->nranks > 1)) {
 			long long packets = (n + 1) / 2;
 			long long want = (packets + EW_BLOCK - 1) / EW_BLOCK;
-			int grid = static_cast<int>(std::min<long long>(want, SM_COUNT * EW_CTAS_PER_SM));
-			if (grid < 1)
-				grid = 1;
+			const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, MAX_RED_BLOCKS)));
 			g.launch(g.args, grid, c->stream);
 			FSB_CUDA(cudaGetLastError());
 			c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
@@ -333,11 +341,9 @@ void flush(fsb_ctx_s * c) {
 				const int f = fold_of(q[k].op);
 				const double ident = f == 0 ? 0.0 : (f == 1 ? -HUGE_VAL : HUGE_VAL);
 				FSB_CUDA(cudaMemcpyAsync(c->d_results + slot, &ident, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-				if (c->nranks == 1) {
-					FSB_CUDA(cudaStreamSynchronize(c->stream));
-					c->h_results[slot] = ident;
-					c->h_flags[slot] = q[k].token;
-				}
+				FSB_CUDA(cudaStreamSynchronize(c->stream));
+				c->h_results[slot] = ident;
+				c->h_flags[slot] = q[k].token;
 			}
 		}
 		for (int k = i; k < i + len; ++k) // ghost copies of overwritten vectors are stale from here on

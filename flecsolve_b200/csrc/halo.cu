@@ -1,0 +1,276 @@
+// Ghost exchange over NVLink peer memory (replaces NCCL send/recv when cudaIpc mapping works).
+//
+// Reference: the FleCSI copy plan of topo::csr (topo/csr.hh:116-187, 237-245, 277-304): destination =
+// the contiguous ghost interval of the `cols` space, sources = (owner colour, shared offset) pairs.
+// Here every rank owns a double-buffered landing area that its neighbours have mapped; an exchange is
+//   push   : copy my boundary entries straight into each neighbour's landing area (stores over
+//            NVLink), system fence, then store the exchange number into the neighbour's `ready` flag;
+//   unpack : wait for my `ready` flags, move the landing area into the ghost interval of x, then
+//            store the exchange number into each sender's `ack` flag (buffer may be reused).
+// Both are small kernels on the compute stream: push runs before the diag-block SpMV, unpack after it,
+// so the transfer overlaps the interior rows without a second stream, an NCCL launch or host work.
+#include <cstdlib>
+#include <cstring>
+
+#include "fsb_internal.h"
+
+namespace fsb {
+
+constexpr int HALO_MAX_NBR = 8;
+constexpr int HALO_THREADS = 256;
+
+struct halo_dev {
+	int me, nranks, n_nbr;
+	int nbr_rank[HALO_MAX_NBR];
+	long long send_count[HALO_MAX_NBR]; // entries I send to nbr k
+	long long send_start[HALO_MAX_NBR]; // contiguous: first owned index; packed: offset into send_idx
+	int contiguous[HALO_MAX_NBR];
+	long long dest_off[HALO_MAX_NBR]; // where my entries land in nbr k's ghost interval
+	long long recv_count[HALO_MAX_NBR]; // entries nbr k sends me
+	const int32_t * send_idx; // packed send lists (general partitions)
+	long long n_ghost; // my ghost entries
+	long long gmax; // landing-area capacity (max ghost count over ranks)
+	unsigned char * base[8]; // every rank's block: [ready 2 x 8][ack 8][pad][landing 0][landing 1]
+	unsigned * counters; // local: [0] push CTAs done, [1] unpack CTAs done
+	int * error_flag;
+};
+
+__device__ __forceinline__ volatile long long * halo_ready(unsigned char * base, int buf, int src) {
+	return reinterpret_cast<volatile long long *>(base) + buf * 8 + src;
+}
+__device__ __forceinline__ volatile long long * halo_ack(unsigned char * base, int dst) {
+	return reinterpret_cast<volatile long long *>(base) + 16 + dst;
+}
+__device__ __forceinline__ double * halo_landing(unsigned char * base, int buf, long long gmax) {
+	return reinterpret_cast<double *>(base + 256) + static_cast<size_t>(buf) * gmax;
+}
+
+__device__ __forceinline__ bool spin_until(volatile long long * flag, long long at_least, bool exact) {
+	const long long t0 = clock64();
+	for (;;) {
+		const long long v = *flag;
+		if (exact ? v == at_least : v >= at_least)
+			return true;
+		if (clock64() - t0 > 20000000000LL)
+			return false;
+	}
+}
+
+__global__ void __launch_bounds__(HALO_THREADS) halo_push_kernel(const halo_dev * hp, const double * __restrict__ x,
+                                                                 long long epoch) {
+	const halo_dev & h = *hp;
+	const int buf = static_cast<int>(epoch & 1);
+	// the landing buffer was last used by exchange epoch-2: its consumer must have acknowledged it
+	if (threadIdx.x < h.n_nbr && h.send_count[threadIdx.x] > 0) {
+		if (!spin_until(halo_ack(h.base[h.me], h.nbr_rank[threadIdx.x]), epoch - 2, false))
+			*reinterpret_cast<volatile int *>(h.error_flag) = 2;
+	}
+	__syncthreads();
+	const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	for (int k = 0; k < h.n_nbr; ++k) {
+		double * dst = halo_landing(h.base[h.nbr_rank[k]], buf, h.gmax) + h.dest_off[k];
+		const long long n = h.send_count[k];
+		if (h.contiguous[k]) {
+			const double * src = x + h.send_start[k];
+			for (long long i = tid; i < n; i += stride)
+				dst[i] = src[i];
+		}
+		else {
+			const int32_t * idx = h.send_idx + h.send_start[k];
+			for (long long i = tid; i < n; i += stride)
+				dst[i] = x[idx[i]];
+		}
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (atomicAdd(&h.counters[0], 1u) == gridDim.x - 1) { // every CTA's stores are fenced: publish
+			__threadfence_system();
+			for (int k = 0; k < h.n_nbr; ++k)
+				if (h.send_count[k] > 0)
+					*halo_ready(h.base[h.nbr_rank[k]], buf, h.me) = epoch;
+			h.counters[0] = 0u;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(HALO_THREADS) halo_unpack_kernel(const halo_dev * hp, double * __restrict__ ghosts,
+                                                                   long long epoch) {
+	const halo_dev & h = *hp;
+	const int buf = static_cast<int>(epoch & 1);
+	if (threadIdx.x < h.n_nbr && h.recv_count[threadIdx.x] > 0) {
+		if (!spin_until(halo_ready(h.base[h.me], buf, h.nbr_rank[threadIdx.x]), epoch, true))
+			*reinterpret_cast<volatile int *>(h.error_flag) = 3;
+	}
+	__syncthreads();
+	__threadfence_system();
+	const double * src = halo_landing(h.base[h.me], buf, h.gmax);
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < h.n_ghost; i += stride)
+		ghosts[i] = __ldcg(src + i);
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (atomicAdd(&h.counters[1], 1u) == gridDim.x - 1) { // landing area fully consumed: acknowledge
+			for (int k = 0; k < h.n_nbr; ++k)
+				if (h.recv_count[k] > 0)
+					*halo_ack(h.base[h.nbr_rank[k]], h.me) = epoch;
+			h.counters[1] = 0u;
+		}
+	}
+}
+
+// Collective over the ranks of the context.  dest_off[k]: where my entries land in neighbour k's
+// ghost interval.  Leaves A->halo_p2p null (=> NCCL path) if peer mapping is unavailable.
+void halo_p2p_setup(fsb_parcsr_s * A, const std::vector<int64_t> & dest_off) {
+	fsb_ctx_s * c = A->ctx;
+	const int P = c->nranks;
+	if (P == 1 || !c->d_xrank || P > 8 || static_cast<int>(A->nbrs.size()) > HALO_MAX_NBR)
+		return;
+	if (const char * e = std::getenv("FSB_P2P_HALO"))
+		if (std::atoi(e) == 0)
+			return;
+	// capacity = max ghost count over ranks
+	long long * d_g = nullptr;
+	FSB_CUDA(cudaMalloc(&d_g, sizeof(long long)));
+	long long g = A->n_ghost;
+	FSB_CUDA(cudaMemcpyAsync(d_g, &g, sizeof(g), cudaMemcpyHostToDevice, c->stream));
+	FSB_NCCL(ncclAllReduce(d_g, d_g, 1, ncclInt64, ncclMax, c->nccl, c->stream));
+	FSB_CUDA(cudaMemcpyAsync(&g, d_g, sizeof(g), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(d_g);
+	const long long gmax = std::max<long long>(g, 1);
+	const size_t bytes = 256 + 2 * static_cast<size_t>(gmax) * sizeof(double);
+	unsigned char * block = nullptr;
+	FSB_CUDA(cudaMalloc(&block, bytes));
+	FSB_CUDA(cudaMemset(block, 0, 256));
+	struct packet {
+		cudaIpcMemHandle_t h;
+		long long ok;
+	};
+	packet mine{};
+	mine.ok = cudaIpcGetMemHandle(&mine.h, block) == cudaSuccess ? 1 : 0;
+	packet * d_all = nullptr;
+	FSB_CUDA(cudaMalloc(&d_all, sizeof(packet) * P));
+	FSB_CUDA(cudaMemcpy(d_all + c->rank, &mine, sizeof(packet), cudaMemcpyHostToDevice));
+	FSB_NCCL(ncclAllGather(d_all + c->rank, d_all, sizeof(packet), ncclChar, c->nccl, c->stream));
+	std::vector<packet> all(P);
+	FSB_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(packet) * P, cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(d_all);
+	bool ok = true;
+	for (int q = 0; q < P; ++q)
+		ok = ok && all[q].ok;
+	halo_dev h{};
+	h.me = c->rank;
+	h.nranks = P;
+	std::vector<void *> opened(P, nullptr);
+	for (int q = 0; q < P && ok; ++q) {
+		if (q == c->rank) {
+			h.base[q] = block;
+			continue;
+		}
+		// only neighbours need to be mapped
+		bool is_nbr = false;
+		for (const neighbour & nb : A->nbrs)
+			is_nbr = is_nbr || nb.rank == q;
+		if (!is_nbr)
+			continue;
+		void * p = nullptr;
+		if (cudaIpcOpenMemHandle(&p, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+			cudaGetLastError();
+			ok = false;
+			break;
+		}
+		opened[q] = p;
+		h.base[q] = static_cast<unsigned char *>(p);
+	}
+	long long * d_ok = nullptr;
+	FSB_CUDA(cudaMalloc(&d_ok, sizeof(long long)));
+	long long v = ok ? 1 : 0;
+	FSB_CUDA(cudaMemcpy(d_ok, &v, sizeof(v), cudaMemcpyHostToDevice));
+	FSB_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt64, ncclMin, c->nccl, c->stream));
+	FSB_CUDA(cudaMemcpyAsync(&v, d_ok, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(d_ok);
+	if (!v) {
+		for (void * p : opened)
+			if (p)
+				cudaIpcCloseMemHandle(p);
+		cudaFree(block);
+		return;
+	}
+	h.n_nbr = static_cast<int>(A->nbrs.size());
+	for (int k = 0; k < h.n_nbr; ++k) {
+		const neighbour & nb = A->nbrs[k];
+		h.nbr_rank[k] = nb.rank;
+		h.send_count[k] = nb.send_count;
+		h.contiguous[k] = nb.contiguous_start >= 0 ? 1 : 0;
+		h.send_start[k] = nb.contiguous_start >= 0 ? nb.contiguous_start : nb.send_offset;
+		h.dest_off[k] = dest_off[k];
+		h.recv_count[k] = nb.recv_count;
+	}
+	h.send_idx = A->d_send_idx;
+	h.n_ghost = A->n_ghost;
+	h.gmax = gmax;
+	FSB_CUDA(cudaMalloc(&h.counters, 2 * sizeof(unsigned)));
+	FSB_CUDA(cudaMemset(h.counters, 0, 2 * sizeof(unsigned)));
+	FSB_CUDA(cudaHostGetDevicePointer(&h.error_flag, c->h_xrank_error, 0));
+	halo_dev * d_h = nullptr;
+	FSB_CUDA(cudaMalloc(&d_h, sizeof(halo_dev)));
+	FSB_CUDA(cudaMemcpy(d_h, &h, sizeof(h), cudaMemcpyHostToDevice));
+	A->halo_p2p = d_h;
+	A->halo_block = block;
+	A->halo_counters = h.counters;
+	A->halo_opened = opened;
+	A->halo_epoch = 0;
+	long long total_send = 0;
+	for (const neighbour & nb : A->nbrs)
+		total_send += nb.send_count;
+	A->halo_push_ctas = static_cast<int>(std::max<long long>(1, std::min<long long>(64, (total_send + 2047) / 2048)));
+	A->halo_unpack_ctas = static_cast<int>(std::max<long long>(1, std::min<long long>(64, (A->n_ghost + 2047) / 2048)));
+}
+
+void halo_p2p_destroy(fsb_parcsr_s * A) {
+	if (!A->halo_p2p)
+		return;
+	for (void * p : A->halo_opened)
+		if (p)
+			cudaIpcCloseMemHandle(p);
+	cudaFree(A->halo_counters);
+	cudaFree(A->halo_block);
+	cudaFree(A->halo_p2p);
+	A->halo_p2p = nullptr;
+}
+
+// start exchange number ++epoch: push my boundary entries.  Runs on the communication stream (after
+// everything already queued on the compute stream) so it overlaps the diag-block SpMV.
+void halo_p2p_push(fsb_parcsr_s * A, fsb_vec_s * x) {
+	fsb_ctx_s * c = A->ctx;
+	++A->halo_epoch;
+	FSB_CUDA(cudaEventRecord(c->ev_main, c->stream));
+	FSB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_main, 0));
+	halo_push_kernel<<<A->halo_push_ctas, HALO_THREADS, 0, c->comm_stream>>>(static_cast<const halo_dev *>(A->halo_p2p),
+	                                                                          x->d, A->halo_epoch);
+	FSB_CUDA(cudaGetLastError());
+	FSB_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
+	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+	c->stats[FSB_STAT_HALO_EXCHANGES]++;
+}
+
+// finish it: ghosts of x become valid (compute stream)
+void halo_p2p_unpack(fsb_parcsr_s * A, fsb_vec_s * x) {
+	fsb_ctx_s * c = A->ctx;
+	halo_unpack_kernel<<<A->halo_unpack_ctas, HALO_THREADS, 0, c->stream>>>(static_cast<const halo_dev *>(A->halo_p2p),
+	                                                                         x->d + x->n_owned, A->halo_epoch);
+	FSB_CUDA(cudaGetLastError());
+	// my own push has long finished by now (the peers waited for it); ordering it before whatever
+	// the compute stream does next keeps later writers of x from racing with it
+	FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+	x->halo_valid = true;
+	x->halo_for = A;
+}
+
+} // namespace fsb

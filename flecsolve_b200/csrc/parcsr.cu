@@ -5,6 +5,7 @@
 // (topo/csr.hh:116-187,277-304), mat::parcsr_ops::spmv (matrices/parcsr.hh:61-91),
 // mg::bound_jacobi::relax (solvers/mg/jacobi.hh:44-93), Dinv() (util/test/mesh.hh:123-140).
 #include <algorithm>
+#include <cstdlib>
 #include <cub/cub.cuh>
 #include <numeric>
 #include <thrust/iterator/transform_iterator.h>
@@ -155,6 +156,16 @@ static void build_halo_plan(fsb_parcsr_s * A) {
 		A->d_send_buf = dev_alloc<double>(static_cast<size_t>(send_total));
 		FSB_CUDA(cudaStreamSynchronize(c->stream));
 	}
+	// where my entries land in each neighbour's ghost interval: ghosts are ordered by owner rank,
+	// so it is the number of entries that neighbour receives from lower ranks
+	std::vector<int64_t> dest_off;
+	for (const neighbour & nb : A->nbrs) {
+		int64_t off = 0;
+		for (int s = 0; s < me; ++s)
+			off += all[static_cast<size_t>(nb.rank) * P + s];
+		dest_off.push_back(off);
+	}
+	halo_p2p_setup(A, dest_off);
 }
 
 __global__ void pack_kernel(const double * __restrict__ x, const int32_t * __restrict__ idx, double * __restrict__ buf,
@@ -191,6 +202,7 @@ static void halo_exchange_async(fsb_parcsr_s * A, fsb_vec_s * x) {
 	FSB_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
 	c->stats[FSB_STAT_HALO_EXCHANGES]++;
 	x->halo_valid = true;
+	x->halo_for = A;
 }
 
 void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x) {
@@ -199,6 +211,11 @@ void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x) {
 	if (c->nranks == 1 || A->nbrs.empty())
 		return;
 	FSB_REQUIRE(x->n_owned == A->n_local && x->n_ghost >= A->n_ghost, "halo_exchange: vector does not match the matrix");
+	if (A->halo_p2p) {
+		halo_p2p_push(A, x);
+		halo_p2p_unpack(A, x);
+		return;
+	}
 	halo_exchange_async(A, x);
 	FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
 }
@@ -210,28 +227,39 @@ void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot) {
 	fsb_parcsr_s * A = sp.A;
 	fsb_vec_s *x = sp.x, *y = sp.y;
 	const bool multi = c->nranks > 1 && !A->nbrs.empty();
-	bool waited = true;
-	if (multi && !x->halo_valid) {
-		halo_exchange_async(A, x); // overlaps the diag block below
-		waited = false;
+	bool waited = true, unpack = false;
+	static const bool debug_skip_halo = std::getenv("FSB_DEBUG_SKIP_HALO") != nullptr; // timing experiments only
+	if (multi && !(x->halo_valid && x->halo_for == A) && !debug_skip_halo) {
+		if (A->halo_p2p) {
+			halo_p2p_push(A, x); // peers' pushes land while the diag block below runs
+			unpack = true;
+		}
+		else {
+			halo_exchange_async(A, x); // NCCL on the communication stream, overlaps the diag block
+			waited = false;
+		}
 	}
 	const double * u = nullptr;
 	if (dot) {
 		fsb_vec_s * other = dot->x == y ? dot->y : dot->x;
 		u = other->d; // other == y gives sum y^2
 	}
-	const int np_diag = launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream);
-	int np_offd = 0;
-	if (A->offd.n_blk > 0) {
+	const bool has_offd = A->offd.n_blk > 0;
+	const int64_t token = dot ? dot->token : 0;
+	// the launch that runs last folds the dot partials (no separate fold kernel)
+	const int np_diag = launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream, has_offd ? 0 : token);
+	if (unpack)
+		halo_p2p_unpack(A, x);
+	if (has_offd) {
 		if (!waited)
 			FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
 		waited = true;
-		np_offd = launch_spmv(c, A->offd, x->d, y->d, true, u, c->d_partials, np_diag, c->stream);
+		launch_spmv(c, A->offd, x->d, y->d, true, u, c->d_partials, np_diag, c->stream, token);
 	}
 	if (!waited) // ghosts were requested but no row uses them: still order the streams
 		FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
-	if (dot)
-		finalize_reduction(c, np_diag + np_offd, dot->token, 0);
+	if (dot && A->diag.n_blk == 0 && !has_offd)
+		finalize_reduction(c, 0, dot->token, 0); // empty local matrix: publish 0
 	y->halo_valid = false;
 }
 
@@ -581,6 +609,13 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 			A->nbrs.push_back(nb);
 		}
 	}
+	if (P > 1) { // collective: every rank takes part even if it had no ghosts
+		std::vector<int64_t> dest_off;
+		for (const neighbour & nb : A->nbrs)
+			dest_off.push_back(nb.rank < me ? (nb.rank > 0 ? plane : 0) : 0); // my plane lands after its lower ghosts
+		FSB_CUDA(cudaStreamSynchronize(c->stream));
+		halo_p2p_setup(A, dest_off);
+	}
 	FSB_CUDA(cudaStreamSynchronize(c->stream));
 	cudaFree(cnt_d);
 	cudaFree(cnt_o);
@@ -591,6 +626,7 @@ void fsb_parcsr_destroy_impl(fsb_parcsr_s * A) {
 	flush(A->ctx);
 	cudaStreamSynchronize(A->ctx->stream);
 	cudaStreamSynchronize(A->ctx->comm_stream);
+	halo_p2p_destroy(A);
 	free_block(A->diag);
 	free_block(A->offd);
 	cudaFree(A->d_colmap);
@@ -665,9 +701,15 @@ void fsb_parcsr_jacobi_relax_impl(fsb_parcsr_s * A, double omega, int64_t nrelax
 	const bool multi = c->nranks > 1 && !A->nbrs.empty();
 	for (int64_t s = 0; s < nrelax; ++s) {
 		// tmp = x over the whole span incl. ghosts (mg/jacobi.hh:63): refresh ghosts of x, then copy
-		if (multi && !x->halo_valid) {
-			halo_exchange_async(A, x);
-			FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+		if (multi && !(x->halo_valid && x->halo_for == A)) {
+			if (A->halo_p2p) {
+				halo_p2p_push(A, x);
+				halo_p2p_unpack(A, x);
+			}
+			else {
+				halo_exchange_async(A, x);
+				FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+			}
 		}
 		FSB_CUDA(cudaMemcpyAsync(tmp->d, x->d, (x->n_owned + A->n_ghost) * sizeof(double), cudaMemcpyDeviceToDevice,
 		                         c->stream));

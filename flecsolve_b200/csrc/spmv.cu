@@ -30,7 +30,6 @@
 namespace fsb {
 
 constexpr int SPMV_MAX_THREADS = 544; // 512 consumer threads + one producer warp
-constexpr int GATHER = 8;
 
 // one row block = the unit of work of a pipeline stage
 struct blk_desc {
@@ -50,10 +49,15 @@ struct spmv_args {
 	const double * x;
 	double * y;
 	const double * u; // dot operand or nullptr; u == y means sum y_i^2
-	double * partials; // one per CTA
+	double * partials; // one per CTA (this launch writes [fold_extra, fold_extra + gridDim.x))
+	unsigned * sched; // [0] next unclaimed row block (dynamic scheduling), [1] finished CTAs (last-CTA election)
+	red_out result; // where the folded dot goes (token == 0: do not fold in this launch)
+	const xrank_info * xr; // cross-rank all-reduce over peer memory, or nullptr
+	int fold_extra; // partials written by an earlier launch that take part in the fold
 	int n_blk;
 	int cap; // nnz capacity of one stage (multiple of 4, includes alignment slack)
 	int rcap; // row-offset capacity of one stage
+	int chunk; // row blocks claimed per atomic (1..4)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) {
@@ -96,8 +100,10 @@ __device__ __forceinline__ void consumer_sync(int nconsumers) {
 // Warp-specialised: warp 0 is the producer (one lane issues descriptor loads and bulk copies and
 // runs up to NSTAGE row blocks ahead, throttled by the `empty` barriers); all other warps are
 // consumers (wait `full`, multiply thread-per-row out of shared memory, release the stage).
-template<class OffT, int NSTAGE, bool ACC, bool DOT, bool ROWLIST>
-__global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const __grid_constant__ spmv_args a) {
+// GATHER: x[col] loads in flight per thread before the in-order sum (8 for short rows; 32 covers a
+// whole 27-point row in one round trip to L2 at the price of registers)
+template<class OffT, int NSTAGE, bool ACC, bool DOT, bool ROWLIST, int GATHER>
+__global__ void __launch_bounds__(GATHER > 8 ? 288 : SPMV_MAX_THREADS, 2) spmv_stream_kernel(const __grid_constant__ spmv_args a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint64_t full[NSTAGE], empty[NSTAGE];
 	__shared__ blk_desc sdesc[NSTAGE];
@@ -108,7 +114,6 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const 
 	const double * __restrict__ x = a.x;
 	const int tid = threadIdx.x;
 	const int nconsumers = blockDim.x - 32;
-	const int first = blockIdx.x, step = gridDim.x;
 
 	if (tid == 0) {
 		for (int s = 0; s < NSTAGE; ++s) {
@@ -124,22 +129,34 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const 
 
 	if (tid < 32) {
 		// ------------------------------------------------ producer
-		// The whole warp fetches block descriptors 32 iterations at a time (lane l holds the
-		// descriptor of iteration base + l, the next batch is already in flight) so their DRAM
-		// latency never sits between a freed stage and the next bulk copy; lane 0 issues.
+		// Row blocks are claimed dynamically, CHUNK (<= 4) consecutive blocks per atomic: a CTA that starts
+		// late (e.g. its SM was busy with an NCCL kernel) simply takes fewer blocks, so the launch
+		// never degrades into a second wave, and blocks are still handed out in row order (x stays
+		// in L2).  Lane l holds the descriptor of block base + l; the next claim and its descriptor
+		// loads are issued before the current chunk is staged, so neither the atomic nor the DRAM
+		// latency of the descriptors sits between a freed stage and the next bulk copy.
+		const int CHUNK = a.chunk; // 1..4, chosen on the host so that every CTA sees several claims
 		const int lane = tid;
-		const int niter = first < a.n_blk ? (a.n_blk - first + step - 1) / step : 0;
-		auto fetch = [&](int iter) {
+		auto claim = [&]() {
+			int base = 0;
+			if (lane == 0)
+				base = static_cast<int>(atomicAdd(&a.sched[0], static_cast<unsigned>(CHUNK)));
+			return __shfl_sync(0xffffffffu, base, 0);
+		};
+		auto fetch = [&](int base) {
 			blk_desc d{};
-			if (iter < niter)
-				d = a.desc[first + static_cast<long long>(iter) * step];
+			if (lane < CHUNK && base + lane < a.n_blk)
+				d = a.desc[base + lane];
 			return d;
 		};
-		blk_desc cur = fetch(lane);
-		for (int base = 0; base < niter; base += 32) {
-			const blk_desc nxt = fetch(base + 32 + lane);
-			const int jmax = min(32, niter - base);
-			for (int j = 0; j < jmax; ++j) {
+		int base = claim();
+		blk_desc cur = fetch(base);
+		int it = 0;
+		while (base < a.n_blk) {
+			const int nbase = claim();
+			const blk_desc nxt = fetch(nbase);
+			const int jmax = min(CHUNK, a.n_blk - base);
+			for (int j = 0; j < jmax; ++j, ++it) {
 				blk_desc d;
 				d.z0 = __shfl_sync(0xffffffffu, cur.z0, j);
 				d.r0 = __shfl_sync(0xffffffffu, cur.r0, j);
@@ -147,7 +164,6 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const 
 				d.nnz = __shfl_sync(0xffffffffu, cur.nnz, j);
 				d.pad = 0;
 				if (lane == 0) {
-					const int it = base + j;
 					const int s = it % NSTAGE;
 					if (it >= NSTAGE)
 						mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
@@ -172,7 +188,15 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const 
 				}
 				__syncwarp();
 			}
+			base = nbase;
 			cur = nxt;
+		}
+		if (lane == 0) { // end-of-work marker for the consumers
+			const int s = it % NSTAGE;
+			if (it >= NSTAGE)
+				mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+			sdesc[s].nrows = -1;
+			mbar_arrive(&full[s]);
 		}
 	}
 	else {
@@ -194,11 +218,12 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const 
 			a.y[yr] = out;
 		};
 
-		int it = 0;
-		for (int blk = first; blk < a.n_blk; blk += step, ++it) {
+		for (int it = 0;; ++it) {
 			const int s = it % NSTAGE;
 			mbar_wait(&full[s], (it / NSTAGE) & 1);
 			const blk_desc d = sdesc[s];
+			if (d.nrows < 0)
+				break;
 			const unsigned char * base = smem + s * stage_bytes;
 			const double * sv = reinterpret_cast<const double *>(base);
 			const int32_t * sc = reinterpret_cast<const int32_t *>(base + static_cast<size_t>(a.cap) * 8);
@@ -269,10 +294,39 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const 
 		}
 	}
 
-	if constexpr (DOT) {
+	// ---- epilogue: the last CTA to finish folds the dot partials and re-arms the scheduler words
+	__shared__ bool is_last;
+	if constexpr (DOT)
 		dot_acc = block_fold<0>(dot_acc, scratch);
-		if (tid == 0)
-			a.partials[blockIdx.x] = dot_acc;
+	else
+		__syncthreads();
+	if (tid == 0) {
+		if constexpr (DOT)
+			a.partials[a.fold_extra + blockIdx.x] = dot_acc;
+		__threadfence();
+		is_last = atomicAdd(&a.sched[1], 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (is_last) {
+		if constexpr (DOT) {
+			if (a.result.token != 0) {
+				// fold every partial in a fixed order and publish like the element-wise epilogue
+				__threadfence();
+				const int total = a.fold_extra + static_cast<int>(gridDim.x);
+				double t = 0.0;
+				for (int i = tid; i < total; i += blockDim.x)
+					t += __ldcg(&a.partials[i]);
+				t = block_fold<0>(t, scratch);
+				if (a.xr)
+					t = xrank_allreduce<0>(a.xr, t, a.result.token, scratch);
+				if (tid == 0)
+					publish(a.result, t);
+			}
+		}
+		if (tid == 0) {
+			a.sched[0] = 0u;
+			a.sched[1] = 0u;
+		}
 	}
 }
 
@@ -300,24 +354,21 @@ __global__ void build_desc_kernel(const void * rowptr, bool wide, const int32_t 
 }
 
 // one CTA: fold `n` partials in fixed order and publish like the element-wise epilogue
-__global__ void __launch_bounds__(256) fold_partials_kernel(const double * partials, int n, red_out out) {
+__global__ void __launch_bounds__(256) fold_partials_kernel(const double * partials, int n, red_out out,
+                                                            const xrank_info * xr) {
 	__shared__ double scratch[32];
 	double t = 0.0;
 	for (int i = threadIdx.x; i < n; i += blockDim.x)
 		t += partials[i];
 	t = block_fold<0>(t, scratch);
-	if (threadIdx.x == 0) {
-		*out.d_value = t;
-		if (out.h_value) {
-			*reinterpret_cast<volatile double *>(out.h_value) = t;
-			__threadfence_system();
-			*reinterpret_cast<volatile long long *>(out.h_flag) = out.token;
-		}
-	}
+	if (xr)
+		t = xrank_allreduce<0>(xr, t, out.token, scratch);
+	if (threadIdx.x == 0)
+		publish(out, t);
 }
 
 struct spmv_config {
-	int nstage, threads, cap, rcap, grid;
+	int nstage, threads, cap, rcap, grid, gather;
 	size_t smem;
 };
 
@@ -338,7 +389,13 @@ static spmv_config configure(const fsb_ctx_s * c, const csr_block & B) {
 	const size_t stage_bytes = static_cast<size_t>(k.cap) * 12 + static_cast<size_t>(k.rcap) * (B.wide ? 8 : 4);
 	// consumer threads: one per row of a block, at most 512
 	int consumers = env_threads > 0 ? env_threads : (c->spmv_threads > 0 ? c->spmv_threads : 512);
-	consumers = std::min(consumers, 512);
+	static const int env_gather = env_int("FSB_SPMV_GATHER", 0);
+	// 8 gathers in flight per thread is the measured optimum; the 32-wide variant (a whole 27-point row
+	// per round trip) costs registers => resident CTAs and was slower on B200 (profiles/r1_spmv_sweep.txt)
+	k.gather = 8;
+	if (env_gather > 0)
+		k.gather = env_gather > 8 ? 32 : 8;
+	consumers = std::min(consumers, k.gather > 8 ? 256 : 512);
 	while (consumers > 64 && consumers / 2 >= B.max_blk_rows)
 		consumers /= 2;
 	k.threads = consumers + 32;
@@ -349,7 +406,7 @@ static spmv_config configure(const fsb_ctx_s * c, const csr_block & B) {
 	const size_t ctas_for_1024 = (1024 + consumers - 1) / consumers;
 	k.nstage = (2 * stage_bytes * ctas_for_1024 <= budget) ? 2 : 1;
 	if (env_stages > 0)
-		k.nstage = std::min(env_stages, 4);
+		k.nstage = std::min(env_stages, 2);
 	while (k.nstage > 1 && stage_bytes * k.nstage > budget)
 		--k.nstage;
 	k.smem = stage_bytes * k.nstage;
@@ -357,9 +414,9 @@ static spmv_config configure(const fsb_ctx_s * c, const csr_block & B) {
 	return k;
 }
 
-template<class OffT, int NSTAGE, bool ACC, bool DOT, bool ROWLIST>
+template<class OffT, int NSTAGE, bool ACC, bool DOT, bool ROWLIST, int GATHER>
 static int launch_variant(const spmv_args & a, const spmv_config & k, cudaStream_t s) {
-	auto kern = spmv_stream_kernel<OffT, NSTAGE, ACC, DOT, ROWLIST>;
+	auto kern = spmv_stream_kernel<OffT, NSTAGE, ACC, DOT, ROWLIST, GATHER>;
 	// resident CTAs per SM for this (threads, smem): persistent grid = exactly one wave
 	static int cached_threads = -1, cached_ctas = 0;
 	static size_t cached_smem = 0;
@@ -372,54 +429,56 @@ static int launch_variant(const spmv_args & a, const spmv_config & k, cudaStream
 		cached_smem = k.smem;
 		cached_ctas = nb;
 		if (std::getenv("FSB_SPMV_DEBUG"))
-			fprintf(stderr, "[fsb] spmv config: threads %d stages %d smem %zu B cap %d -> %d CTAs/SM\n", k.threads, NSTAGE,
-			        k.smem, k.cap, nb);
+			fprintf(stderr, "[fsb] spmv config: threads %d stages %d gather %d smem %zu B cap %d -> %d CTAs/SM\n", k.threads,
+			        NSTAGE, GATHER, k.smem, k.cap, nb);
 	}
 	int ctas = cached_ctas;
 	if (k.grid > 0)
 		ctas = std::min(ctas, k.grid);
 	const int grid = std::max(1, std::min(a.n_blk, SM_COUNT * ctas));
-	kern<<<grid, k.threads, k.smem, s>>>(a);
+	spmv_args b = a;
+	b.chunk = std::max(1, std::min(4, a.n_blk / (grid * 8))); // >= 8 claims per CTA, else finest grain
+	kern<<<grid, k.threads, k.smem, s>>>(b);
 	FSB_CUDA(cudaGetLastError());
 	return grid;
 }
 
-template<class OffT, int NSTAGE>
+template<class OffT, int NSTAGE, int GATHER>
 static int launch_flags(const spmv_args & a, const spmv_config & k, bool acc, bool dot, bool rowlist, cudaStream_t s) {
 	if (rowlist) { // off-process block: always accumulates
 		if (dot)
-			return launch_variant<OffT, NSTAGE, true, true, true>(a, k, s);
+			return launch_variant<OffT, NSTAGE, true, true, true, GATHER>(a, k, s);
 		else
-			return launch_variant<OffT, NSTAGE, true, false, true>(a, k, s);
+			return launch_variant<OffT, NSTAGE, true, false, true, GATHER>(a, k, s);
 	}
 	else if (acc) {
 		if (dot)
-			return launch_variant<OffT, NSTAGE, true, true, false>(a, k, s);
+			return launch_variant<OffT, NSTAGE, true, true, false, GATHER>(a, k, s);
 		else
-			return launch_variant<OffT, NSTAGE, true, false, false>(a, k, s);
+			return launch_variant<OffT, NSTAGE, true, false, false, GATHER>(a, k, s);
 	}
 	else {
 		if (dot)
-			return launch_variant<OffT, NSTAGE, false, true, false>(a, k, s);
+			return launch_variant<OffT, NSTAGE, false, true, false, GATHER>(a, k, s);
 		else
-			return launch_variant<OffT, NSTAGE, false, false, false>(a, k, s);
+			return launch_variant<OffT, NSTAGE, false, false, false, GATHER>(a, k, s);
 	}
 }
 
 template<class OffT>
 static int launch_stages(const spmv_args & a, const spmv_config & k, bool acc, bool dot, bool rowlist, cudaStream_t s) {
-	switch (k.nstage) {
-	case 1: return launch_flags<OffT, 1>(a, k, acc, dot, rowlist, s);
-	case 2: return launch_flags<OffT, 2>(a, k, acc, dot, rowlist, s);
-	case 3: return launch_flags<OffT, 3>(a, k, acc, dot, rowlist, s);
-	default: return launch_flags<OffT, 4>(a, k, acc, dot, rowlist, s);
-	}
+	if (k.gather > 8)
+		return k.nstage >= 2 ? launch_flags<OffT, 2, 32>(a, k, acc, dot, rowlist, s)
+		                     : launch_flags<OffT, 1, 32>(a, k, acc, dot, rowlist, s);
+	return k.nstage >= 2 ? launch_flags<OffT, 2, 8>(a, k, acc, dot, rowlist, s)
+	                     : launch_flags<OffT, 1, 8>(a, k, acc, dot, rowlist, s);
 }
 
-// y (+)= B x on stream s.  When dot_u != nullptr, CTA b writes its partial of sum y_i u_i
-// to d_partials[partial_offset + b].  Returns the number of CTAs launched (= partials written).
+// y (+)= B x on stream s.  When dot_u != nullptr, CTA b writes its partial of sum y_i u_i to
+// d_partials[partial_offset + b]; with fold_token > 0 the last CTA folds partials [0, partial_offset + grid)
+// into that reduction token.  Returns the number of CTAs launched (= partials written).
 int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
-                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s) {
+                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s, int64_t fold_token) {
 	if (B.n_blk == 0)
 		return 0;
 	const spmv_config k = configure(c, B);
@@ -433,7 +492,19 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y
 	a.x = x;
 	a.y = y;
 	a.u = dot_u;
-	a.partials = d_partials ? d_partials + partial_offset : nullptr;
+	a.partials = d_partials;
+	a.fold_extra = partial_offset;
+	a.sched = c->d_sched;
+	if (dot_u && fold_token > 0) {
+		const int slot = static_cast<int>(fold_token % FSB_RED_RING);
+		a.result.d_value = c->d_results + slot;
+		a.result.token = fold_token;
+		if (c->nranks == 1 || c->d_xrank) {
+			a.result.h_value = c->h_results_dev + slot;
+			a.result.h_flag = reinterpret_cast<long long *>(c->h_flags_dev + slot);
+		}
+		a.xr = c->d_xrank;
+	}
 	a.n_blk = B.n_blk;
 	a.cap = k.cap;
 	a.rcap = k.rcap;
@@ -448,6 +519,9 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y
 			c->prof_events.push_back(e);
 		}
 		FSB_CUDA(cudaEventRecord(c->prof_events[c->prof_used], s));
+		if (c->prof_tag.size() < c->prof_used / 2 + 1)
+			c->prof_tag.resize(c->prof_used / 2 + 1);
+		c->prof_tag[c->prof_used / 2] = rowlist ? 1 : 0;
 	}
 	const int grid = B.wide ? launch_stages<long long>(a, k, accumulate, dot, rowlist, s)
 	                        : launch_stages<int>(a, k, accumulate, dot, rowlist, s);
@@ -464,11 +538,11 @@ void finalize_reduction(fsb_ctx_s * c, int n_partials, int64_t token, int /*op_k
 	red_out r{};
 	r.d_value = c->d_results + slot;
 	r.token = token;
-	if (c->nranks == 1) {
+	if (c->nranks == 1 || c->d_xrank) {
 		r.h_value = c->h_results_dev + slot;
 		r.h_flag = reinterpret_cast<long long *>(c->h_flags_dev + slot);
 	}
-	fold_partials_kernel<<<1, 256, 0, c->stream>>>(c->d_partials, n_partials, r);
+	fold_partials_kernel<<<1, 256, 0, c->stream>>>(c->d_partials, n_partials, r, c->d_xrank);
 	FSB_CUDA(cudaGetLastError());
 	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
 }
@@ -514,6 +588,12 @@ void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * hos
 		while (pow2 * 2 <= rows)
 			pow2 *= 2;
 		rows = pow2;
+		// small matrices (the off-process block of a slab): one row block per resident CTA, so the
+		// whole block is a single latency-bound pass instead of several sequential ones
+		int fit = 32;
+		while (fit < rows && static_cast<long long>(fit) * SM_COUNT * 2 < B.n_rows)
+			fit *= 2;
+		rows = std::min(rows, fit);
 		if (c->spmv_rows_per_cta > 0)
 			rows = c->spmv_rows_per_cta;
 		if (env_rows > 0)

@@ -17,6 +17,7 @@
 #include "flecsolve/solvers/cg.hh"
 #include "flecsolve/solvers/gmres.hh"
 #include "flecsolve/solvers/mg/jacobi.hh"
+#include "flecsolve/time-integrators/bdf.hh"
 #include "flecsolve/time-integrators/operator_adapter.hh"
 #include "flecsolve/vectors/multi.hh"
 
@@ -107,6 +108,28 @@ struct fsbh_options {
 	int use_zero_guess;
 	int max_krylov_dim, restart, pre_side_left; // gmres
 	int ev_start, ev_stop; // record CUDA events 0 / 1 after this many iterations (-1: never)
+};
+
+// settings of time_integrator::bdf (enum values in the order of bdf_parameters.hh)
+struct fsbh_bdf_options {
+	int method; // 0 CN, 1 BE, 2..6 BDF2..BDF6
+	int starting; // 0 CN, 1 BE
+	int predictor; // 0 ab2, 1 leapfrog
+	int strategy; // 0 truncation-error, 1 constant, 2 final-constant, 3 limit-relative-change
+	int controller; // 0 H211b, 1 PC.4.7, 2 PC11, 3 Deadbeat
+	int use_pi_controller;
+	int norm; // 0 inf, 1 l2
+	int error_scaling; // 0 fixed-resolution, 1 fixed-scaling
+	double time_rtol, time_atol, problem_scale;
+	double initial_time, final_time, initial_dt, max_dt, min_dt;
+	int max_steps;
+	int max_attempts; // stop after this many advance() calls (0: until final_time)
+};
+
+struct fsbh_bdf_result {
+	int attempts, steps, rejects;
+	double final_time, value_max, value_l2; // max and l2 norm of the final solution
+	int inner_iterations; // total Krylov iterations over all attempts (heat driver)
 };
 
 }
@@ -318,6 +341,181 @@ int fsbh_solve_subset(fsb_ctx_t ctx_h, fsb_parcsr_t Ah, int which, const fsbh_op
 		device::check(fsb_vec_download(x0.data.handle(), x_host, n, 0));
 		device::check(fsb_vec_download(x1.data.handle(), x_host + n, n, 0));
 		fill(info, si, 0);
+	});
+}
+
+// ---- time integration (time-integrators/bdf.hh) ------------------------------------------------
+} // extern "C"
+
+namespace {
+
+time_integrator::bdf::settings bdf_settings(const fsbh_bdf_options & o) {
+	namespace b = time_integrator::bdf;
+	b::settings s{};
+	s.initial_time = o.initial_time;
+	s.final_time = o.final_time;
+	s.max_steps = o.max_steps;
+	s.max_dt = o.max_dt;
+	s.min_dt = o.min_dt;
+	s.initial_dt = o.initial_dt;
+	s.integrator = static_cast<b::method>(o.method);
+	s.starting_integrator = static_cast<b::method>(o.starting);
+	s.predictor = static_cast<b::predictor>(o.predictor);
+	s.timestep_strategy = static_cast<b::strategy>(o.strategy);
+	s.pi_controller_type = static_cast<b::controller>(o.controller);
+	s.use_pi_controller = o.use_pi_controller != 0;
+	s.time_trunc_err_norm = o.norm == 0 ? vec::norm_type::inf : vec::norm_type::l2;
+	s.time_error_scaling = static_cast<b::error_scaling>(o.error_scaling);
+	s.time_rtol = o.time_rtol;
+	s.time_atol = o.time_atol;
+	s.problem_scales = {o.problem_scale};
+	return s;
+}
+
+// the reference test's scalar decay operator (time-integrators/test/implicit.cc:15-50): F(x) = lambda x,
+// apply() = x - gamma F(x)
+struct rate_params {
+	double lambda, gamma;
+};
+struct rate : op::base<rate_params> {
+	explicit rate(double lambda) : op::base<rate_params>(rate_params{lambda, 1.}) {}
+	template<class D, class R>
+	void apply(const D & x, R & y) const {
+		apply_rhs(x, y);
+		y.axpy(-params.gamma, y, x);
+	}
+	template<class D, class R>
+	void apply_rhs(const D & x, R & y) const {
+		y.scale(params.lambda, x);
+	}
+	template<class V>
+	bool is_valid(const V &) {
+		return true;
+	}
+	double get_scaling() const { return params.gamma; }
+	void set_scaling(double g) { params.gamma = g; }
+	double get_rate() const { return params.lambda; }
+};
+struct rate_solver : op::base<> {
+	explicit rate_solver(op::handle<op::core<rate>> h) : F(h) {}
+	template<class D, class R>
+	solve_info apply(const D & b, R & x) const {
+		const double rhs = b.min().get();
+		const auto & o = F.get();
+		x.set_scalar(rhs / (1. - o.get_rate() * o.get_scaling()));
+		solve_info info;
+		info.status = solve_info::stop_reason::converged_atol;
+		return info;
+	}
+	op::handle<op::core<rate>> F;
+};
+
+// the protocol every flecsolve application uses to drive an integrator (examples/heat_equation/implicit.cc:38-53)
+template<class TI, class Vec, class OnAttempt>
+void integrate(TI & ti, Vec & u, Vec & unew, int max_attempts, fsbh_bdf_result & res, OnAttempt && on_attempt) {
+	double dt = ti.get_current_dt();
+	bool first_step = true;
+	res.attempts = 0;
+	while (ti.get_current_time() < ti.get_final_time() && (max_attempts <= 0 || res.attempts < max_attempts)) {
+		ti.advance(dt, first_step, u, unew);
+		const bool good = ti.check_solution();
+		on_attempt(res.attempts, dt, good, unew);
+		++res.attempts;
+		if (good) {
+			ti.update();
+			std::swap(u, unew);
+			first_step = false;
+		}
+		dt = ti.get_next_dt(good);
+	}
+	res.steps = ti.get_current_step();
+	res.rejects = ti.num_step_rejects();
+	res.final_time = ti.get_current_time();
+	res.value_max = u.max().get();
+	res.value_l2 = u.l2norm().get();
+}
+
+}
+
+extern "C" {
+
+// x' = lambda x, x(0) = ic on every entry of a vector living on A's topology, exact inner solver.
+// step_*[k] describe attempt k: the dt tried, whether it was accepted, max of the candidate solution.
+int fsbh_bdf_rate(fsb_ctx_t ctx_h, fsb_parcsr_t Ah, const fsbh_bdf_options * o, double lambda, double ic,
+                  fsbh_bdf_result * res, double * step_dt, int * step_good, double * step_val, int cap) {
+	return guarded([&] {
+		using namespace time_integrator;
+		device::context ctx(ctx_h);
+		op::core<parcsr> A(ctx, Ah, false);
+		static const vec_def ud, unewd;
+		auto u = vec::make(ud(A.data.topo()));
+		auto unew = vec::make(unewd(A.data.topo()));
+		auto F = op::make_shared<rate>(lambda);
+		auto solver = op::make_shared<rate_solver>(F);
+		bdf::integrator ti(bdf::parameters(bdf_settings(*o), F, bdf::make_work(u), solver));
+		u.set_scalar(ic);
+		*res = fsbh_bdf_result{};
+		integrate(ti, u, unew, o->max_attempts, *res, [&](int k, double dt, bool good, auto & cand) {
+			if (k < cap) {
+				step_dt[k] = dt;
+				step_good[k] = good ? 1 : 0;
+				step_val[k] = cand.max().get();
+			}
+		});
+	});
+}
+
+// u_t = F u with F = the session's matrix (e.g. alpha/h^2 times the negative 7-point stencil), implicit
+// BDF steps with a Krylov inner solve of (I - gamma F) u = rhs (examples/heat_equation: operator_adapter +
+// bdf::integrator + Krylov solver).  Host buffers: u0 in, u out.
+int fsbh_bdf_heat(void * sv, const fsbh_bdf_options * o, const fsbh_options * so, const double * u0_host, double * u_host,
+                  fsbh_bdf_result * res, double * step_dt, int * step_good, int * step_iters, int cap) {
+	return guarded([&] {
+		using namespace time_integrator;
+		session & S = *static_cast<session *>(sv);
+		static const vec_def ud, unewd;
+		auto u = vec::make(ud(S.A.data.topo()));
+		auto unew = vec::make(unewd(S.A.data.topo()));
+		const std::int64_t n = fsb_vec_local_size(u.data.handle());
+		device::check(fsb_vec_upload(u.data.handle(), u0_host, n, 0));
+
+		auto F = op::make_shared<operator_adapter<matrix_rhs>>(&S.A);
+		int total_iters = 0, last_iters = 0;
+		auto count = [&](const auto &, double) {
+			++last_iters;
+			return false;
+		};
+		*res = fsbh_bdf_result{};
+		auto run = [&](auto slv_op) {
+			auto solver = op::make_shared(std::move(slv_op));
+			bdf::integrator ti(bdf::parameters(bdf_settings(*o), F, bdf::make_work(u), solver));
+			integrate(ti, u, unew, o->max_attempts, *res, [&](int k, double dt, bool good, auto &) {
+				if (k < cap) {
+					step_dt[k] = dt;
+					step_good[k] = good ? 1 : 0;
+					step_iters[k] = last_iters;
+				}
+				total_iters += last_iters;
+				last_iters = 0;
+			});
+		};
+		if (so->solver == 1) {
+			gmres::settings st{{so->maxiter, so->rtol, so->atol, so->use_zero_guess != 0},
+			                   so->max_krylov_dim,
+			                   gmres::precond_side::right,
+			                   so->restart != 0};
+			run(gmres::solver(st, gmres::make_work(u))(F, op::I, std::ref(count)));
+		}
+		else if (so->solver == 2) {
+			bicgstab::settings st{{so->maxiter, so->rtol, so->atol, so->use_zero_guess != 0}};
+			run(bicgstab::solver(st, bicgstab::make_work(u))(F, op::I, std::ref(count)));
+		}
+		else {
+			run(cg::solver(cg::settings{so->maxiter, so->rtol, so->atol, so->use_zero_guess != 0}, cg::make_work(u))(
+				F, op::I, std::ref(count)));
+		}
+		res->inner_iterations = total_iters;
+		device::check(fsb_vec_download(u.data.handle(), u_host, n, 0));
 	});
 }
 

@@ -96,6 +96,8 @@ int fsb_ctx_event_elapsed_ms(fsb_ctx_t ctx, int slot_start, int slot_stop, doubl
 /* with FSB_OPT_PROFILE on: total device time and count of the SpMV kernels launched since the last
  * read (waits for them); used by bench.py for the roofline of the dominant kernel                 */
 int fsb_ctx_profile_read(fsb_ctx_t ctx, double * spmv_ms, int64_t * spmv_launches);
+/* same, split by block: index 0 = diag (owned columns) launches, 1 = offd (ghost columns) launches */
+int fsb_ctx_profile_read_split(fsb_ctx_t ctx, double * ms2, int64_t * launches2);
 
 /* ---- vectors -----------------------------------------------------------
  * A vector is the device image of one field on the reference's `cols' index

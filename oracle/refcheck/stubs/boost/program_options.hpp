@@ -13,6 +13,11 @@ struct typed_value : value_semantic {
 	typed_value * default_value(const T &) { return this; }
 	template<class U>
 	typed_value * default_value(const U &) { return this; }
+	template<class U>
+	typed_value * default_value(const U &, const char *) { return this; }
+	template<class F>
+	typed_value * notifier(F &&) { return this; }
+	typed_value * multitoken() { return this; }
 };
 template<class T>
 typed_value<T> * value(T *) {

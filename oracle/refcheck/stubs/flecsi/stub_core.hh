@@ -25,6 +25,14 @@
 		std::cerr << msg << std::endl;                                               \
 		std::abort();                                                                \
 	} while (0)
+#define flog_error(msg)                                                              \
+	do {                                                                             \
+		std::cerr << msg << std::endl;                                               \
+	} while (0)
+#define flog_warn(msg)                                                               \
+	do {                                                                             \
+		std::cerr << msg << std::endl;                                               \
+	} while (0)
 #define FLECSI_INLINE_TARGET inline
 
 // forall / reduceall: only ever appear inside uninstantiated task templates
@@ -74,6 +82,16 @@ template<class T, unsigned short D>
 struct mdcolex {
 	mdcolex(T * ptr, std::array<std::size_t, D> ext) : p(ptr), e(ext) {}
 	T & operator()(std::size_t i, std::size_t j) const { return p[i + j * e[0]]; }
+	T * p;
+	std::array<std::size_t, D> e;
+};
+
+// row-major multi-dimensional view (solvers/nka.hh only; never instantiated by refcheck)
+template<class T, unsigned short D>
+struct mdspan {
+	using size_type = std::size_t;
+	mdspan(T * ptr, std::array<std::size_t, D> ext) : p(ptr), e(ext) {}
+	T & operator()(std::size_t i, std::size_t j) const { return p[i * e[1] + j]; }
 	T * p;
 	std::array<std::size_t, D> e;
 };

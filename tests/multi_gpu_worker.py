@@ -95,6 +95,10 @@ def main():
     m = min(len(hist), len(ohist), 30)
     assert np.allclose(hist[:m], ohist[:m], rtol=1e-8)
     assert ctx.stat("halo_exchanges") > 0 or P == 1
+    if P > 1 and os.environ.get("FSB_P2P_REDUCE") == "0":
+        assert ctx.stat("allreduces") > 0  # the NCCL path really ran
+    elif P > 1:
+        assert ctx.stat("allreduces") == 0  # reductions went through peer memory inside the kernels
     S.close()
     B.destroy()
     ctx.close()
