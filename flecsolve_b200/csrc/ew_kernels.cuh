@@ -269,4 +269,118 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_const
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// Generic program kernel: the same semantics as ew_program_kernel for ANY canonical program, with
+// the program passed at run time.  Slots are indexed dynamically, so they live in local memory
+// (L1-resident) instead of registers: slower per element than a registered instantiation, but one
+// pass over HBM instead of one pass per statement.  Used for statement groups that have no
+// compile-time instantiation (fuser.cu).
+struct interp_args {
+	ew_args a;
+	program p;
+};
+
+__device__ __forceinline__ void interp_exec(const program & P, const ew_args & a, double * v, double * acc) {
+	for (int i = 0; i < P.n; ++i) {
+		const stmt S = P.st[i];
+		switch (S.op) {
+		case OP_SET: v[S.z] = a.s[S.a]; break;
+		case OP_SCALE: v[S.z] = __dmul_rn(v[S.x], a.s[S.a]); break;
+		case OP_LIN2: v[S.z] = __dadd_rn(__dmul_rn(a.s[S.a], v[S.x]), __dmul_rn(a.s[S.b], v[S.y])); break;
+		case OP_MUL: v[S.z] = __dmul_rn(v[S.x], v[S.y]); break;
+		case OP_DIV: v[S.z] = __ddiv_rn(v[S.x], v[S.y]); break;
+		case OP_RECIP: v[S.z] = __ddiv_rn(1.0, v[S.x]); break;
+		case OP_ABS: v[S.z] = fabs(v[S.x]); break;
+		case OP_ADDS: v[S.z] = __dadd_rn(v[S.x], a.s[S.a]); break;
+		case RD_DOT: acc[S.z] = fma(v[S.x], v[S.y], acc[S.z]); break;
+		case RD_ASUM: acc[S.z] += fabs(v[S.x]); break;
+		case RD_AMAX: acc[S.z] = fmax(acc[S.z], fabs(v[S.x])); break;
+		case RD_MIN: acc[S.z] = fmin(acc[S.z], v[S.x]); break;
+		case RD_MAX: acc[S.z] = fmax(acc[S.z], v[S.x]); break;
+		case RD_POWSUM: acc[S.z] += pow(v[S.x], a.s[S.a]); break;
+		}
+	}
+}
+
+__device__ __forceinline__ double fold_rt(int f, double x, double y) { return f == 0 ? x + y : (f == 1 ? fmax(x, y) : fmin(x, y)); }
+__device__ __forceinline__ double ident_rt(int f) {
+	return f == 0 ? 0.0 : (f == 1 ? -__longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0x7ff0000000000000LL));
+}
+
+template<int UNUSED = 0> // template only so the header may be included by several translation units
+__global__ void __launch_bounds__(EW_BLOCK) ew_interp_kernel(const __grid_constant__ interp_args ia) {
+	const ew_args & a = ia.a;
+	const program & P = ia.p;
+	__shared__ int rfold[MAXR];
+	if (threadIdx.x == 0)
+		for (int i = 0; i < P.n; ++i)
+			if (is_reduction(P.st[i].op))
+				rfold[P.st[i].z] = fold_of(P.st[i].op);
+	__syncthreads();
+	double acc[MAXR];
+	for (int r = 0; r < P.nr; ++r)
+		acc[r] = ident_rt(rfold[r]);
+
+	const long long n2 = a.n >> 1;
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2; i += stride) {
+		double lo[MAXV], hi[MAXV];
+		for (int k = 0; k < P.nv; ++k)
+			if (P.load_mask & (1u << k)) {
+				const double2 t = reinterpret_cast<const double2 *>(a.v[k])[i];
+				lo[k] = t.x;
+				hi[k] = t.y;
+			}
+		interp_exec(P, a, lo, acc);
+		interp_exec(P, a, hi, acc);
+		for (int k = 0; k < P.nv; ++k)
+			if (P.store_mask & (1u << k))
+				reinterpret_cast<double2 *>(a.v[k])[i] = make_double2(lo[k], hi[k]);
+	}
+	if ((a.n & 1) && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+		const long long i = a.n - 1;
+		double t[MAXV];
+		for (int k = 0; k < P.nv; ++k)
+			if (P.load_mask & (1u << k))
+				t[k] = a.v[k][i];
+		interp_exec(P, a, t, acc);
+		for (int k = 0; k < P.nv; ++k)
+			if (P.store_mask & (1u << k))
+				a.v[k][i] = t[k];
+	}
+	if (P.nr > 0) {
+		__shared__ double scratch[32];
+		__shared__ bool is_last;
+		for (int r = 0; r < P.nr; ++r) {
+			const int f = rfold[r];
+			double t = f == 0 ? block_fold<0>(acc[r], scratch) : (f == 1 ? block_fold<1>(acc[r], scratch) : block_fold<2>(acc[r], scratch));
+			if (threadIdx.x == 0)
+				a.partials[r * a.partial_stride + blockIdx.x] = t;
+		}
+		if (threadIdx.x == 0) {
+			__threadfence();
+			is_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+		}
+		__syncthreads();
+		if (is_last) {
+			__threadfence();
+			for (int r = 0; r < P.nr; ++r) {
+				const int f = rfold[r];
+				double t = ident_rt(f);
+				for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += blockDim.x)
+					t = fold_rt(f, t, __ldcg(&a.partials[r * a.partial_stride + b]));
+				t = f == 0 ? block_fold<0>(t, scratch) : (f == 1 ? block_fold<1>(t, scratch) : block_fold<2>(t, scratch));
+				if (a.xr)
+					t = f == 0 ? xrank_allreduce<0>(a.xr, t, a.r[r].token, scratch)
+					           : (f == 1 ? xrank_allreduce<1>(a.xr, t, a.r[r].token, scratch)
+					                     : xrank_allreduce<2>(a.xr, t, a.r[r].token, scratch));
+				if (threadIdx.x == 0)
+					publish(a.r[r], t);
+			}
+			if (threadIdx.x == 0)
+				*a.counter = 0u;
+		}
+	}
+}
+
 } // namespace fsb

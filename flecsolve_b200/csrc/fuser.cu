@@ -202,13 +202,28 @@ static std::string describe(const pending * q, int n) {
 }
 
 struct bound_group {
-	launcher_t launch = nullptr;
+	launcher_t launch = nullptr; // registered instantiation, or nullptr => generic kernel with `prog`
 	ew_args args{};
+	program prog{};
 	int nr = 0;
 };
 
-// try to bind queue[i, i+len) to a registered kernel
-static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & g) {
+static void launch_interp(const bound_group & g, int want, cudaStream_t s) {
+	static int resident = 0;
+	if (resident == 0) {
+		int nb = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ew_interp_kernel<0>, EW_BLOCK, 0) != cudaSuccess || nb < 1)
+			nb = 4;
+		resident = nb * SM_COUNT;
+	}
+	interp_args ia;
+	ia.a = g.args;
+	ia.p = g.prog;
+	ew_interp_kernel<0><<<want < resident ? want : resident, EW_BLOCK, 0, s>>>(ia);
+}
+
+// bind queue[i, i+len) to a registered kernel; with allow_generic, to the generic kernel if there is none
+static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & g, bool allow_generic = false) {
 	raw_stmt rs[MAXS];
 	fsb_vec_s * vecs[3 * MAXS];
 	int nvec = 0;
@@ -229,9 +244,10 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 	if (!cr.ok)
 		return false;
 	auto it = registry().map.find(key_of(cr.p));
-	if (it == registry().map.end())
+	if (it == registry().map.end() && !allow_generic)
 		return false;
-	g.launch = it->second;
+	g.launch = it == registry().map.end() ? nullptr : it->second;
+	g.prog = cr.p;
 	g.nr = cr.p.nr;
 	ew_args & a = g.args;
 	for (int k = 0; k < cr.p.nv; ++k)
@@ -312,23 +328,27 @@ void flush(fsb_ctx_s * c) {
 		const int cap = c->fusion ? MAXS : 1;
 		while (j < total && j - i < cap && q[j].kind != pending::SPMV && length_of(q[j]) == n)
 			++j;
+		// the whole run as one launch: a registered instantiation if there is one, else the generic
+		// program kernel; a run that exceeds the slot limits is cut at the longest prefix that fits
 		bound_group g;
 		int len = j - i;
 		for (; len >= 1; --len)
-			if (bind_group(c, &q[i], len, g))
+			if (bind_group(c, &q[i], len, g, true))
 				break;
 		if (len < 1)
 			throw error(FSB_ERR_STATE, "no kernel for statement: " + describe(&q[i], 1));
-		if (len < j - i)
+		if (!g.launch)
 			c->stats[FSB_STAT_UNMATCHED_GROUPS]++;
 		if (c->trace)
-			fprintf(stderr, "[fsb] launch: %s%s\n", describe(&q[i], len).c_str(),
-			        len < j - i ? ("   <-- split from: " + describe(&q[i], j - i)).c_str() : "");
+			fprintf(stderr, "[fsb] launch%s: %s\n", g.launch ? "" : " (generic)", describe(&q[i], len).c_str());
 		if (n > 0 || (g.nr > 0 && c->nranks > 1)) {
 			long long packets = (n + 1) / 2;
 			long long want = (packets + EW_BLOCK - 1) / EW_BLOCK;
 			const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, MAX_RED_BLOCKS)));
-			g.launch(g.args, grid, c->stream);
+			if (g.launch)
+				g.launch(g.args, grid, c->stream);
+			else
+				launch_interp(g, grid, c->stream);
 			FSB_CUDA(cudaGetLastError());
 			c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
 		}

@@ -37,6 +37,35 @@ class Options(C.Structure):
                 ("ev_start", C.c_int), ("ev_stop", C.c_int)]
 
 
+class BdfOptions(C.Structure):
+    _fields_ = [("method", C.c_int), ("starting", C.c_int), ("predictor", C.c_int), ("strategy", C.c_int),
+                ("controller", C.c_int), ("use_pi_controller", C.c_int), ("norm", C.c_int), ("error_scaling", C.c_int),
+                ("time_rtol", C.c_double), ("time_atol", C.c_double), ("problem_scale", C.c_double),
+                ("initial_time", C.c_double), ("final_time", C.c_double), ("initial_dt", C.c_double),
+                ("max_dt", C.c_double), ("min_dt", C.c_double), ("max_steps", C.c_int), ("max_attempts", C.c_int)]
+
+
+class BdfResult(C.Structure):
+    _fields_ = [("attempts", C.c_int), ("steps", C.c_int), ("rejects", C.c_int), ("final_time", C.c_double),
+                ("value_max", C.c_double), ("value_l2", C.c_double), ("inner_iterations", C.c_int)]
+
+
+BDF_METHODS = {"CN": 0, "BE": 1, "BDF2": 2, "BDF3": 3, "BDF4": 4, "BDF5": 5, "BDF6": 6}
+BDF_CONTROLLERS = {"H211b": 0, "PC.4.7": 1, "PC11": 2, "Deadbeat": 3}
+
+
+def make_bdf_options(method="BDF2", starting="CN", predictor="leapfrog", strategy="truncation-error",
+                     controller="PC.4.7", use_pi_controller=True, norm="inf", error_scaling="fixed-resolution",
+                     time_rtol=1e-9, time_atol=1e-15, problem_scale=1.0, initial_time=0.0, final_time=1.0,
+                     initial_dt=0.0, max_dt=float("inf"), min_dt=0.0, max_steps=1000, max_attempts=0) -> BdfOptions:
+    strategies = {"truncation-error": 0, "constant": 1, "final-constant": 2, "limit-relative-change": 3}
+    return BdfOptions(BDF_METHODS[method], BDF_METHODS[starting], {"ab2": 0, "leapfrog": 1}[predictor],
+                      strategies[strategy], BDF_CONTROLLERS[controller], int(use_pi_controller),
+                      {"inf": 0, "l2": 1}[norm], {"fixed-resolution": 0, "fixed-scaling": 1}[error_scaling],
+                      time_rtol, time_atol, problem_scale, initial_time, final_time, initial_dt, max_dt, min_dt,
+                      max_steps, max_attempts)
+
+
 def make_options(solver="cg", precond=None, maxiter=1000, rtol=1e-9, atol=0.0, use_zero_guess=False, omega=2 / 3,
                  nrelax=1, max_krylov_dim=-1, restart=False, pre_side="right", ev_start=-1, ev_stop=-1) -> Options:
     return Options(SOLVERS[solver], PRECONDS[precond], omega, nrelax, maxiter, rtol, atol, int(use_zero_guess),
@@ -67,6 +96,11 @@ def lib() -> C.CDLL:
         L.fsbh_solve_subset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Options), _pd, _pd,
                                         C.POINTER(Info)]
         L.fsbh_vector_selftest.argtypes = [C.c_void_p, _pd]
+        _pi = C.POINTER(C.c_int)
+        L.fsbh_bdf_rate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BdfOptions), C.c_double, C.c_double,
+                                    C.POINTER(BdfResult), _pd, _pi, _pd, C.c_int]
+        L.fsbh_bdf_heat.argtypes = [C.c_void_p, C.POINTER(BdfOptions), C.POINTER(Options), _pd, _pd,
+                                    C.POINTER(BdfResult), _pd, _pi, _pi, C.c_int]
         _lib = L
     return _lib
 
@@ -118,6 +152,18 @@ class Session:
         _check(lib().fsbh_adapter_apply(self.h, gamma, _d(x), _d(y)))
         return y
 
+    def bdf_heat(self, u0, bdf: BdfOptions, cap=4096, **solver_kw):
+        """u_t = A u by time_integrator::bdf with a Krylov inner solver on (I - gamma A)."""
+        so = make_options(**solver_kw)
+        u0 = np.ascontiguousarray(u0, dtype=np.float64)
+        u = np.zeros_like(u0)
+        res = BdfResult()
+        dts, good, iters = np.zeros(cap), np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+        _check(lib().fsbh_bdf_heat(self.h, C.byref(bdf), C.byref(so), _d(u0), _d(u), C.byref(res), _d(dts),
+                                   good.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)), cap))
+        k = min(res.attempts, cap)
+        return u, res, dts[:k], good[:k], iters[:k]
+
     def vector_selftest(self) -> np.ndarray:
         out = np.zeros(16)
         _check(lib().fsbh_vector_selftest(self.h, _d(out)))
@@ -142,3 +188,13 @@ def solve_subset(ctx: F.Context, A: F.ParCSR, which: int, b, x0, **kw):
     x = np.array(x0, dtype=np.float64)
     _check(lib().fsbh_solve_subset(ctx.h, A.h, which, C.byref(opts), _d(b), _d(x), C.byref(info)))
     return x, info
+
+
+def bdf_rate(ctx: F.Context, A: F.ParCSR, bdf: BdfOptions, lam: float, ic: float, cap=4096):
+    """x' = lam x on every entry of a vector on A's topology (time-integrators/test/implicit.cc)."""
+    res = BdfResult()
+    dts, good, vals = np.zeros(cap), np.zeros(cap, dtype=np.int32), np.zeros(cap)
+    _check(lib().fsbh_bdf_rate(ctx.h, A.h, C.byref(bdf), lam, ic, C.byref(res), _d(dts),
+                               good.ctypes.data_as(C.POINTER(C.c_int)), _d(vals), cap))
+    k = min(res.attempts, cap)
+    return res, dts[:k], good[:k], vals[:k]

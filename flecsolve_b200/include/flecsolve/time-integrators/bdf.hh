@@ -219,7 +219,7 @@ protected:
 		}
 		else {
 			const int k = memory_size(m);
-			double h[6], n[6], a[7];
+			double h[6] = {}, n[6] = {}, a[7] = {};
 			h[0] = current_dt;
 			for (int i = 1; i < k; ++i)
 				h[i] = h[i - 1] + prev[i - 1].dt;

@@ -61,7 +61,7 @@ enum fsb_stat {
 	FSB_STAT_HALO_EXCHANGES = 2,
 	FSB_STAT_ALLREDUCES = 3,
 	FSB_STAT_HOST_SYNCS = 4,
-	FSB_STAT_UNMATCHED_GROUPS = 5 /* groups that had to be split (no fused kernel) */
+	FSB_STAT_UNMATCHED_GROUPS = 5 /* groups launched through the generic program kernel (no compile-time instantiation) */
 };
 
 const char * fsb_last_error(void);

@@ -49,6 +49,66 @@ def run_case(c):
     return info, b, x, hist
 
 
+REFCHECK_BDF = os.path.join(ROOT, "oracle", "_ref", "refcheck_bdf")
+
+# method, rtol, atol, initial_dt, max_dt, min_dt, final_time, lambda, ic, n, use_pi, controller, predictor
+BDF_RATE_CASES = [
+    ("BDF2", 1e-7, 1e-5, 0.5, 0.5, 0.001, 1.0, -1.0, 3.0, 1, 1, "PC.4.7", "leapfrog"),  # test/implicit.cfg [bdf-2]
+    ("BDF5", 1e-7, 1e-5, 0.5, 0.5, 0.001, 1.0, -1.0, 3.0, 1, 1, "PC.4.7", "leapfrog"),  # test/implicit.cfg [bdf-5]
+    ("BDF3", 1e-6, 1e-6, 0.25, 0.5, 0.001, 2.0, -2.0, 1.5, 7, 1, "H211b", "leapfrog"),
+    ("BDF4", 1e-6, 1e-6, 0.25, 0.5, 0.001, 1.0, -0.5, 2.0, 3, 0, "Deadbeat", "leapfrog"),
+    ("BDF6", 1e-7, 1e-6, 0.1, 0.5, 0.001, 1.0, -1.0, 1.0, 2, 1, "PC11", "leapfrog"),
+    ("BE", 1e-3, 1e-4, 0.1, 0.5, 0.001, 1.0, -1.0, 1.0, 2, 1, "PC.4.7", "leapfrog"),
+]
+# heat: method, rtol, atol, initial_dt, max_dt, min_dt, final_time, ic, (nx, ny, nz), length, solver, inner_rtol, maxiter, kdim, max_attempts
+BDF_HEAT_CASES = [
+    ("BDF2", 1e-2, 1e-4, 1e-2, 1e-2, 1e-6, 0.1, 50.0, (16, 16, 16), 10.0, "gmres", 1e-6, 10000, 50, 0),
+    ("BDF2", 1e-2, 1e-4, 1e-2, 1e-2, 1e-6, 0.1, 50.0, (12, 10, 8), 10.0, "cg", 1e-6, 10000, 50, 0),
+    ("BDF3", 1e-3, 1e-5, 5e-3, 1e-2, 1e-6, 0.05, 50.0, (14, 14, 14), 10.0, "gmres", 1e-8, 10000, 30, 0),
+]
+
+
+def heat_scale(dims, length):
+    """-alpha / h^2 with alpha = 1, h = length / (nx + 1): F = scale * stencil is the Laplacian."""
+    h = length / (dims[0] + 1)
+    return -1.0 / (h * h)
+
+
+def run_bdf_rate(c):
+    r = subprocess.run([REFCHECK_BDF, c[0], *[repr(float(v)) for v in c[1:9]], str(c[9]), str(c[10]), c[11], c[12]],
+                       capture_output=True, text=True, check=True)
+    return json.loads(r.stdout)
+
+
+def run_bdf_heat(c):
+    method, rtol, atol, dt0, dtmax, dtmin, tf, ic, dims, length, solver, irtol, imax, kdim, maxatt = c
+    out = tempfile.mktemp(suffix=".bin")
+    r = subprocess.run([REFCHECK_BDF, method, *[repr(float(v)) for v in (rtol, atol, dt0, dtmax, dtmin, tf, 0.0, ic)], "1",
+                        "1", "PC.4.7", "leapfrog", "heat", *map(str, dims), repr(heat_scale(dims, length)), solver,
+                        repr(float(irtol)), str(imax), str(kdim), str(maxatt), out], capture_output=True, text=True, check=True)
+    d = json.loads(r.stdout)
+    u = np.fromfile(out, dtype=np.float64)
+    os.unlink(out)
+    d["u_sha256"] = hashlib.sha256(u.tobytes()).hexdigest()
+    d["u_head"] = [float(v).hex() for v in u[len(u) // 2:len(u) // 2 + 8]]
+    return d
+
+
+def main_bdf():
+    out = {"generator": "tests/golden/make_golden.py (oracle/_ref/refcheck_bdf = the reference's bdf.hh, bdf.cc, gmres.hh, "
+                        "cg.hh, operator_adapter.hh + stubs)", "rate": [], "heat": []}
+    for c in BDF_RATE_CASES:
+        d = run_bdf_rate(c)
+        out["rate"].append({"case": list(c), "result": d})
+        print("bdf rate", c[0], "steps", d["nsteps"], "rejects", d["rejects"], "attempts", len(d["steps"]))
+    for c in BDF_HEAT_CASES:
+        d = run_bdf_heat(c)
+        out["heat"].append({"case": [c[0], *c[1:8], list(c[8]), *c[9:]], "result": d})
+        print("bdf heat", c[0], c[8], c[10], "steps", d["nsteps"], "rejects", d["rejects"], "inner", d["inner_iterations"])
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_bdf.json"), "w") as f:
+        json.dump(out, f, indent=0)
+
+
 def main():
     if not os.path.exists(REFCHECK):
         sys.path.insert(0, ROOT)
@@ -70,3 +130,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    main_bdf()
