@@ -29,9 +29,9 @@ enum ew_op : int {
 	RD_POWSUM = 21 // r[z] += pow(x, s[a])
 };
 
-constexpr int MAXS = 8; // statements per program
-constexpr int MAXV = 8; // distinct vectors per program
-constexpr int MAXSC = 16; // scalars per program
+constexpr int MAXS = 12; // statements per program
+constexpr int MAXV = 12; // distinct vectors per program
+constexpr int MAXSC = 24; // scalars per program
 constexpr int MAXR = 4; // reductions per program
 
 constexpr bool is_reduction(int op) { return op >= RD_FIRST; }

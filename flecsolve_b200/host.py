@@ -50,6 +50,12 @@ class BdfResult(C.Structure):
                 ("value_max", C.c_double), ("value_l2", C.c_double), ("inner_iterations", C.c_int)]
 
 
+class RkOptions(C.Structure):
+    _fields_ = [("order", C.c_int), ("initial_time", C.c_double), ("final_time", C.c_double), ("initial_dt", C.c_double),
+                ("max_dt", C.c_double), ("min_dt", C.c_double), ("max_steps", C.c_int), ("safety_factor", C.c_float),
+                ("atol", C.c_float), ("use_fixed_dt", C.c_int)]
+
+
 BDF_METHODS = {"CN": 0, "BE": 1, "BDF2": 2, "BDF3": 3, "BDF4": 4, "BDF5": 5, "BDF6": 6}
 BDF_CONTROLLERS = {"H211b": 0, "PC.4.7": 1, "PC11": 2, "Deadbeat": 3}
 
@@ -99,6 +105,8 @@ def lib() -> C.CDLL:
         _pi = C.POINTER(C.c_int)
         L.fsbh_bdf_rate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BdfOptions), C.c_double, C.c_double,
                                     C.POINTER(BdfResult), _pd, _pi, _pd, C.c_int]
+        L.fsbh_rk_rate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RkOptions), C.c_double, C.c_double,
+                                   C.POINTER(BdfResult), _pd, _pi, _pd, C.c_int]
         L.fsbh_bdf_heat.argtypes = [C.c_void_p, C.POINTER(BdfOptions), C.POINTER(Options), _pd, _pd,
                                     C.POINTER(BdfResult), _pd, _pi, _pi, C.c_int]
         _lib = L
@@ -196,5 +204,17 @@ def bdf_rate(ctx: F.Context, A: F.ParCSR, bdf: BdfOptions, lam: float, ic: float
     dts, good, vals = np.zeros(cap), np.zeros(cap, dtype=np.int32), np.zeros(cap)
     _check(lib().fsbh_bdf_rate(ctx.h, A.h, C.byref(bdf), lam, ic, C.byref(res), _d(dts),
                                good.ctypes.data_as(C.POINTER(C.c_int)), _d(vals), cap))
+    k = min(res.attempts, cap)
+    return res, dts[:k], good[:k], vals[:k]
+
+
+def rk_rate(ctx: F.Context, A: F.ParCSR, order: int, lam: float, ic: float, initial_dt, max_dt, min_dt, final_time,
+            safety_factor, atol, use_fixed_dt, cap=4096):
+    """x' = lam x with rk23 / rk45 (time-integrators/test/explicit.cc)."""
+    o = RkOptions(order, 0.0, final_time, initial_dt, max_dt, min_dt, 1000, safety_factor, atol, int(use_fixed_dt))
+    res = BdfResult()
+    dts, good, vals = np.zeros(cap), np.zeros(cap, dtype=np.int32), np.zeros(cap)
+    _check(lib().fsbh_rk_rate(ctx.h, A.h, C.byref(o), lam, ic, C.byref(res), _d(dts),
+                              good.ctypes.data_as(C.POINTER(C.c_int)), _d(vals), cap))
     k = min(res.attempts, cap)
     return res, dts[:k], good[:k], vals[:k]

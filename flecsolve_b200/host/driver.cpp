@@ -19,6 +19,7 @@
 #include "flecsolve/solvers/mg/jacobi.hh"
 #include "flecsolve/time-integrators/bdf.hh"
 #include "flecsolve/time-integrators/operator_adapter.hh"
+#include "flecsolve/time-integrators/rk45.hh"
 #include "flecsolve/vectors/multi.hh"
 
 using namespace flecsolve;
@@ -124,6 +125,14 @@ struct fsbh_bdf_options {
 	double initial_time, final_time, initial_dt, max_dt, min_dt;
 	int max_steps;
 	int max_attempts; // stop after this many advance() calls (0: until final_time)
+};
+
+struct fsbh_rk_options {
+	int order; // 23 or 45
+	double initial_time, final_time, initial_dt, max_dt, min_dt;
+	int max_steps;
+	float safety_factor, atol;
+	int use_fixed_dt;
 };
 
 struct fsbh_bdf_result {
@@ -396,6 +405,15 @@ struct rate : op::base<rate_params> {
 	void set_scaling(double g) { params.gamma = g; }
 	double get_rate() const { return params.lambda; }
 };
+// plain right-hand side F(x) = lambda x for the explicit integrators (test/explicit.cc)
+struct decay : op::base<> {
+	double lambda;
+	explicit decay(double l) : lambda(l) {}
+	template<class D, class R>
+	void apply(const D & x, R & y) const {
+		y.scale(lambda, x);
+	}
+};
 struct rate_solver : op::base<> {
 	explicit rate_solver(op::handle<op::core<rate>> h) : F(h) {}
 	template<class D, class R>
@@ -462,6 +480,62 @@ int fsbh_bdf_rate(fsb_ctx_t ctx_h, fsb_parcsr_t Ah, const fsbh_bdf_options * o, 
 				step_val[k] = cand.max().get();
 			}
 		});
+	});
+}
+
+// x' = lambda x with the explicit integrators rk23 / rk45, driven like time-integrators/test/explicit.cc:52-68
+int fsbh_rk_rate(fsb_ctx_t ctx_h, fsb_parcsr_t Ah, const fsbh_rk_options * o, double lambda, double ic,
+                 fsbh_bdf_result * res, double * step_dt, int * step_good, double * step_val, int cap) {
+	return guarded([&] {
+		using namespace time_integrator;
+		device::context ctx(ctx_h);
+		op::core<parcsr> A(ctx, Ah, false);
+		static const vec_def ud, unewd;
+		auto u = vec::make(ud(A.data.topo()));
+		auto unew = vec::make(unewd(A.data.topo()));
+		op::core<decay> F(lambda);
+		rk45::settings s{};
+		s.initial_time = o->initial_time;
+		s.final_time = o->final_time;
+		s.initial_dt = o->initial_dt;
+		s.max_dt = o->max_dt;
+		s.min_dt = o->min_dt;
+		s.max_steps = o->max_steps;
+		s.safety_factor = o->safety_factor;
+		s.atol = o->atol;
+		s.use_fixed_dt = o->use_fixed_dt != 0;
+		*res = fsbh_bdf_result{};
+		auto drive = [&](auto & ti) {
+			u.set_scalar(ic);
+			double dt = ti.get_current_dt();
+			while (ti.get_current_time() < ti.get_final_time()) {
+				ti.advance(dt, u, unew);
+				const bool good = ti.check_solution();
+				if (res->attempts < cap) {
+					step_dt[res->attempts] = dt;
+					step_good[res->attempts] = good ? 1 : 0;
+					step_val[res->attempts] = unew.max().get();
+				}
+				++res->attempts;
+				if (good || ti.fixed_dt()) {
+					ti.update();
+					std::swap(u, unew);
+				}
+				dt = ti.get_next_dt(good);
+			}
+			res->steps = ti.get_current_step();
+			res->final_time = ti.get_current_time();
+			res->value_max = u.max().get();
+			res->value_l2 = u.l2norm().get();
+		};
+		if (o->order == 23) {
+			rk23::integrator ti(rk23::parameters(static_cast<const rk23::settings &>(s), op::ref(F), rk23::make_work(u)));
+			drive(ti);
+		}
+		else {
+			rk45::integrator ti(rk45::parameters(s, op::ref(F), rk45::make_work(u)));
+			drive(ti);
+		}
 	});
 }
 

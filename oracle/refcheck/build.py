@@ -22,6 +22,7 @@ def main() -> int:
         ("refcheck_bdf", "refcheck_bdf.cpp", ["flecsolve/time-integrators/bdf.cc",
                                               "flecsolve/time-integrators/bdf_parameters.cc",
                                               "flecsolve/vectors/util.cc"]),
+        ("refcheck_rk", "refcheck_rk.cpp", []),
     ]
     rc = 0
     for name, driver, ref_units in targets:

@@ -94,6 +94,31 @@ def run_bdf_heat(c):
     return d
 
 
+REFCHECK_RK = os.path.join(ROOT, "oracle", "_ref", "refcheck_rk")
+# order, initial_dt, max_dt, min_dt, final_time, safety, atol, fixed, lambda, ic, n  (test/explicit.cfg [variable] / [fixed])
+RK_CASES = [
+    (23, 0.5, 0.5, 0.001, 1.0, 0.5, 1e-5, 0, -1.0, 3.0, 1),
+    (45, 0.5, 0.5, 0.001, 1.0, 0.5, 1e-5, 0, -1.0, 3.0, 1),
+    (23, 0.05, 0.5, 0.001, 1.0, 0.05, 1e-10, 1, -1.0, 3.0, 1),
+    (45, 0.05, 0.5, 0.001, 1.0, 0.05, 1e-10, 1, -1.0, 3.0, 1),
+    (23, 0.25, 0.5, 0.001, 2.0, 0.8, 1e-6, 0, -2.0, 1.5, 5),
+    (45, 0.25, 0.5, 0.001, 2.0, 0.8, 1e-7, 0, -2.0, 1.5, 5),
+]
+
+
+def main_rk():
+    out = {"generator": "tests/golden/make_golden.py (oracle/_ref/refcheck_rk = the reference's rk23.hh / rk45.hh + stubs)",
+           "cases": []}
+    for c in RK_CASES:
+        r = subprocess.run([REFCHECK_RK, str(c[0]), *[repr(float(v)) for v in c[1:7]], str(c[7]), repr(float(c[8])),
+                            repr(float(c[9])), str(c[10])], capture_output=True, text=True, check=True)
+        d = json.loads(r.stdout)
+        out["cases"].append({"case": list(c), "result": d})
+        print("rk", c[0], "fixed" if c[7] else "variable", "steps", d["nsteps"], "attempts", len(d["steps"]))
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_rk.json"), "w") as f:
+        json.dump(out, f, indent=0)
+
+
 def main_bdf():
     out = {"generator": "tests/golden/make_golden.py (oracle/_ref/refcheck_bdf = the reference's bdf.hh, bdf.cc, gmres.hh, "
                         "cg.hh, operator_adapter.hh + stubs)", "rate": [], "heat": []}
@@ -131,3 +156,4 @@ def main():
 if __name__ == "__main__":
     main()
     main_bdf()
+    main_rk()

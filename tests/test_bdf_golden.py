@@ -49,3 +49,14 @@ def test_live_refcheck_bdf_reproduces_golden():
     out = subprocess.run([exe, c[0], *[repr(float(v)) for v in c[1:9]], str(c[9]), str(c[10]), c[11], c[12]],
                          capture_output=True, text=True, check=True).stdout
     assert json.loads(out) == e["result"]
+
+
+def test_reference_kat_rk():
+    """time-integrators/test/explicit.cc:69-98 on the reference-generated goldens."""
+    rk = json.load(open(os.path.join(HERE, "golden", "reference_rk.json")))["cases"]
+    by = {(c["case"][0], c["case"][7]): c["result"] for c in rk if c["case"][8] == -1.0 and c["case"][9] == 3.0}
+    assert float.fromhex(by[(23, 1)]["error"]) < 1e-5 and float.fromhex(by[(45, 1)]["error"]) < 1e-9
+    assert by[(23, 0)]["nsteps"] == 32 and float.fromhex(by[(23, 0)]["error"]) < 1e-5
+    assert by[(45, 0)]["nsteps"] == 6 and float.fromhex(by[(45, 0)]["error"]) < 1e-6
+    for r in by.values():
+        assert float.fromhex(r["final_time"]) == 1.0

@@ -83,3 +83,21 @@ def test_heat_equation_matches_reference(ctx, entry):
     # physics: heat is conserved up to the Dirichlet boundary loss and the maximum principle holds
     assert u.min() >= -1e-9 and u.max() <= ic
     S.close(); A.destroy()
+
+
+RK = json.load(open(os.path.join(HERE, "golden", "reference_rk.json")))["cases"]
+
+
+@pytest.mark.parametrize("entry", RK, ids=lambda e: f"rk{e['case'][0]}-{'fixed' if e['case'][7] else 'var'}-n{e['case'][10]}")
+def test_explicit_integrators_match_reference(ctx, entry):
+    order, dt0, dtmax, dtmin, tf, safety, atol, fixed, lam, ic, n = entry["case"]
+    ref = entry["result"]
+    A = _topology(ctx, n)
+    res, dts, good, vals = H.rk_rate(ctx, A, order, lam, ic, dt0, dtmax, dtmin, tf, safety, atol, bool(fixed))
+    assert res.steps == ref["nsteps"] and res.attempts == len(ref["steps"])
+    assert np.array_equal(good, np.array([s[1] for s in ref["steps"]]))
+    assert np.allclose(dts, [float.fromhex(s[0]) for s in ref["steps"]], rtol=1e-10)
+    assert np.allclose(vals, [float.fromhex(s[2]) for s in ref["steps"]], rtol=1e-12)
+    assert abs(res.final_time - float.fromhex(ref["final_time"])) <= 1e-12
+    assert abs(res.value_max - float.fromhex(ref["value"])) <= 1e-12 * abs(res.value_max)
+    A.destroy()
