@@ -6,6 +6,7 @@
 // launches e.g. {x += a p; r -= a w; |r|^2} as ONE kernel when the norm is read.
 // Statements are evaluated in program order per element, so fusing never changes a
 // value; only reductions see a different (fixed, reproducible) summation order.
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -309,10 +310,31 @@ void flush(fsb_ctx_s * c) {
 	while (i < total) {
 		if (q[i].kind == pending::SPMV) {
 			// y = A x, optionally fused with a following dot that involves y
+			// (the dot may sit behind other SpMVs and dots of the same burst — vec::multi issues
+			// A0 x0, A1 x1, <r0,y0>, <r1,y1> — it commutes with them unless one of them writes an operand)
 			const pending * dot = nullptr;
-			if (c->fusion && i + 1 < total && q[i + 1].kind == pending::RED && q[i + 1].op == RD_DOT &&
-			    (q[i + 1].x == q[i].y || q[i + 1].y == q[i].y))
-				dot = &q[i + 1];
+			if (c->fusion) {
+				for (int j = i + 1; j < total; ++j) {
+					if (q[j].kind == pending::SPMV) {
+						if (q[j].y == q[i].y)
+							break;
+						continue;
+					}
+					if (q[j].kind != pending::RED || q[j].op != RD_DOT)
+						break;
+					if (q[j].x != q[i].y && q[j].y != q[i].y)
+						continue;
+					fsb_vec_s * u = q[j].x == q[i].y ? q[j].y : q[j].x;
+					bool clobbered = false;
+					for (int k = i + 1; k < j; ++k)
+						clobbered |= q[k].kind == pending::SPMV && q[k].y == u;
+					if (!clobbered) {
+						std::rotate(q.begin() + i + 1, q.begin() + j, q.begin() + j + 1);
+						dot = &q[i + 1];
+					}
+					break;
+				}
+			}
 			if (c->trace)
 				fprintf(stderr, "[fsb] launch: spmv%s\n", dot ? " + dot" : "");
 			spmv_group(c, q[i], dot);

@@ -256,3 +256,28 @@ def test_device_matches_reference_golden(ctx, entry):
     assert np.allclose(hist[:m], ref_hist[:m], rtol=1e-7)
     assert abs(np.linalg.norm(x) - float.fromhex(entry["x_norm2"])) <= 1e-6 * float.fromhex(entry["x_norm2"])
     S.close(); A.destroy()
+
+
+def test_config5_residual_history_parity(ctx):
+    """BASELINE config 5 (27-point, diag 26 / off -1, b = A 1, x0 = 0, Jacobi-CG) at 64^3: the first 50
+    residual norms agree with the oracle to 1e-8, plus a sampled-row SpMV check."""
+    nn = 64
+    rp, col, val = O.stencil_csr(27, nn, nn, nn)
+    n = nn ** 3
+    M = O.ParCSR(rp, col, val, colours=1)
+    b = M.spmv(np.ones(n))
+    _, oinfo, ohist = M.cg(b, dinv=M.dinv(), rtol=0.0, maxiter=50, history_cap=50)
+    A = F.ParCSR.stencil(ctx, 27, nn, nn, nn)
+    S = H.Session(ctx, A)
+    _, info, hist = S.solve(b, np.zeros(n), solver="cg", precond="dinv", rtol=0.0, maxiter=50, history_cap=50)
+    assert len(hist) == len(ohist) == 50
+    assert np.max(np.abs(hist - ohist) / ohist) <= 1e-8
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(n)
+    xv, yv = A.vector(x), A.vector()
+    A.spmv(xv, yv)
+    y = yv.download()
+    rows = rng.integers(0, n, 2000)
+    ref = np.array([val[rp[r]:rp[r + 1]] @ x[col[rp[r]:rp[r + 1]]] for r in rows])
+    assert np.max(np.abs(y[rows] - ref)) <= 1e-12 * np.abs(ref).max()
+    xv.destroy(); yv.destroy(); S.close(); A.destroy()

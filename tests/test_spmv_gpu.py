@@ -104,6 +104,38 @@ def test_fused_dot_matches_separate(ctx):
     A.destroy()
 
 
+def test_fused_dot_reaches_across_a_burst(ctx):
+    """vec::multi issues A0 x0, A1 x1, <r0,y0>, <r1,y1> (vectors/operations/multi.hh): each dot still rides in its SpMV."""
+    rp, col, val = O.stencil_csr(7, 12, 11, 10)
+    n = len(rp) - 1
+    rng = np.random.default_rng(9)
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    x0, x1, r0, r1 = (A.vector(rng.standard_normal(n)) for _ in range(4))
+    y0, y1 = A.vector(), A.vector()
+    e0 = O.csr_spmv(rp, col, val, x0.download())
+    e1 = O.csr_spmv(rp, col, val, x1.download())
+    ctx.reset_stats()
+    A.spmv(x0, y0)
+    A.spmv(x1, y1)
+    t0 = r0.dot_token(y0)
+    t1 = r1.dot_token(y1)
+    g0, g1 = ctx.get(t0), ctx.get(t1)
+    assert ctx.stat("launches") == 2
+    assert np.array_equal(y0.download(), e0) and np.array_equal(y1.download(), e1)
+    for got, e, r in ((g0, e0, r0), (g1, e1, r1)):
+        rr = r.download()
+        assert abs(got - rr @ e) <= 1e-13 * (np.abs(rr) @ np.abs(e))
+    # a dot whose other operand is overwritten by an intervening SpMV must not move ahead of it
+    ctx.reset_stats()
+    A.spmv(x0, y0)
+    A.spmv(x1, y1)
+    t = y0.dot_token(y1)
+    assert abs(ctx.get(t) - e0 @ e1) <= 1e-13 * (np.abs(e0) @ np.abs(e1))
+    for v in (x0, x1, r0, r1, y0, y1):
+        v.destroy()
+    A.destroy()
+
+
 def test_spmv_rejects_aliasing_and_size_mismatch(ctx):
     rp, col, val = O.stencil_csr(5, 8, 8)
     A = F.ParCSR.from_csr(ctx, 64, [0, 64], rp, col, val)
