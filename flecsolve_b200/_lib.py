@@ -147,8 +147,8 @@ def device_count() -> int:
 
 
 STAT = {"launches": 0, "fused_statements": 1, "halo_exchanges": 2, "allreduces": 3, "host_syncs": 4,
-        "unmatched_groups": 5}
-OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3, "profile": 4}
+        "unmatched_groups": 5, "wait_ns": 6, "flush_ns": 7}
+OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3, "profile": 4, "reproducible": 5}
 
 
 class Context:

@@ -155,6 +155,7 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 		c->device = device;
 		c->rank = rank;
 		c->nranks = nranks;
+		c->reproducible = nranks == 1;
 		FSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 		FSB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
 		FSB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
@@ -267,6 +268,9 @@ int fsb_ctx_set_option(fsb_ctx_t c, int option, int64_t value) {
 			break;
 		case FSB_OPT_PROFILE:
 			c->profile = value != 0;
+			break;
+		case FSB_OPT_REPRODUCIBLE:
+			c->reproducible = value != 0;
 			break;
 		default:
 			throw fsb::error(FSB_ERR_ARG, "unknown option");
@@ -591,6 +595,7 @@ static void wait_token(fsb_ctx_t c, fsb_token_t tok) {
 	FSB_REQUIRE(tok > 0 && tok < c->next_token, "unknown reduction token");
 	FSB_REQUIRE(tok + FSB_RED_RING > c->next_token - 1, "reduction token expired");
 	flush(c);
+	const auto t_begin = std::chrono::steady_clock::now();
 	const int slot = static_cast<int>(tok % FSB_RED_RING);
 	if (c->nranks > 1 && !c->d_xrank) {
 		FSB_CUDA(cudaEventSynchronize(c->token_event[slot]));
@@ -613,6 +618,8 @@ static void wait_token(fsb_ctx_t c, fsb_token_t tok) {
 			throw fsb::error(FSB_ERR_STATE, "cross-rank reduction timed out waiting for a peer");
 	}
 	c->stats[FSB_STAT_HOST_SYNCS]++;
+	c->stats[FSB_STAT_WAIT_NS] +=
+		std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
 }
 
 int fsb_red_wait(fsb_ctx_t c, fsb_token_t tok) {

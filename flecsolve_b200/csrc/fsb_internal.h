@@ -105,6 +105,7 @@ struct fsb_ctx_s {
 	std::vector<fsb::pending> queue;
 	bool fusion = true;
 	bool trace = false;
+	bool reproducible = true; // SpMV row blocks statically assigned to CTAs (set from nranks at creation)
 	int spmv_rows_per_cta = 0; // 0 = auto
 	int spmv_threads = 0;
 

@@ -6,6 +6,7 @@
 // launches e.g. {x += a p; r -= a w; |r|^2} as ONE kernel when the norm is read.
 // Statements are evaluated in program order per element, so fusing never changes a
 // value; only reductions see a different (fixed, reproducible) summation order.
+#include <chrono>
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -303,6 +304,14 @@ static void publish_multi_rank(fsb_ctx_s * c, const pending * q, int len) {
 void flush(fsb_ctx_s * c) {
 	if (c->queue.empty())
 		return;
+	struct stopwatch {
+		fsb_ctx_s * c;
+		std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+		~stopwatch() {
+			c->stats[FSB_STAT_FLUSH_NS] +=
+				std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+		}
+	} watch{c};
 	std::vector<pending> q;
 	q.swap(c->queue); // launches below must not re-enter the queue
 	const int total = static_cast<int>(q.size());

@@ -58,6 +58,7 @@ struct spmv_args {
 	int cap; // nnz capacity of one stage (multiple of 4, includes alignment slack)
 	int rcap; // row-offset capacity of one stage
 	int chunk; // row blocks claimed per atomic (1..4)
+	int static_sched; // 1: claims are handed out round-robin by CTA index (bitwise reproducible dot partials)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) {
@@ -137,7 +138,11 @@ __global__ void __launch_bounds__(GATHER > 8 ? 288 : SPMV_MAX_THREADS, 2) spmv_s
 		// latency of the descriptors sits between a freed stage and the next bulk copy.
 		const int CHUNK = a.chunk; // 1..4, chosen on the host so that every CTA sees several claims
 		const int lane = tid;
+		int round = 0;
 		auto claim = [&]() {
+			if (a.static_sched) // fixed row blocks per CTA: the per-CTA dot partials do not depend on timing
+				return static_cast<int>(min(static_cast<long long>(a.n_blk),
+				                            (static_cast<long long>(round++) * gridDim.x + blockIdx.x) * CHUNK));
 			int base = 0;
 			if (lane == 0)
 				base = static_cast<int>(atomicAdd(&a.sched[0], static_cast<unsigned>(CHUNK)));
@@ -506,6 +511,7 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y
 		a.xr = c->d_xrank;
 	}
 	a.n_blk = B.n_blk;
+	a.static_sched = c->reproducible ? 1 : 0;
 	a.cap = k.cap;
 	a.rcap = k.rcap;
 	const bool rowlist = B.row_ids != nullptr;

@@ -23,7 +23,7 @@ class Info(C.Structure):
     _fields_ = [("status", C.c_int), ("iters", C.c_int), ("restarts", C.c_int),
                 ("res_norm_initial", C.c_float), ("res_norm_final", C.c_float),
                 ("sol_norm_initial", C.c_float), ("sol_norm_final", C.c_float), ("rhs_norm", C.c_float),
-                ("callbacks", C.c_int), ("window_launches", C.c_int)]
+                ("callbacks", C.c_int), ("window_launches", C.c_int), ("solve_ms", C.c_double)]
 
     @property
     def reason(self) -> str:

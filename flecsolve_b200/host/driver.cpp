@@ -4,6 +4,9 @@
 // bind a solver, call it -- compiled once so tests and bench.py can drive it through ctypes.
 // All arithmetic happens behind include/fsb.h; nothing here touches vector data on the host
 // except the explicit host-buffer copies of fsbh_solve.
+#include <cstdio>
+#include <cstdlib>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -97,6 +100,7 @@ struct fsbh_info {
 	float res_norm_initial, res_norm_final, sol_norm_initial, sol_norm_final, rhs_norm;
 	int callbacks; // times the diagnostic ran
 	int window_launches; // kernels launched between the two event marks
+	double solve_ms; // wall clock around the solver call alone, device idle on both sides (multi-vector driver)
 };
 
 struct fsbh_options {
@@ -168,6 +172,7 @@ void fill(fsbh_info * out, const solve_info & i, int callbacks, std::int64_t win
 	out->sol_norm_final = i.sol_norm_final;
 	out->rhs_norm = i.rhs_norm;
 	out->callbacks = callbacks;
+	out->solve_ms = 0;
 }
 
 template<class S, class P>
@@ -286,6 +291,8 @@ int fsbh_solve_multi2(fsb_ctx_t ctx_h, fsb_parcsr_t A0h, fsb_parcsr_t A1h, const
 		device::check(fsb_vec_upload(x0.data.handle(), x_host, n0, 0));
 		device::check(fsb_vec_upload(x1.data.handle(), x_host + n0, n1, 0));
 		vec::multi b(b0, b1), x(x0, x1);
+		fsb_ctx_sync(ctx_h);
+		const auto t_begin = std::chrono::steady_clock::now();
 
 		auto blockdiag = op::make_shell(
 			[&](const auto & xin, auto & yout) {
@@ -311,9 +318,12 @@ int fsbh_solve_multi2(fsb_ctx_t ctx_h, fsb_parcsr_t A0h, fsb_parcsr_t A1h, const
 				std::ref(rec));
 			si = slv(b, x);
 		}
+		fsb_ctx_sync(ctx_h);
+		const double solve_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 		device::check(fsb_vec_download(x0.data.handle(), x_host, n0, 0));
 		device::check(fsb_vec_download(x1.data.handle(), x_host + n0, n1, 0));
 		fill(info, si, rec.count);
+		info->solve_ms = solve_ms;
 	});
 }
 

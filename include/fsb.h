@@ -52,7 +52,11 @@ enum fsb_option {
 	FSB_OPT_SPMV_ROWS_PER_CTA = 1, /* tuning knob for matrices created afterwards */
 	FSB_OPT_SPMV_THREADS = 2,
 	FSB_OPT_TRACE = 3, /* 1: print every launched group signature to stderr */
-	FSB_OPT_PROFILE = 4 /* 1: bracket every SpMV kernel with CUDA events (fsb_ctx_profile_read) */
+	FSB_OPT_PROFILE = 4, /* 1: bracket every SpMV kernel with CUDA events (fsb_ctx_profile_read) */
+	FSB_OPT_REPRODUCIBLE = 5 /* 1: SpMV row blocks are assigned to CTAs statically, so a fused dot is bitwise
+	                            reproducible run to run (default on one rank); 0: row blocks are claimed
+	                            dynamically, which tolerates SMs shared with communication kernels
+	                            (default on several ranks; results then vary in the last bits) */
 };
 
 enum fsb_stat {
@@ -61,7 +65,9 @@ enum fsb_stat {
 	FSB_STAT_HALO_EXCHANGES = 2,
 	FSB_STAT_ALLREDUCES = 3,
 	FSB_STAT_HOST_SYNCS = 4,
-	FSB_STAT_UNMATCHED_GROUPS = 5 /* groups launched through the generic program kernel (no compile-time instantiation) */
+	FSB_STAT_UNMATCHED_GROUPS = 5, /* groups launched through the generic program kernel (no compile-time instantiation) */
+	FSB_STAT_WAIT_NS = 6, /* host time spent waiting for reduction results (fsb_red_get / fsb_red_wait) */
+	FSB_STAT_FLUSH_NS = 7 /* host time spent turning queued statements into launches */
 };
 
 const char * fsb_last_error(void);

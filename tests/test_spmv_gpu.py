@@ -136,6 +136,29 @@ def test_fused_dot_reaches_across_a_burst(ctx):
     A.destroy()
 
 
+def test_fused_dot_is_bitwise_reproducible(ctx):
+    """One rank: row blocks are assigned to CTAs statically (FSB_OPT_REPRODUCIBLE), so the dot fused into the
+    SpMV gives the same bits on every run; the dynamic schedule is allowed to differ in the last bits only."""
+    A = F.ParCSR.stencil(ctx, 27, 96, 96, 96)
+    n = A.local_rows
+    rng = np.random.default_rng(5)
+    x, u, y = A.vector(rng.standard_normal(n)), A.vector(rng.standard_normal(n)), A.vector()
+    vals = []
+    for _ in range(6):
+        A.spmv(x, y)
+        vals.append(ctx.get(u.dot_token(y)))
+    assert len(set(vals)) == 1
+    ctx.set_option("reproducible", 0)
+    A.spmv(x, y)
+    dyn = ctx.get(u.dot_token(y))
+    ctx.set_option("reproducible", 1)
+    yy, uu = y.download(), u.download()
+    assert abs(dyn - vals[0]) <= 1e-13 * (np.abs(yy) @ np.abs(uu))
+    for v in (x, u, y):
+        v.destroy()
+    A.destroy()
+
+
 def test_spmv_rejects_aliasing_and_size_mismatch(ctx):
     rp, col, val = O.stencil_csr(5, 8, 8)
     A = F.ParCSR.from_csr(ctx, 64, [0, 64], rp, col, val)
