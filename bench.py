@@ -140,12 +140,16 @@ def run_ours(args):
     split = {}
 
     # ---- device-resident timing: iterations W+1 .. W+K of one solve, CUDA events on the library's stream
-    def timed_solve():
+    def timed_solve(solver=args.solver):
         S.x.zero()
         ctx.sync()
         ctx.profile_read()
         D.barrier(world)
-        _, info, _ = S.solve(solver="cg", precond=precond, maxiter=W + K, rtol=0.0, ev_start=W, ev_stop=W + K)
+        # cg_device looks at iteration j (and fires the event marks) after issuing iteration j + lag: issue
+        # lag more iterations so that the marks still bracket exactly K of them
+        lag = 2 if solver == "cg_device" else 0
+        _, info, _ = S.solve(solver=solver, precond=precond, maxiter=W + K + lag, rtol=0.0, ev_start=W, ev_stop=W + K,
+                             lag=lag)
         ctx.sync()
         D.barrier(world)
         ms = ctx.event_elapsed_ms(0, 1)
@@ -158,6 +162,13 @@ def run_ours(args):
     # the timed region is short (K x ~0.5 ms): run it `repeats` times and report the MEDIAN run
     runs = sorted((timed_solve() for _ in range(max(1, args.repeats))), key=lambda r: r[0])
     ms, info, spmv_ms, spmv_n = runs[len(runs) // 2]
+    # the other CG flavour beside it (cg: flecsolve's template, 3 host reads per iteration;
+    # cg_device: scalars on the device, residual norm inspected late -- SURVEY 8(f) N1)
+    other = "cg_device" if args.solver == "cg" else "cg"
+    timed_solve(other)
+    oruns = sorted((timed_solve(other) for _ in range(max(1, args.repeats))), key=lambda r: r[0])
+    oms, oinfo = oruns[len(oruns) // 2][:2]
+    oms = D.max_over_ranks(world, oms)
     clocks = sampler.stop() if sampler else {}
     ms = D.max_over_ranks(world, ms)
     ms_per_step = ms / K
@@ -235,6 +246,10 @@ def run_ours(args):
             "max_abs_error_vs_x_true": err,
         },
         "gpu_launches": int(info.window_launches),
+        "solver": args.solver,
+        "other_solver": {"solver": other, "value": 1000.0 * K / oms, "ms_per_step": oms / K,
+                         "gpu_launches": int(oinfo.window_launches),
+                         "iteration_frac_of_peak": iter_bytes / (oms / K) / 1e6 / peak},
         "clocks": clocks,
         "setup_seconds": setup_s,
     }
@@ -302,6 +317,8 @@ def main():
     ap.add_argument("--cpu-iters-cap", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--repeats", type=int, default=3, help="timed solves of W+K iterations; the median one is reported")
+    ap.add_argument("--solver", default="cg", choices=["cg", "cg_device"],
+                    help="cg: flecsolve's CG template unchanged (headline); cg_device: scalars kept on the device")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -66,6 +66,18 @@ _pi64 = C.POINTER(C.c_int64)
 _pi32 = C.POINTER(C.c_int32)
 
 
+class Coef(C.Structure):
+    """fsb_coef: scale * scalar[num] / scalar[den]; (v, 0, 0) is the plain number v."""
+    _fields_ = [("scale", C.c_double), ("num", C.c_int32), ("den", C.c_int32)]
+
+
+class RedOpts(C.Structure):
+    _fields_ = [("store", C.c_int32), ("halt_mode", C.c_int), ("halt_threshold", C.c_double)]
+
+
+HALT_NEVER, HALT_IF_SQRT_LT, HALT_IF_LT = 0, 1, 2
+
+
 def _declare(L: C.CDLL) -> None:
     def f(name, res, *args):
         fn = getattr(L, name)
@@ -119,6 +131,14 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_vec_global_size", C.c_int, _p, _pi64)
     f("fsb_red_get", C.c_int, _p, _i64, _pd)
     f("fsb_red_wait", C.c_int, _p, _i64)
+    f("fsb_scalar_create", C.c_int, _p, C.POINTER(C.c_int32))
+    f("fsb_scalar_destroy", C.c_int, _p, C.c_int32)
+    f("fsb_scalar_set", C.c_int, _p, C.c_int32, _dbl)
+    f("fsb_scalar_get", C.c_int, _p, C.c_int32, _pd)
+    f("fsb_vec_linear_sum_c", C.c_int, _p, Coef, _p, Coef, _p)
+    f("fsb_vec_dot_opts", C.c_int, _p, _p, C.POINTER(RedOpts), _pi64)
+    f("fsb_ctx_halt_arm", C.c_int, _p)
+    f("fsb_ctx_halt_disarm", C.c_int, _p, C.POINTER(C.c_int))
     f("fsb_parcsr_create", C.c_int, _p, _i64, _pi64, _pi64, _pi64, _pd, C.POINTER(_p))
     f("fsb_parcsr_create_stencil", C.c_int, _p, C.c_int, _i64, _i64, _i64, _dbl, _dbl, C.POINTER(_p))
     f("fsb_parcsr_destroy", C.c_int, _p)
@@ -226,6 +246,29 @@ class Context:
         check(lib().fsb_red_get(self.h, token, C.byref(out)))
         return out.value
 
+    # device scalars (fsb.h "device scalars")
+    def scalar(self, value: float | None = None) -> int:
+        s = C.c_int32()
+        check(lib().fsb_scalar_create(self.h, C.byref(s)))
+        if value is not None:
+            check(lib().fsb_scalar_set(self.h, s.value, value))
+        return s.value
+
+    def scalar_destroy(self, s: int): check(lib().fsb_scalar_destroy(self.h, s))
+    def scalar_set(self, s: int, value: float): check(lib().fsb_scalar_set(self.h, s, value))
+
+    def scalar_get(self, s: int) -> float:
+        out = _dbl()
+        check(lib().fsb_scalar_get(self.h, s, C.byref(out)))
+        return out.value
+
+    def halt_arm(self): check(lib().fsb_ctx_halt_arm(self.h))
+
+    def halt_disarm(self) -> bool:
+        v = C.c_int()
+        check(lib().fsb_ctx_halt_disarm(self.h, C.byref(v)))
+        return bool(v.value)
+
 
 class Vector:
     def __init__(self, ctx: Context, n_owned: int, n_ghost: int = 0, handle=None):
@@ -281,6 +324,18 @@ class Vector:
         return t.value
 
     def dot_token(self, x): return self._tok(lib().fsb_vec_dot, self.h, x.h)
+
+    def dot_opts_token(self, x, store=0, halt_mode=HALT_NEVER, halt_threshold=0.0):
+        o = RedOpts(store, halt_mode, halt_threshold)
+        t = _i64()
+        check(lib().fsb_vec_dot_opts(self.h, x.h, C.byref(o), C.byref(t)))
+        return t.value
+
+    def linear_sum_c(self, a, x, b, y):
+        """a, b: float or (scale, num, den) naming device scalars"""
+        ca = Coef(*a) if isinstance(a, tuple) else Coef(a, 0, 0)
+        cb = Coef(*b) if isinstance(b, tuple) else Coef(b, 0, 0)
+        check(lib().fsb_vec_linear_sum_c(self.h, ca, x.h, cb, y.h))
     def sumsq_token(self): return self._tok(lib().fsb_vec_sumsq, self.h)
     def dot(self, x): return self.ctx.get(self.dot_token(x))
     def l2norm(self): return float(np.sqrt(self.ctx.get(self.sumsq_token())))

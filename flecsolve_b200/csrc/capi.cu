@@ -166,6 +166,15 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 		FSB_CUDA(cudaMalloc(&c->d_sched, 2 * sizeof(unsigned)));
 		FSB_CUDA(cudaMemset(c->d_sched, 0, 2 * sizeof(unsigned)));
 		FSB_CUDA(cudaMalloc(&c->d_results, sizeof(double) * FSB_RED_RING));
+		FSB_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * fsb::MAX_SCALARS));
+		{
+			std::vector<double> init(fsb::MAX_SCALARS, 0.0);
+			init[0] = 1.0;
+			FSB_CUDA(cudaMemcpy(c->d_scalars, init.data(), sizeof(double) * fsb::MAX_SCALARS, cudaMemcpyHostToDevice));
+			c->scalar_used[0] = true;
+		}
+		FSB_CUDA(cudaMalloc(&c->d_halt, sizeof(int)));
+		FSB_CUDA(cudaMemset(c->d_halt, 0, sizeof(int)));
 		FSB_CUDA(cudaHostAlloc(&c->h_results, sizeof(double) * FSB_RED_RING, cudaHostAllocMapped));
 		FSB_CUDA(cudaHostAlloc(&c->h_flags, sizeof(int64_t) * FSB_RED_RING, cudaHostAllocMapped));
 		std::memset(c->h_results, 0, sizeof(double) * FSB_RED_RING);
@@ -222,6 +231,8 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 		cudaFree(c->d_counter);
 		cudaFree(c->d_sched);
 		cudaFree(c->d_results);
+		cudaFree(c->d_scalars);
+		cudaFree(c->d_halt);
 		cudaFree(c->d_flush);
 		cudaFreeHost(c->h_results);
 		cudaFreeHost(c->h_flags);
@@ -432,12 +443,20 @@ static void check_same(fsb_vec_t a, fsb_vec_t b) {
 	FSB_REQUIRE(a->n_owned == b->n_owned, "vector sizes differ");
 }
 
-static void push_ew(int op, fsb_vec_t z, fsb_vec_t x, fsb_vec_t y, double a, double b) {
+static void check_coef(fsb_ctx_s * c, const fsb_coef & k) {
+	FSB_REQUIRE(k.num >= 0 && k.num < fsb::MAX_SCALARS && k.den >= 0 && k.den < fsb::MAX_SCALARS &&
+	                c->scalar_used[k.num] && c->scalar_used[k.den],
+	            "coefficient names an unknown device scalar");
+}
+
+static void push_ew_c(int op, fsb_vec_t z, fsb_vec_t x, fsb_vec_t y, fsb_coef a, fsb_coef b) {
 	FSB_REQUIRE(z, "null vector");
 	if (x)
 		check_same(z, x);
 	if (y)
 		check_same(z, y);
+	check_coef(z->ctx, a);
+	check_coef(z->ctx, b);
 	// commutative statements: keep an aliased destination in the y operand
 	if ((op == OP_LIN2 || op == OP_MUL) && z == x && z != y) {
 		std::swap(x, y);
@@ -449,10 +468,22 @@ static void push_ew(int op, fsb_vec_t z, fsb_vec_t x, fsb_vec_t y, double a, dou
 	p.z = z;
 	p.x = x;
 	p.y = y;
-	p.a = a;
-	p.b = b;
+	p.a = a.scale;
+	p.b = b.scale;
+	if (a.num != 0 || a.den != 0) {
+		p.a_num = a.num;
+		p.a_den = a.den;
+	}
+	if (b.num != 0 || b.den != 0) {
+		p.b_num = b.num;
+		p.b_den = b.den;
+	}
 	z->halo_valid = false;
 	enqueue(z->ctx, p);
+}
+
+static void push_ew(int op, fsb_vec_t z, fsb_vec_t x, fsb_vec_t y, double a, double b) {
+	push_ew_c(op, z, x, y, fsb_coef{a, 0, 0}, fsb_coef{b, 0, 0});
 }
 
 int fsb_vec_copy(fsb_vec_t z, fsb_vec_t x) {
@@ -485,6 +516,9 @@ int fsb_vec_recip(fsb_vec_t z, fsb_vec_t x) {
 }
 int fsb_vec_linear_sum(fsb_vec_t z, double a, fsb_vec_t x, double b, fsb_vec_t y) {
 	return guarded([&] { push_ew(OP_LIN2, z, x, y, a, b); });
+}
+int fsb_vec_linear_sum_c(fsb_vec_t z, fsb_coef a, fsb_vec_t x, fsb_coef b, fsb_vec_t y) {
+	return guarded([&] { push_ew_c(OP_LIN2, z, x, y, a, b); });
 }
 int fsb_vec_axpy(fsb_vec_t z, double a, fsb_vec_t x, fsb_vec_t y) {
 	return guarded([&] { push_ew(OP_LIN2, z, x, y, a, 1.0); });
@@ -531,7 +565,7 @@ int fsb_vec_dump(fsb_vec_t x, const char * prefix) {
 
 // ------------------------------------------------------------------ reductions
 
-static void push_red(int op, fsb_vec_t x, fsb_vec_t y, double a, fsb_token_t * tok) {
+static void push_red(int op, fsb_vec_t x, fsb_vec_t y, double a, fsb_token_t * tok, const fsb_red_opts * o = nullptr) {
 	FSB_REQUIRE(x && tok, "bad arguments");
 	if (y)
 		check_same(x, y);
@@ -542,6 +576,15 @@ static void push_red(int op, fsb_vec_t x, fsb_vec_t y, double a, fsb_token_t * t
 	p.x = x;
 	p.y = y;
 	p.a = a;
+	if (o) {
+		FSB_REQUIRE(o->store >= 0 && o->store < fsb::MAX_SCALARS && c->scalar_used[o->store], "unknown device scalar");
+		FSB_REQUIRE(o->halt_mode >= FSB_HALT_NEVER && o->halt_mode <= FSB_HALT_IF_LT, "bad halt mode");
+		FSB_REQUIRE(o->halt_mode == FSB_HALT_NEVER || c->halt_armed, "halt test outside fsb_ctx_halt_arm/disarm");
+		if (o->store > 0)
+			p.store = o->store;
+		p.halt_mode = o->halt_mode;
+		p.halt_thr = o->halt_threshold;
+	}
 	p.token = new_token(c, fold_of(op));
 	*tok = p.token;
 	enqueue(c, p);
@@ -552,6 +595,68 @@ int fsb_vec_dot(fsb_vec_t x, fsb_vec_t y, fsb_token_t * tok) {
 }
 int fsb_vec_sumsq(fsb_vec_t x, fsb_token_t * tok) {
 	return guarded([&] { push_red(RD_DOT, x, x, 0, tok); });
+}
+int fsb_vec_dot_opts(fsb_vec_t x, fsb_vec_t y, const fsb_red_opts * o, fsb_token_t * tok) {
+	return guarded([&] { push_red(RD_DOT, x, y, 0, tok, o); });
+}
+
+// ------------------------------------------------------------------ device scalars
+
+int fsb_scalar_create(fsb_ctx_t c, fsb_scalar_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(c && out, "bad arguments");
+		for (int k = 1; k < fsb::MAX_SCALARS; ++k)
+			if (!c->scalar_used[k]) {
+				c->scalar_used[k] = true;
+				*out = k;
+				return;
+			}
+		throw fsb::error(FSB_ERR_STATE, "out of device scalars");
+	});
+}
+int fsb_scalar_destroy(fsb_ctx_t c, fsb_scalar_t s) {
+	return guarded([&] {
+		FSB_REQUIRE(c && s > 0 && s < fsb::MAX_SCALARS && c->scalar_used[s], "unknown device scalar");
+		flush(c); // queued statements may still name it
+		c->scalar_used[s] = false;
+	});
+}
+int fsb_scalar_set(fsb_ctx_t c, fsb_scalar_t s, double v) {
+	return guarded([&] {
+		FSB_REQUIRE(c && s > 0 && s < fsb::MAX_SCALARS && c->scalar_used[s], "unknown device scalar");
+		flush(c);
+		FSB_CUDA(cudaMemcpyAsync(c->d_scalars + s, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		FSB_CUDA(cudaStreamSynchronize(c->stream)); // v is a stack temporary
+	});
+}
+int fsb_scalar_get(fsb_ctx_t c, fsb_scalar_t s, double * out) {
+	return guarded([&] {
+		FSB_REQUIRE(c && out && s >= 0 && s < fsb::MAX_SCALARS && c->scalar_used[s], "unknown device scalar");
+		flush(c);
+		FSB_CUDA(cudaMemcpyAsync(out, c->d_scalars + s, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		FSB_CUDA(cudaStreamSynchronize(c->stream));
+		c->stats[FSB_STAT_HOST_SYNCS]++;
+	});
+}
+int fsb_ctx_halt_arm(fsb_ctx_t c) {
+	return guarded([&] {
+		FSB_REQUIRE(c, "null context");
+		flush(c);
+		FSB_CUDA(cudaMemsetAsync(c->d_halt, 0, sizeof(int), c->stream));
+		c->halt_armed = true;
+	});
+}
+int fsb_ctx_halt_disarm(fsb_ctx_t c, int * was_halted) {
+	return guarded([&] {
+		FSB_REQUIRE(c, "null context");
+		flush(c);
+		if (was_halted) {
+			FSB_CUDA(cudaMemcpyAsync(was_halted, c->d_halt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+			FSB_CUDA(cudaStreamSynchronize(c->stream));
+		}
+		FSB_CUDA(cudaMemsetAsync(c->d_halt, 0, sizeof(int), c->stream));
+		c->halt_armed = false;
+	});
 }
 int fsb_vec_asum(fsb_vec_t x, fsb_token_t * tok) {
 	return guarded([&] { push_red(RD_ASUM, x, nullptr, 0, tok); });

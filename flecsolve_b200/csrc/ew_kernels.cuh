@@ -20,6 +20,12 @@ struct red_out {
 	double * h_value; // mapped host slot or nullptr (multi-rank: NCCL finishes the job)
 	long long * h_flag;
 	long long token;
+	// device-scalar solvers (fsb.h, "device scalars"): keep the value on the device for later
+	// coefficients, and raise the context's halt flag when the convergence test passes
+	double * d_extra; // scalar slot or nullptr
+	int * halt; // flag to raise, used when halt_mode != 0
+	double halt_thr;
+	int halt_mode; // 0 none, 1: sqrt(value) < thr, 2: value < thr
 };
 
 // Cross-rank all-reduce of one scalar over NVLink peer memory, executed by the CTA that finishes
@@ -37,6 +43,10 @@ struct xrank_info {
 struct ew_args {
 	double * v[MAXV];
 	double s[MAXSC];
+	// coefficient k is s[k] when snum[k] < 0, else s[k] * sdev[snum[k]] / sdev[sden[k]] read at kernel start
+	const double * sdev;
+	signed char snum[MAXSC], sden[MAXSC];
+	const int * halt; // non-null while a device-scalar solver is running: skip all element work once set
 	long long n;
 	double * partials; // [MAXR][MAX_RED_BLOCKS]
 	unsigned * counter;
@@ -132,6 +142,10 @@ __device__ __forceinline__ double xrank_allreduce(const xrank_info * xr, double 
 // publish a finished reduction: device slot, then mapped host value + token (thread 0 only)
 __device__ __forceinline__ void publish(const red_out & r, double t) {
 	*r.d_value = t;
+	if (r.d_extra)
+		*r.d_extra = t;
+	if (r.halt_mode != 0 && (r.halt_mode == 1 ? sqrt(t) : t) < r.halt_thr)
+		*reinterpret_cast<volatile int *>(r.halt) = 1;
 	if (r.h_value) {
 		*reinterpret_cast<volatile double *>(r.h_value) = t;
 		__threadfence_system();
@@ -139,17 +153,17 @@ __device__ __forceinline__ void publish(const red_out & r, double t) {
 	}
 }
 
-template<class PT, int I>
-__device__ __forceinline__ void exec_stmt(double (&v)[MAXV], double (&acc)[MAXR], const ew_args & a) {
+template<class PT, int I, class SC>
+__device__ __forceinline__ void exec_stmt(double (&v)[MAXV], double (&acc)[MAXR], const SC & sc) {
 	constexpr stmt S = PT::value.st[I];
 	// products and sums are rounded separately on purpose (see fsb.h): the reference's
 	// task bodies (vectors/operations/topo_tasks.hh) compiled for baseline x86-64 do the same.
 	if constexpr (S.op == OP_SET)
-		v[S.z] = a.s[S.a];
+		v[S.z] = sc[S.a];
 	else if constexpr (S.op == OP_SCALE)
-		v[S.z] = __dmul_rn(v[S.x], a.s[S.a]);
+		v[S.z] = __dmul_rn(v[S.x], sc[S.a]);
 	else if constexpr (S.op == OP_LIN2)
-		v[S.z] = __dadd_rn(__dmul_rn(a.s[S.a], v[S.x]), __dmul_rn(a.s[S.b], v[S.y]));
+		v[S.z] = __dadd_rn(__dmul_rn(sc[S.a], v[S.x]), __dmul_rn(sc[S.b], v[S.y]));
 	else if constexpr (S.op == OP_MUL)
 		v[S.z] = __dmul_rn(v[S.x], v[S.y]);
 	else if constexpr (S.op == OP_DIV)
@@ -159,7 +173,7 @@ __device__ __forceinline__ void exec_stmt(double (&v)[MAXV], double (&acc)[MAXR]
 	else if constexpr (S.op == OP_ABS)
 		v[S.z] = fabs(v[S.x]);
 	else if constexpr (S.op == OP_ADDS)
-		v[S.z] = __dadd_rn(v[S.x], a.s[S.a]);
+		v[S.z] = __dadd_rn(v[S.x], sc[S.a]);
 	else if constexpr (S.op == RD_DOT)
 		acc[S.z] = fma(v[S.x], v[S.y], acc[S.z]);
 	else if constexpr (S.op == RD_ASUM)
@@ -171,33 +185,21 @@ __device__ __forceinline__ void exec_stmt(double (&v)[MAXV], double (&acc)[MAXR]
 	else if constexpr (S.op == RD_MAX)
 		acc[S.z] = fmax(acc[S.z], v[S.x]);
 	else if constexpr (S.op == RD_POWSUM)
-		acc[S.z] += pow(v[S.x], a.s[S.a]);
+		acc[S.z] += pow(v[S.x], sc[S.a]);
 }
 
-template<class PT>
-__device__ __forceinline__ void exec_all(double (&v)[MAXV], double (&acc)[MAXR], const ew_args & a) {
+template<class PT, class SC>
+__device__ __forceinline__ void exec_all(double (&v)[MAXV], double (&acc)[MAXR], const SC & sc) {
 	[&]<size_t... I>(std::index_sequence<I...>) {
-		(exec_stmt<PT, static_cast<int>(I)>(v, acc, a), ...);
+		(exec_stmt<PT, static_cast<int>(I)>(v, acc, sc), ...);
 	}(std::make_index_sequence<PT::value.n>{});
 }
 
-// fold kind of reduction output R of program P
-template<class PT, int R>
-constexpr int red_fold() {
-	for (int i = 0; i < PT::value.n; ++i)
-		if (is_reduction(PT::value.st[i].op) && PT::value.st[i].z == R)
-			return fold_of(PT::value.st[i].op);
-	return 0;
-}
-
-template<class PT>
-__global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_constant__ ew_args a) {
+// the element loops of a program; SC is either the kernel-parameter array (immediate coefficients,
+// served by the constant bank) or a register copy with the device-resident coefficients resolved
+template<class PT, class SC>
+__device__ __forceinline__ void run_elements(const ew_args & a, const SC & sc, double (&acc)[MAXR]) {
 	constexpr program P = PT::value;
-	double acc[MAXR];
-	[&]<size_t... R>(std::index_sequence<R...>) {
-		((acc[R] = fold_identity<red_fold<PT, static_cast<int>(R)>()>()), ...);
-	}(std::make_index_sequence<(P.nr > 0 ? P.nr : 0)>{});
-
 	const long long n2 = a.n >> 1; // number of double2 packets
 	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
 	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2; i += stride) {
@@ -210,8 +212,8 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_const
 				hi[k] = t.y;
 			}
 		}
-		exec_all<PT>(lo, acc, a);
-		exec_all<PT>(hi, acc, a);
+		exec_all<PT>(lo, acc, sc);
+		exec_all<PT>(hi, acc, sc);
 #pragma unroll
 		for (int k = 0; k < P.nv; ++k) {
 			if (P.store_mask & (1u << k))
@@ -225,12 +227,43 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_const
 		for (int k = 0; k < P.nv; ++k)
 			if (P.load_mask & (1u << k))
 				t[k] = a.v[k][i];
-		exec_all<PT>(t, acc, a);
+		exec_all<PT>(t, acc, sc);
 #pragma unroll
 		for (int k = 0; k < P.nv; ++k)
 			if (P.store_mask & (1u << k))
 				a.v[k][i] = t[k];
 	}
+}
+
+// fold kind of reduction output R of program P
+template<class PT, int R>
+constexpr int red_fold() {
+	for (int i = 0; i < PT::value.n; ++i)
+		if (is_reduction(PT::value.st[i].op) && PT::value.st[i].z == R)
+			return fold_of(PT::value.st[i].op);
+	return 0;
+}
+
+// DEV: some coefficients live in device memory (and the halt flag is honoured)
+template<class PT, bool DEV = false>
+__global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_constant__ ew_args a) {
+	constexpr program P = PT::value;
+	double acc[MAXR];
+	[&]<size_t... R>(std::index_sequence<R...>) {
+		((acc[R] = fold_identity<red_fold<PT, static_cast<int>(R)>()>()), ...);
+	}(std::make_index_sequence<(P.nr > 0 ? P.nr : 0)>{});
+
+	if constexpr (DEV) {
+		if (!(a.halt && *a.halt)) { // once halted, vectors stay as they are; reductions publish identities
+			double sc[MAXSC];
+#pragma unroll
+			for (int k = 0; k < P.ns; ++k)
+				sc[k] = a.snum[k] < 0 ? a.s[k] : __dmul_rn(a.s[k], __ddiv_rn(a.sdev[a.snum[k]], a.sdev[a.sden[k]]));
+			run_elements<PT>(a, sc, acc);
+		}
+	}
+	else
+		run_elements<PT>(a, a.s, acc);
 
 	if constexpr (P.nr > 0) {
 		__shared__ double scratch[32];
@@ -280,24 +313,24 @@ struct interp_args {
 	program p;
 };
 
-__device__ __forceinline__ void interp_exec(const program & P, const ew_args & a, double * v, double * acc) {
+__device__ __forceinline__ void interp_exec(const program & P, const double * sc, double * v, double * acc) {
 	for (int i = 0; i < P.n; ++i) {
 		const stmt S = P.st[i];
 		switch (S.op) {
-		case OP_SET: v[S.z] = a.s[S.a]; break;
-		case OP_SCALE: v[S.z] = __dmul_rn(v[S.x], a.s[S.a]); break;
-		case OP_LIN2: v[S.z] = __dadd_rn(__dmul_rn(a.s[S.a], v[S.x]), __dmul_rn(a.s[S.b], v[S.y])); break;
+		case OP_SET: v[S.z] = sc[S.a]; break;
+		case OP_SCALE: v[S.z] = __dmul_rn(v[S.x], sc[S.a]); break;
+		case OP_LIN2: v[S.z] = __dadd_rn(__dmul_rn(sc[S.a], v[S.x]), __dmul_rn(sc[S.b], v[S.y])); break;
 		case OP_MUL: v[S.z] = __dmul_rn(v[S.x], v[S.y]); break;
 		case OP_DIV: v[S.z] = __ddiv_rn(v[S.x], v[S.y]); break;
 		case OP_RECIP: v[S.z] = __ddiv_rn(1.0, v[S.x]); break;
 		case OP_ABS: v[S.z] = fabs(v[S.x]); break;
-		case OP_ADDS: v[S.z] = __dadd_rn(v[S.x], a.s[S.a]); break;
+		case OP_ADDS: v[S.z] = __dadd_rn(v[S.x], sc[S.a]); break;
 		case RD_DOT: acc[S.z] = fma(v[S.x], v[S.y], acc[S.z]); break;
 		case RD_ASUM: acc[S.z] += fabs(v[S.x]); break;
 		case RD_AMAX: acc[S.z] = fmax(acc[S.z], fabs(v[S.x])); break;
 		case RD_MIN: acc[S.z] = fmin(acc[S.z], v[S.x]); break;
 		case RD_MAX: acc[S.z] = fmax(acc[S.z], v[S.x]); break;
-		case RD_POWSUM: acc[S.z] += pow(v[S.x], a.s[S.a]); break;
+		case RD_POWSUM: acc[S.z] += pow(v[S.x], sc[S.a]); break;
 		}
 	}
 }
@@ -320,8 +353,12 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_interp_kernel(const __grid_consta
 	double acc[MAXR];
 	for (int r = 0; r < P.nr; ++r)
 		acc[r] = ident_rt(rfold[r]);
+	double sc[MAXSC];
+	for (int k = 0; k < P.ns; ++k)
+		sc[k] = a.snum[k] < 0 ? a.s[k] : __dmul_rn(a.s[k], __ddiv_rn(a.sdev[a.snum[k]], a.sdev[a.sden[k]]));
+	const bool halted = a.halt && *a.halt;
 
-	const long long n2 = a.n >> 1;
+	const long long n2 = halted ? 0 : a.n >> 1;
 	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
 	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2; i += stride) {
 		double lo[MAXV], hi[MAXV];
@@ -331,19 +368,19 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_interp_kernel(const __grid_consta
 				lo[k] = t.x;
 				hi[k] = t.y;
 			}
-		interp_exec(P, a, lo, acc);
-		interp_exec(P, a, hi, acc);
+		interp_exec(P, sc, lo, acc);
+		interp_exec(P, sc, hi, acc);
 		for (int k = 0; k < P.nv; ++k)
 			if (P.store_mask & (1u << k))
 				reinterpret_cast<double2 *>(a.v[k])[i] = make_double2(lo[k], hi[k]);
 	}
-	if ((a.n & 1) && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+	if (!halted && (a.n & 1) && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
 		const long long i = a.n - 1;
 		double t[MAXV];
 		for (int k = 0; k < P.nv; ++k)
 			if (P.load_mask & (1u << k))
 				t[k] = a.v[k][i];
-		interp_exec(P, a, t, acc);
+		interp_exec(P, sc, t, acc);
 		for (int k = 0; k < P.nv; ++k)
 			if (P.store_mask & (1u << k))
 				a.v[k][i] = t[k];

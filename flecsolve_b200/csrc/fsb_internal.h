@@ -15,6 +15,8 @@
 
 namespace fsb {
 struct xrank_info;
+struct red_out;
+constexpr int MAX_SCALARS = 64; // device scalars per context; slot 0 is the constant 1.0
 }
 
 namespace fsb {
@@ -63,6 +65,12 @@ struct pending {
 	double a = 0, b = 0;
 	int64_t token = -1; // RED
 	fsb_parcsr_s * A = nullptr; // SPMV
+	// device-resident coefficients: a (b) is multiplied by scalars[a_num] / scalars[a_den] when a_num >= 0
+	int a_num = -1, a_den = -1, b_num = -1, b_den = -1;
+	// RED: also store the all-rank value into this scalar slot; raise the halt flag when the test passes
+	int store = -1;
+	int halt_mode = 0; // 0 none, 1 sqrt(value) < halt_thr, 2 value < halt_thr
+	double halt_thr = 0;
 };
 
 struct red_slot {
@@ -98,6 +106,11 @@ struct fsb_ctx_s {
 	void * peer_mailbox[8] = {};
 	fsb::xrank_info * d_xrank = nullptr; // device copy handed to kernels; nullptr => NCCL path
 	int * h_xrank_error = nullptr; // mapped host flag
+	// device scalars + halt flag (device-scalar solver variants)
+	double * d_scalars = nullptr; // [MAX_SCALARS], [0] == 1.0
+	bool scalar_used[64] = {};
+	int * d_halt = nullptr;
+	bool halt_armed = false;
 	std::vector<int> token_op; // per ring slot: nccl op kind of the reduction
 	std::vector<cudaEvent_t> token_event; // multi-rank path
 
@@ -192,9 +205,13 @@ void flush(fsb_ctx_s * c);
 int64_t new_token(fsb_ctx_s * c, int nccl_op);
 
 // kernels (declared here, defined in their .cu)
+// `fold`: the queued dot whose partials the last CTA of this launch folds and publishes (or nullptr)
 int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
-                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s, int64_t fold_token = 0);
-void finalize_reduction(fsb_ctx_s * c, int n_partials, int64_t token, int op_kind);
+                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s,
+                const pending * fold = nullptr);
+void fill_red_out(fsb_ctx_s * c, const pending & red, red_out & r);
+void finish_reduction_nccl(fsb_ctx_s * c, const pending & red);
+void finalize_reduction(fsb_ctx_s * c, int n_partials, const pending & red);
 void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x);
 
 void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * host_rowptr);

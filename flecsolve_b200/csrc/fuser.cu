@@ -35,6 +35,19 @@ static void launch_program(const ew_args & a, int want, cudaStream_t s) {
 	ew_program_kernel<PT><<<grid, EW_BLOCK, 0, s>>>(a);
 }
 
+template<class PT>
+static void launch_program_dev(const ew_args & a, int want, cudaStream_t s) {
+	static int resident = 0;
+	if (resident == 0) {
+		int nb = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ew_program_kernel<PT, true>, EW_BLOCK, 0) != cudaSuccess || nb < 1)
+			nb = 4;
+		resident = nb * SM_COUNT;
+	}
+	const int grid = want < resident ? want : resident;
+	ew_program_kernel<PT, true><<<grid, EW_BLOCK, 0, s>>>(a);
+}
+
 static std::string key_of(const program & p) {
 	std::string k(reinterpret_cast<const char *>(&p.n), sizeof(int));
 	k.append(reinterpret_cast<const char *>(p.st), sizeof(stmt) * p.n);
@@ -43,10 +56,16 @@ static std::string key_of(const program & p) {
 
 struct registry_t {
 	std::unordered_map<std::string, launcher_t> map;
+	std::unordered_map<std::string, launcher_t> dev_map; // instantiations that read device-resident coefficients
 	template<class PT>
 	void add() {
 		static_assert(PT::ok, "program exceeds slot limits");
 		map.emplace(key_of(PT::value), &launch_program<PT>);
+	}
+	template<class PT>
+	void add_dev() {
+		static_assert(PT::ok, "program exceeds slot limits");
+		dev_map.emplace(key_of(PT::value), &launch_program_dev<PT>);
 	}
 };
 
@@ -153,6 +172,20 @@ FSB_PROGRAM(p_dot_dot, R_DOT(0, 1), R_DOT(2, 3))
 FSB_PROGRAM(p_lin2_lin2, S_LIN2(2, 0, 1), S_LIN2(5, 3, 4))
 FSB_PROGRAM(p_scale2, S_SCALE(1, 0), S_SCALE(3, 2))
 FSB_PROGRAM(p_set2, S_SET(0), S_SET(1))
+// BiCGStab on a two-component vec::multi (vectors/operations/multi.hh applies every call per component):
+// bicgstab.hh:132-134  s = -a v + res per component ; |s|^2 per component
+FSB_PROGRAM(p_bicg2_s, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), R_DOT(3, 3), R_DOT(1, 1))
+// bicgstab.hh:153-158  x += a p_hat ; x += w s_hat ; res = -w t + s ; |res|^2, both components
+FSB_PROGRAM(p_bicg2_update, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), S_LIN2(1, 4, 1), S_LIN2(3, 5, 3), S_LIN2(8, 6, 7),
+            S_LIN2(11, 9, 10), R_DOT(11, 11), R_DOT(8, 8))
+// bicgstab.hh:120-124  p = -w v + p ; p = b p + res ; p_hat = p (identity), both components
+FSB_PROGRAM(p_bicg2_dir_copy, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), S_LIN2(1, 4, 1), S_LIN2(3, 5, 3), S_SCALE(6, 1),
+            S_SCALE(7, 3))
+
+// Device-scalar CG (solvers/cg_device.hh): no host read separates the update from the preconditioner, so
+//   x = a p + x ; r = -a w + r ; |r|^2 ; z = dinv * r ; r.z     is ONE pass (64 B/row)
+FSB_PROGRAM(p_cgdev_update_jacobi, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), R_DOT(3, 3), S_MUL(5, 4, 3), R_DOT(3, 5))
+FSB_PROGRAM(p_cgdev_update_copy, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), R_DOT(3, 3), S_SCALE(4, 3), R_DOT(3, 4))
 
 static registry_t & registry() {
 	static registry_t r = [] {
@@ -174,6 +207,9 @@ static registry_t & registry() {
 		g.add<p_bicg_dir_jacobi>(); g.add<p_bicg_dir_copy>(); g.add<p_bicg_dir>(); g.add<p_bicg_update>();
 		g.add<p_dot2>(); g.add<p_mul_sumsq>(); g.add<p_sumsq2>(); g.add<p_dot_dot>();
 		g.add<p_lin2_lin2>(); g.add<p_scale2>(); g.add<p_set2>();
+		g.add<p_bicg2_s>(); g.add<p_bicg2_update>(); g.add<p_bicg2_dir_copy>();
+		g.add_dev<p_cgdev_update_jacobi>(); g.add_dev<p_cgdev_update_copy>(); g.add_dev<p_lin2_zy>();
+		g.add_dev<p_cg_update>(); g.add_dev<p_axpy2>();
 		return g;
 	}();
 	return r;
@@ -245,10 +281,14 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 	const canon_result cr = canonicalize(rs, len);
 	if (!cr.ok)
 		return false;
-	auto it = registry().map.find(key_of(cr.p));
-	if (it == registry().map.end() && !allow_generic)
+	bool dev = c->halt_armed;
+	for (int i = 0; i < len; ++i)
+		dev = dev || q[i].a_num >= 0 || q[i].b_num >= 0;
+	const auto & table = dev ? registry().dev_map : registry().map;
+	auto it = table.find(key_of(cr.p));
+	if (it == table.end() && !allow_generic)
 		return false;
-	g.launch = it == registry().map.end() ? nullptr : it->second;
+	g.launch = it == table.end() ? nullptr : it->second;
 	g.prog = cr.p;
 	g.nr = cr.p.nr;
 	ew_args & a = g.args;
@@ -259,46 +299,77 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 	a.counter = c->d_counter;
 	a.partial_stride = MAX_RED_BLOCKS;
 	a.xr = c->d_xrank;
+	a.sdev = c->d_scalars;
+	a.halt = c->halt_armed ? c->d_halt : nullptr;
+	for (int k = 0; k < MAXSC; ++k)
+		a.snum[k] = a.sden[k] = -1;
 	for (int i = 0; i < len; ++i) {
 		const stmt & s = cr.p.st[i];
-		if (s.a >= 0)
+		if (s.a >= 0) {
 			a.s[s.a] = q[i].a;
-		if (s.b >= 0)
-			a.s[s.b] = q[i].b;
-		if (is_reduction(s.op)) {
-			const int slot = static_cast<int>(q[i].token % FSB_RED_RING);
-			red_out & r = a.r[s.z];
-			r.d_value = c->d_results + slot;
-			r.token = q[i].token;
-			if (c->nranks == 1 || c->d_xrank) {
-				r.h_value = c->h_results_dev + slot;
-				r.h_flag = reinterpret_cast<long long *>(c->h_flags_dev + slot);
-			}
-			else {
-				r.h_value = nullptr;
-				r.h_flag = nullptr;
-			}
+			a.snum[s.a] = static_cast<signed char>(q[i].a_num);
+			a.sden[s.a] = static_cast<signed char>(q[i].a_den);
 		}
+		if (s.b >= 0) {
+			a.s[s.b] = q[i].b;
+			a.snum[s.b] = static_cast<signed char>(q[i].b_num);
+			a.sden[s.b] = static_cast<signed char>(q[i].b_den);
+		}
+		if (is_reduction(s.op))
+			fill_red_out(c, q[i], a.r[s.z]);
 	}
 	return true;
+}
+
+// where a finished reduction goes.  One rank / peer-memory all-reduce: the producing kernel has the
+// all-rank value, so it also serves the scalar slot and the convergence test; NCCL transport: the
+// kernel only leaves the rank-local value in d_results and finish_reduction_nccl() does the rest.
+void fill_red_out(fsb_ctx_s * c, const pending & red, red_out & r) {
+	const int slot = static_cast<int>(red.token % FSB_RED_RING);
+	r = red_out{};
+	r.d_value = c->d_results + slot;
+	r.token = red.token;
+	if (c->nranks == 1 || c->d_xrank) {
+		r.h_value = c->h_results_dev + slot;
+		r.h_flag = reinterpret_cast<long long *>(c->h_flags_dev + slot);
+		r.d_extra = red.store >= 0 ? c->d_scalars + red.store : nullptr;
+		r.halt = c->d_halt;
+		r.halt_thr = red.halt_thr;
+		r.halt_mode = red.halt_mode;
+	}
+}
+
+__global__ void after_allreduce_kernel(const double * value, double * extra, int * halt, int mode, double thr) {
+	const double t = *value;
+	if (extra)
+		*extra = t;
+	if (mode != 0 && (mode == 1 ? sqrt(t) : t) < thr)
+		*halt = 1;
+}
+
+void finish_reduction_nccl(fsb_ctx_s * c, const pending & red) {
+	const int slot = static_cast<int>(red.token % FSB_RED_RING);
+	const int f = fold_of(red.op);
+	const ncclRedOp_t op = f == 0 ? ncclSum : (f == 1 ? ncclMax : ncclMin);
+	FSB_NCCL(ncclAllReduce(c->d_results + slot, c->d_results + slot, 1, ncclDouble, op, c->nccl, c->stream));
+	c->stats[FSB_STAT_ALLREDUCES]++;
+	if (red.store >= 0 || red.halt_mode != 0) {
+		after_allreduce_kernel<<<1, 1, 0, c->stream>>>(c->d_results + slot, red.store >= 0 ? c->d_scalars + red.store : nullptr,
+		                                               c->d_halt, red.halt_mode, red.halt_thr);
+		FSB_CUDA(cudaGetLastError());
+		c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+	}
+	FSB_CUDA(cudaMemcpyAsync(c->h_results + slot, c->d_results + slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaEventRecord(c->token_event[slot], c->stream));
 }
 
 // After a kernel that produced intra-rank reduction values: finish across ranks.
 static void publish_multi_rank(fsb_ctx_s * c, const pending * q, int len) {
 	if (c->nranks == 1 || c->d_xrank) // the producing kernel already reduced across ranks
 		return;
-	for (int i = 0; i < len; ++i) {
-		if (q[i].kind != pending::RED)
-			continue;
-		const int slot = static_cast<int>(q[i].token % FSB_RED_RING);
-		const int f = fold_of(q[i].op);
-		const ncclRedOp_t op = f == 0 ? ncclSum : (f == 1 ? ncclMax : ncclMin);
-		FSB_NCCL(ncclAllReduce(c->d_results + slot, c->d_results + slot, 1, ncclDouble, op, c->nccl, c->stream));
-		c->stats[FSB_STAT_ALLREDUCES]++;
-		FSB_CUDA(cudaMemcpyAsync(c->h_results + slot, c->d_results + slot, sizeof(double), cudaMemcpyDeviceToHost,
-		                         c->stream));
-		FSB_CUDA(cudaEventRecord(c->token_event[slot], c->stream));
-	}
+	for (int i = 0; i < len; ++i)
+		if (q[i].kind == pending::RED)
+			finish_reduction_nccl(c, q[i]);
 }
 
 void flush(fsb_ctx_s * c) {
@@ -357,7 +428,16 @@ void flush(fsb_ctx_s * c) {
 		int j = i;
 		const int64_t n = length_of(q[i]);
 		const int cap = c->fusion ? MAXS : 1;
-		while (j < total && j - i < cap && q[j].kind != pending::SPMV && length_of(q[j]) == n)
+		// a statement whose coefficient is produced by a reduction of this very run needs the finished
+		// (grid-wide, all-rank) value: it starts the next launch
+		auto needs_result_of_run = [&](int k) {
+			for (int m = i; m < k; ++m)
+				if (q[m].kind == pending::RED && q[m].store >= 0 &&
+				    (q[m].store == q[k].a_num || q[m].store == q[k].a_den || q[m].store == q[k].b_num || q[m].store == q[k].b_den))
+					return true;
+			return false;
+		};
+		while (j < total && j - i < cap && q[j].kind != pending::SPMV && length_of(q[j]) == n && !needs_result_of_run(j))
 			++j;
 		// the whole run as one launch: a registered instantiation if there is one, else the generic
 		// program kernel; a run that exceeds the slot limits is cut at the longest prefix that fits

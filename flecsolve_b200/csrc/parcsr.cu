@@ -245,21 +245,20 @@ void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot) {
 		u = other->d; // other == y gives sum y^2
 	}
 	const bool has_offd = A->offd.n_blk > 0;
-	const int64_t token = dot ? dot->token : 0;
 	// the launch that runs last folds the dot partials (no separate fold kernel)
-	const int np_diag = launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream, has_offd ? 0 : token);
+	const int np_diag = launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream, has_offd ? nullptr : dot);
 	if (unpack)
 		halo_p2p_unpack(A, x);
 	if (has_offd) {
 		if (!waited)
 			FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
 		waited = true;
-		launch_spmv(c, A->offd, x->d, y->d, true, u, c->d_partials, np_diag, c->stream, token);
+		launch_spmv(c, A->offd, x->d, y->d, true, u, c->d_partials, np_diag, c->stream, dot);
 	}
 	if (!waited) // ghosts were requested but no row uses them: still order the streams
 		FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
 	if (dot && A->diag.n_blk == 0 && !has_offd)
-		finalize_reduction(c, 0, dot->token, 0); // empty local matrix: publish 0
+		finalize_reduction(c, 0, *dot); // empty local matrix: publish 0
 	y->halo_valid = false;
 }
 

@@ -483,7 +483,7 @@ static int launch_stages(const spmv_args & a, const spmv_config & k, bool acc, b
 // d_partials[partial_offset + b]; with fold_token > 0 the last CTA folds partials [0, partial_offset + grid)
 // into that reduction token.  Returns the number of CTAs launched (= partials written).
 int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
-                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s, int64_t fold_token) {
+                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s, const pending * fold) {
 	if (B.n_blk == 0)
 		return 0;
 	const spmv_config k = configure(c, B);
@@ -500,14 +500,8 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y
 	a.partials = d_partials;
 	a.fold_extra = partial_offset;
 	a.sched = c->d_sched;
-	if (dot_u && fold_token > 0) {
-		const int slot = static_cast<int>(fold_token % FSB_RED_RING);
-		a.result.d_value = c->d_results + slot;
-		a.result.token = fold_token;
-		if (c->nranks == 1 || c->d_xrank) {
-			a.result.h_value = c->h_results_dev + slot;
-			a.result.h_flag = reinterpret_cast<long long *>(c->h_flags_dev + slot);
-		}
+	if (dot_u && fold) {
+		fill_red_out(c, *fold, a.result);
 		a.xr = c->d_xrank;
 	}
 	a.n_blk = B.n_blk;
@@ -539,15 +533,9 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y
 }
 
 // fold the SpMV partials [0, n) into the reduction slot of `token`
-void finalize_reduction(fsb_ctx_s * c, int n_partials, int64_t token, int /*op_kind*/) {
-	const int slot = static_cast<int>(token % FSB_RED_RING);
+void finalize_reduction(fsb_ctx_s * c, int n_partials, const pending & red) {
 	red_out r{};
-	r.d_value = c->d_results + slot;
-	r.token = token;
-	if (c->nranks == 1 || c->d_xrank) {
-		r.h_value = c->h_results_dev + slot;
-		r.h_flag = reinterpret_cast<long long *>(c->h_flags_dev + slot);
-	}
+	fill_red_out(c, red, r);
 	fold_partials_kernel<<<1, 256, 0, c->stream>>>(c->d_partials, n_partials, r, c->d_xrank);
 	FSB_CUDA(cudaGetLastError());
 	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;

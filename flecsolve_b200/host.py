@@ -15,7 +15,7 @@ _lib = None
 
 STOP_REASONS = ["converged_atol", "converged_rtol", "converged_user", "diverged_dtol", "diverged_iters",
                 "diverged_breakdown", "unknown"]
-SOLVERS = {"cg": 0, "gmres": 1, "bicgstab": 2, "fcg": 3}
+SOLVERS = {"cg": 0, "gmres": 1, "bicgstab": 2, "fcg": 3, "cg_device": 4}
 PRECONDS = {None: 0, "none": 0, "identity": 0, "dinv": 1, "jacobi": 1, "relax": 2}
 
 
@@ -34,7 +34,7 @@ class Options(C.Structure):
     _fields_ = [("solver", C.c_int), ("precond", C.c_int), ("omega", C.c_float), ("nrelax", C.c_int),
                 ("maxiter", C.c_int), ("rtol", C.c_float), ("atol", C.c_float), ("use_zero_guess", C.c_int),
                 ("max_krylov_dim", C.c_int), ("restart", C.c_int), ("pre_side_left", C.c_int),
-                ("ev_start", C.c_int), ("ev_stop", C.c_int)]
+                ("ev_start", C.c_int), ("ev_stop", C.c_int), ("lag", C.c_int)]
 
 
 class BdfOptions(C.Structure):
@@ -73,9 +73,9 @@ def make_bdf_options(method="BDF2", starting="CN", predictor="leapfrog", strateg
 
 
 def make_options(solver="cg", precond=None, maxiter=1000, rtol=1e-9, atol=0.0, use_zero_guess=False, omega=2 / 3,
-                 nrelax=1, max_krylov_dim=-1, restart=False, pre_side="right", ev_start=-1, ev_stop=-1) -> Options:
+                 nrelax=1, max_krylov_dim=-1, restart=False, pre_side="right", ev_start=-1, ev_stop=-1, lag=2) -> Options:
     return Options(SOLVERS[solver], PRECONDS[precond], omega, nrelax, maxiter, rtol, atol, int(use_zero_guess),
-                   max_krylov_dim, int(restart), int(pre_side == "left"), ev_start, ev_stop)
+                   max_krylov_dim, int(restart), int(pre_side == "left"), ev_start, ev_stop, lag)
 
 
 _pd = C.POINTER(C.c_double)

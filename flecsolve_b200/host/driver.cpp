@@ -18,6 +18,7 @@
 #include "flecsolve/operators/shell.hh"
 #include "flecsolve/solvers/bicgstab.hh"
 #include "flecsolve/solvers/cg.hh"
+#include "flecsolve/solvers/cg_device.hh"
 #include "flecsolve/solvers/gmres.hh"
 #include "flecsolve/solvers/mg/jacobi.hh"
 #include "flecsolve/time-integrators/bdf.hh"
@@ -104,7 +105,7 @@ struct fsbh_info {
 };
 
 struct fsbh_options {
-	int solver; // 0 cg, 1 gmres, 2 bicgstab, 3 fcg
+	int solver; // 0 cg, 1 gmres, 2 bicgstab, 3 fcg, 4 cg with device-resident scalars (cg_device.hh)
 	int precond; // 0 identity (op::I), 1 diagonal inverse, 2 weighted Jacobi relaxation
 	float omega; // precond 2
 	int nrelax; // precond 2
@@ -113,6 +114,7 @@ struct fsbh_options {
 	int use_zero_guess;
 	int max_krylov_dim, restart, pre_side_left; // gmres
 	int ev_start, ev_stop; // record CUDA events 0 / 1 after this many iterations (-1: never)
+	int lag; // solver 4: iterations the host runs ahead of the residual norm it inspects
 };
 
 // settings of time_integrator::bdf (enum values in the order of bdf_parameters.hh)
@@ -184,6 +186,11 @@ solve_info run_solver(session & S_, const fsbh_options & o, P precond_handle, re
 	if (o.solver == 0) {
 		auto slv = cg::solver(cg::settings{o.maxiter, o.rtol, o.atol, o.use_zero_guess != 0},
 		                      cg::make_work(x))(op::ref(A), precond_handle, std::ref(rec));
+		return slv(b, x);
+	}
+	if (o.solver == 4) {
+		cg_device::settings st{{o.maxiter, o.rtol, o.atol, o.use_zero_guess != 0}, o.lag};
+		auto slv = cg_device::solver(st, cg_device::make_work(x))(op::ref(A), precond_handle, std::ref(rec));
 		return slv(b, x);
 	}
 	if (o.solver == 3) {

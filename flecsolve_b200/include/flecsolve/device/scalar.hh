@@ -1,0 +1,73 @@
+// Device-resident scalars for solver variants that never read a reduction on the host
+// (include/fsb.h, "device scalars").  No counterpart in the reference: its loops read every
+// reduction through future.get() (solvers/cg.hh:98-131); SURVEY 8(f) N1 asks for variants that
+// keep alpha/beta on the device and look at the residual norm late.
+#ifndef FLECSOLVE_B200_DEVICE_SCALAR_HH
+#define FLECSOLVE_B200_DEVICE_SCALAR_HH
+
+#include "flecsolve/device/runtime.hh"
+#include "flecsolve/util/future.hh"
+
+namespace flecsolve::device {
+
+struct scalar {
+	explicit scalar(fsb_ctx_t c) : ctx_(c) { check(fsb_scalar_create(c, &id_)); }
+	scalar(const scalar &) = delete;
+	scalar & operator=(const scalar &) = delete;
+	~scalar() { fsb_scalar_destroy(ctx_, id_); }
+
+	fsb_scalar_t id() const { return id_; }
+	void set(double v) { check(fsb_scalar_set(ctx_, id_, v)); }
+	double get() const {
+		double v = 0;
+		check(fsb_scalar_get(ctx_, id_, &v));
+		return v;
+	}
+
+private:
+	fsb_ctx_t ctx_;
+	fsb_scalar_t id_ = 0;
+};
+
+// coefficient  s * num / den  evaluated on the device when the statement runs
+inline fsb_coef ratio(double s, const scalar & num, const scalar & den) { return fsb_coef{s, num.id(), den.id()}; }
+inline fsb_coef number(double v) { return fsb_coef{v, 0, 0}; }
+
+// z = a x + b y  on single (topology) vectors
+template<class Z, class X, class Y>
+void linear_sum(Z & z, fsb_coef a, const X & x, fsb_coef b, const Y & y) {
+	check(fsb_vec_linear_sum_c(z.data.handle(), a, x.data.handle(), b, y.data.handle()));
+}
+
+// <x, y>, optionally kept in `store` and tested against the halt threshold
+template<class X, class Y>
+device_future dot(const X & x, const Y & y, const scalar * store, int halt_mode = FSB_HALT_NEVER, double threshold = 0) {
+	fsb_red_opts o{store ? store->id() : 0, halt_mode, threshold};
+	device_future f{x.data.ctx(), 0};
+	check(fsb_vec_dot_opts(x.data.handle(), y.data.handle(), &o, &f.token));
+	return f;
+}
+
+// while alive, element-wise statements become no-ops once a reduction's halt test has passed
+struct halt_scope {
+	explicit halt_scope(fsb_ctx_t c) : ctx_(c) { check(fsb_ctx_halt_arm(c)); }
+	halt_scope(const halt_scope &) = delete;
+	halt_scope & operator=(const halt_scope &) = delete;
+	bool release() { // returns whether the flag was raised
+		int was = 0;
+		if (ctx_)
+			check(fsb_ctx_halt_disarm(ctx_, &was));
+		ctx_ = nullptr;
+		return was != 0;
+	}
+	~halt_scope() {
+		if (ctx_)
+			fsb_ctx_halt_disarm(ctx_, nullptr);
+	}
+
+private:
+	fsb_ctx_t ctx_;
+};
+
+}
+#endif

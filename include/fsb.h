@@ -163,6 +163,48 @@ int fsb_vec_global_size(fsb_vec_t x, int64_t * out); /* sum of local sizes (topo
 int fsb_red_get(fsb_ctx_t ctx, fsb_token_t tok, double * out);
 int fsb_red_wait(fsb_ctx_t ctx, fsb_token_t tok);
 
+/* ---- device scalars (solver variants without host reads) ----
+ * The reference's Krylov loops read every reduction on the host and feed it back
+ * as a coefficient of the next vector call (solvers/cg.hh:98-131: alpha = rho /
+ * <p,Ap>, beta = rho' / rho).  These entry points keep that arithmetic on the
+ * device: a reduction may deposit its all-rank value in a scalar slot, a
+ * coefficient may be  scale * slot[num] / slot[den]  (evaluated with one IEEE
+ * division and one multiplication, so scale = +-1 gives the bits the host loop
+ * computes), and a reduction may carry the convergence test: once it passes, the
+ * context's halt flag is raised on the device and every later element-wise
+ * statement is skipped (vectors keep the converged iterate; reductions still
+ * deliver their tokens), until fsb_ctx_halt_disarm.  The host can therefore run
+ * several iterations ahead and look at residual norms late without changing the
+ * iterate it finally returns.  The flag is looked at when a launch begins:
+ * statements queued right behind the testing reduction may share its launch and
+ * still run (in CG: z = P r and <r,z>, which only touch work vectors); a statement
+ * whose coefficient names a slot stored by a reduction of the same run always
+ * starts a new launch, and fsb_ctx_flush ends the current one explicitly.
+ * Slot 0 is the constant 1.0: {v, 0, 0} is the plain number v.
+ * Handles are plain indices of the context (at most 63 live at a time). */
+typedef int32_t fsb_scalar_t;
+typedef struct fsb_coef {
+	double scale;
+	fsb_scalar_t num, den;
+} fsb_coef;
+enum { FSB_HALT_NEVER = 0, FSB_HALT_IF_SQRT_LT = 1, FSB_HALT_IF_LT = 2 };
+typedef struct fsb_red_opts {
+	fsb_scalar_t store; /* slot that receives the value (0: none) */
+	int halt_mode; /* FSB_HALT_*: raise the halt flag when [sqrt](value) < halt_threshold */
+	double halt_threshold;
+} fsb_red_opts;
+int fsb_scalar_create(fsb_ctx_t ctx, fsb_scalar_t * out);
+int fsb_scalar_destroy(fsb_ctx_t ctx, fsb_scalar_t s);
+int fsb_scalar_set(fsb_ctx_t ctx, fsb_scalar_t s, double value); /* in program order */
+int fsb_scalar_get(fsb_ctx_t ctx, fsb_scalar_t s, double * out); /* launches queued work and waits */
+/* z = a x + b y with device-resident coefficients (any aliasing, like fsb_vec_linear_sum) */
+int fsb_vec_linear_sum_c(fsb_vec_t z, fsb_coef a, fsb_vec_t x, fsb_coef b, fsb_vec_t y);
+/* dot / sum of squares (x == y) whose value also goes to opts->store and drives the halt flag */
+int fsb_vec_dot_opts(fsb_vec_t x, fsb_vec_t y, const fsb_red_opts * opts, fsb_token_t * tok);
+/* clear the halt flag and start honouring it / read it (optional), clear it and stop honouring it */
+int fsb_ctx_halt_arm(fsb_ctx_t ctx);
+int fsb_ctx_halt_disarm(fsb_ctx_t ctx, int * was_halted);
+
 /* ---- parallel CSR matrix ------------------------------------------------
  * Device image of mat::parcsr (matrices/parcsr.hh:101-177) on the topology
  * topo::csr (topo/csr.hh): per rank a `diag' CSR over owned columns and an

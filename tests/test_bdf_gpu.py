@@ -44,7 +44,11 @@ def test_scalar_decay_matches_reference(ctx, entry):
     assert np.array_equal(finite, np.isfinite(vals))
     assert np.allclose(vals[finite], rval[finite], rtol=1e-9, atol=0)
     assert abs(res.final_time - float.fromhex(ref["final_time"])) <= 1e-12
-    assert abs(res.value_max - float.fromhex(ref["value"])) <= 1e-9 * abs(res.value_max)
+    ref_value = float.fromhex(ref["value"])
+    if np.isfinite(ref_value):
+        assert abs(res.value_max - ref_value) <= 1e-9 * abs(res.value_max)
+    else:  # the run ended on a blown-up attempt (BDF6 is not zero-stable): non-finite on both sides
+        assert not np.isfinite(res.value_max)
     if method == "BDF5" and lam == -1.0:  # the reference's KAT: 48 steps, 14 rejects, error < 1e-7
         assert res.steps == 48 and res.rejects == 14
         assert abs(ic * np.exp(lam * tf) - res.value_max) < 1e-7
