@@ -47,7 +47,7 @@ class BdfOptions(C.Structure):
 
 class BdfResult(C.Structure):
     _fields_ = [("attempts", C.c_int), ("steps", C.c_int), ("rejects", C.c_int), ("final_time", C.c_double),
-                ("value_max", C.c_double), ("value_l2", C.c_double), ("inner_iterations", C.c_int)]
+                ("value_max", C.c_double), ("value_l2", C.c_double), ("inner_iterations", C.c_int), ("solve_ms", C.c_double)]
 
 
 class RkOptions(C.Structure):
@@ -79,6 +79,7 @@ def make_options(solver="cg", precond=None, maxiter=1000, rtol=1e-9, atol=0.0, u
 
 
 _pd = C.POINTER(C.c_double)
+_pl = C.POINTER(C.c_int64)
 
 
 def lib() -> C.CDLL:
@@ -109,6 +110,10 @@ def lib() -> C.CDLL:
                                    C.POINTER(BdfResult), _pd, _pi, _pd, C.c_int]
         L.fsbh_bdf_heat.argtypes = [C.c_void_p, C.POINTER(BdfOptions), C.POINTER(Options), _pd, _pd,
                                     C.POINTER(BdfResult), _pd, _pi, _pi, C.c_int]
+        L.fsbh_mtx_read.argtypes = [C.c_char_p, _pl, _pl, _pl, _pi, _pl, _pl, _pd]
+        L.fsbh_mtx_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.fsbh_config_dump.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+        L.fsbh_solve_config.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, _pd, _pd, C.POINTER(Info), _pd, C.c_int]
         _lib = L
     return _lib
 
@@ -154,6 +159,16 @@ class Session:
             _check(lib().fsbh_solve(self.h, C.byref(opts), _d(b), _d(x), C.byref(info), _d(hist), history_cap))
         return x, info, hist[:min(info.callbacks, history_cap)]
 
+    def solve_config(self, cfg: str, prefix: str, b, x0=None, precond=None, history_cap=0):
+        """solve with the solver `[prefix] type = ...` names (krylov_factory)"""
+        info = Info()
+        hist = np.zeros(max(history_cap, 1))
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.array(x0 if x0 is not None else np.zeros_like(b), dtype=np.float64)
+        _check(lib().fsbh_solve_config(self.h, cfg.encode(), prefix.encode(), PRECONDS[precond], _d(b), _d(x),
+                                       C.byref(info), _d(hist), history_cap))
+        return x, info, hist[:min(info.callbacks, history_cap)]
+
     def adapter_apply(self, gamma: float, x) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.zeros_like(x)
@@ -176,6 +191,35 @@ class Session:
         out = np.zeros(16)
         _check(lib().fsbh_vector_selftest(self.h, _d(out)))
         return out
+
+
+def read_mtx(path: str):
+    """Matrix Market file -> (nrows, ncols, symmetric, rowptr, col, val) with the reference reader's rules
+    (float-rounded values, mirrored symmetric entries, stable sort by row)."""
+    nr, nc, nz, sym = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+    args = (path.encode(), C.byref(nr), C.byref(nc), C.byref(nz), C.byref(sym))
+    _check(lib().fsbh_mtx_read(*args, None, None, None))
+    rp, col, val = np.zeros(nr.value + 1, dtype=np.int64), np.zeros(nz.value, dtype=np.int64), np.zeros(nz.value)
+    _check(lib().fsbh_mtx_read(*args, rp.ctypes.data_as(_pl), col.ctypes.data_as(_pl), _d(val)))
+    return nr.value, nc.value, bool(sym.value), rp, col, val
+
+
+def mtx_create(ctx: F.Context, path: str) -> F.ParCSR:
+    """this rank's equal row block of a Matrix Market file as a device matrix"""
+    h = C.c_void_p()
+    _check(lib().fsbh_mtx_create(ctx.h, path.encode(), C.byref(h)))
+    return F.ParCSR(ctx, h)
+
+
+CONFIG_KINDS = {"solver": 0, "krylov": 1, "bdf": 2, "heat": 3}
+
+
+def config_dump(path: str, kind: str, prefix: str) -> dict:
+    """read_config(path, <kind>::options(prefix)) -> the settings as a dict"""
+    import json
+    buf = C.create_string_buffer(4096)
+    _check(lib().fsbh_config_dump(path.encode(), CONFIG_KINDS[kind], prefix.encode(), buf, len(buf)))
+    return json.loads(buf.value.decode())
 
 
 def solve_multi2(ctx: F.Context, A0: F.ParCSR, A1: F.ParCSR, b, x0, history_cap=0, **kw):

@@ -13,12 +13,17 @@
 #include <optional>
 #include <string>
 #include <vector>
+#include <variant>
+#include <sstream>
+#include <fstream>
 
 #include "flecsolve/matrices/parcsr.hh"
 #include "flecsolve/operators/shell.hh"
 #include "flecsolve/solvers/bicgstab.hh"
 #include "flecsolve/solvers/cg.hh"
 #include "flecsolve/solvers/cg_device.hh"
+#include "flecsolve/solvers/factory.hh"
+#include "flecsolve/matrices/io/matrix_market.hh"
 #include "flecsolve/solvers/gmres.hh"
 #include "flecsolve/solvers/mg/jacobi.hh"
 #include "flecsolve/time-integrators/bdf.hh"
@@ -145,6 +150,7 @@ struct fsbh_bdf_result {
 	int attempts, steps, rejects;
 	double final_time, value_max, value_l2; // max and l2 norm of the final solution
 	int inner_iterations; // total Krylov iterations over all attempts (heat driver)
+	double solve_ms; // heat driver: wall clock of the integration alone, device idle on both sides
 };
 
 }
@@ -569,6 +575,8 @@ int fsbh_bdf_heat(void * sv, const fsbh_bdf_options * o, const fsbh_options * so
 		auto unew = vec::make(unewd(S.A.data.topo()));
 		const std::int64_t n = fsb_vec_local_size(u.data.handle());
 		device::check(fsb_vec_upload(u.data.handle(), u0_host, n, 0));
+		fsb_ctx_sync(S.ctx.handle());
+		const auto t_begin = std::chrono::steady_clock::now();
 
 		auto F = op::make_shared<operator_adapter<matrix_rhs>>(&S.A);
 		int total_iters = 0, last_iters = 0;
@@ -606,6 +614,8 @@ int fsbh_bdf_heat(void * sv, const fsbh_bdf_options * o, const fsbh_options * so
 				F, op::I, std::ref(count)));
 		}
 		res->inner_iterations = total_iters;
+		fsb_ctx_sync(S.ctx.handle());
+		res->solve_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 		device::check(fsb_vec_download(u.data.handle(), u_host, n, 0));
 	});
 }
@@ -680,6 +690,138 @@ int fsbh_vector_selftest(void * sv, double * err16) {
 		x.set_scalar(-3.141719);
 		err16[k++] = std::abs(x.l1norm().get() - N * 3.141719);
 		err16[k++] = std::abs(x.l2norm().get() - std::sqrt(N * 3.141719 * 3.141719));
+	});
+}
+
+// ---- on-disk formats and configuration -----------------------------------------
+
+// Matrix Market file -> CSR with the reference reader's rules.  First call with rowptr == null to get
+// the sizes (nnz counts mirrored entries of a symmetric file), then with buffers to fill.
+int fsbh_mtx_read(const char * fname, std::int64_t * nrows, std::int64_t * ncols, std::int64_t * nnz, int * symmetric,
+                  std::int64_t * rowptr, std::int64_t * col, double * val) {
+	return guarded([&] {
+		using mm = mat::io::matrix_market<double, std::size_t>;
+		std::ifstream fh(fname);
+		if (!fh)
+			throw std::runtime_error(std::string("cannot open ") + fname);
+		const auto hdr = mm::read_header(fh);
+		const auto csr = mm::read(fh, hdr).tocsr();
+		*nrows = static_cast<std::int64_t>(csr.nrows);
+		*ncols = static_cast<std::int64_t>(csr.ncols);
+		*nnz = static_cast<std::int64_t>(csr.nnz());
+		*symmetric = hdr.symmetric ? 1 : 0;
+		if (rowptr) {
+			std::copy(csr.offsets.begin(), csr.offsets.end(), rowptr);
+			std::copy(csr.indices.begin(), csr.indices.end(), col);
+			std::copy(csr.values.begin(), csr.values.end(), val);
+		}
+	});
+}
+
+// this rank's equal row block of the file as a device matrix (what mat::parcsr does with a
+// matrix_market::definition, matrices/parcsr.hh:101-177)
+int fsbh_mtx_create(fsb_ctx_t ctx_h, const char * fname, fsb_parcsr_t * out) {
+	return guarded([&] {
+		mat::io::matrix_market<double, std::size_t>::definition def(fname);
+		auto ci = def.init_for<csr_topo::init>(static_cast<std::size_t>(fsb_ctx_rank(ctx_h)),
+		                                       static_cast<std::size_t>(fsb_ctx_nranks(ctx_h)));
+		device::check(fsb_parcsr_create(ctx_h, static_cast<std::int64_t>(ci.nrows), ci.row_part.offsets.data(), ci.offsets.data(),
+		                                ci.indices.data(), ci.values.data(), out));
+	});
+}
+
+namespace {
+void put(std::ostream & os, const solver_settings & s) {
+	os << "\"maxiter\": " << s.maxiter << ", \"rtol\": " << s.rtol << ", \"atol\": " << s.atol
+	   << ", \"use_zero_guess\": " << (s.use_zero_guess ? "true" : "false");
+}
+}
+
+// Parse `fname` with one option set and print the resulting settings as JSON:
+//   kind 0: solver_options(prefix)   1: krylov_factory::options(prefix)   2: bdf::options(prefix)
+//   kind 3: bdf::options("time-integrator") and krylov_factory::options("linear-solver") in ONE read_config call,
+//           as examples/heat_equation/implicit.cc:19-22 does (prefix unused)
+int fsbh_config_dump(const char * fname, int kind, const char * prefix, char * out, int cap) {
+	return guarded([&] {
+		std::ostringstream os;
+		os.precision(17);
+		os << "{";
+		std::optional<krylov_factory::settings> ks;
+		std::optional<time_integrator::bdf::settings> bs;
+		if (kind == 3) {
+			auto [ti, ls] = read_config(fname, time_integrator::bdf::options("time-integrator"),
+			                            krylov_factory::options("linear-solver"));
+			bs = ti;
+			ks = ls;
+		}
+		if (kind == 0) {
+			put(os, read_config(fname, solver_options(prefix)));
+		}
+		if (kind == 1 || kind == 3) {
+			auto s = kind == 1 ? read_config(fname, krylov_factory::options(prefix)) : *ks;
+			static const char * names[] = {"cg", "gmres", "bicgstab", "cg-device"};
+			os << "\"type\": \"" << names[static_cast<int>(s.target_id.value())] << "\", ";
+			std::visit(
+				[&](const auto & t) {
+					put(os, t);
+					using T = std::decay_t<decltype(t)>;
+					if constexpr (std::is_same_v<T, gmres::settings>)
+						os << ", \"max_krylov_dim\": " << t.max_krylov_dim << ", \"pre_side\": \"" << t.pre_side
+						   << "\", \"restart\": " << (t.restart ? "true" : "false");
+					if constexpr (std::is_same_v<T, cg_device::settings>)
+						os << ", \"lag\": " << t.lag;
+				},
+				s.target_settings);
+		}
+		if (kind == 3)
+			os << ", ";
+		if (kind == 2 || kind == 3) {
+			auto s = kind == 2 ? read_config(fname, time_integrator::bdf::options(prefix)) : *bs;
+			os << "\"initial_time\": " << s.initial_time << ", \"final_time\": " << s.final_time << ", \"max_steps\": " << s.max_steps
+			   << ", \"max_dt\": " << s.max_dt << ", \"min_dt\": " << s.min_dt << ", \"initial_dt\": " << s.initial_dt
+			   << ", \"integrator\": " << static_cast<int>(s.integrator) << ", \"starting_integrator\": "
+			   << static_cast<int>(s.starting_integrator) << ", \"predictor\": " << static_cast<int>(s.predictor)
+			   << ", \"strategy\": " << static_cast<int>(s.timestep_strategy) << ", \"controller\": "
+			   << static_cast<int>(s.pi_controller_type) << ", \"norm\": " << static_cast<int>(s.time_trunc_err_norm)
+			   << ", \"error_scaling\": " << static_cast<int>(s.time_error_scaling) << ", \"time_rtol\": " << s.time_rtol
+			   << ", \"time_atol\": " << s.time_atol << ", \"use_predictor\": " << (s.use_predictor ? "true" : "false")
+			   << ", \"use_pi_controller\": " << (s.use_pi_controller ? "true" : "false") << ", \"problem_scales\": [";
+			for (std::size_t i = 0; i < s.problem_scales.size(); ++i)
+				os << (i ? ", " : "") << s.problem_scales[i];
+			os << "]";
+		}
+		os << "}";
+		const std::string text = os.str();
+		if (static_cast<int>(text.size()) + 1 > cap)
+			throw std::runtime_error("config dump: buffer too small");
+		std::memcpy(out, text.c_str(), text.size() + 1);
+	});
+}
+
+// Solve with the solver a configuration file names: krylov_factory::options(prefix) -> make(settings, x, A, P, diag)
+// (examples/heat_equation/implicit.cc:19-28 uses the same two calls).  precond: 0 identity, 1 1/diag.
+int fsbh_solve_config(void * sv, const char * fname, const char * prefix, int precond, const double * b_host, double * x_host,
+                      fsbh_info * info, double * history, int history_cap) {
+	return guarded([&] {
+		session & S = *static_cast<session *>(sv);
+		const std::int64_t n = fsb_vec_local_size(S.b.data.handle());
+		device::check(fsb_vec_upload(S.b.data.handle(), b_host, n, 0));
+		device::check(fsb_vec_upload(S.x.data.handle(), x_host, n, 0));
+		auto settings = read_config(fname, krylov_factory::options(prefix));
+		recorder rec{S.ctx.handle(), history, history_cap, -1, -1};
+		solve_info si;
+		if (precond == 1) {
+			if (!S.dinv)
+				S.dinv = std::make_unique<op::core<op::diagonal_inverse<double, std::size_t>>>(S.A);
+			auto slv = krylov_factory::make(settings, S.x, op::ref(S.A), op::ref(*S.dinv), std::ref(rec));
+			si = slv(S.b, S.x);
+		}
+		else {
+			auto slv = krylov_factory::make(settings, S.x, op::ref(S.A), op::I, std::ref(rec));
+			si = slv(S.b, S.x);
+		}
+		device::check(fsb_vec_download(S.x.data.handle(), x_host, n, 0));
+		fill(info, si, rec.count);
 	});
 }
 

@@ -156,6 +156,11 @@ bicgstab(P) -> bicgstab<P>;
 namespace flecsolve::bicgstab {
 static constexpr std::size_t nwork = 8;
 struct settings : solver_settings {};
+struct options : solver_options {
+	using settings_type = settings;
+	options(const char * pre) : solver_options(pre) {}
+	po::options_description operator()(settings_type & s) { return solver_options::operator()(s); }
+};
 static inline work_factory<nwork> make_work;
 
 template<class Workspace>

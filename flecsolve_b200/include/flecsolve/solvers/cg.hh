@@ -194,6 +194,7 @@ fcg(P) -> fcg<P>;
 namespace flecsolve::cg {
 static constexpr std::size_t nwork = 4;
 using settings = solver_settings;
+using options = solver_options;
 static inline work_factory<nwork> make_work;
 
 template<class Work>
@@ -209,6 +210,7 @@ solver(const settings &, W &&) -> solver<std::decay_t<W>>;
 namespace flecsolve::fcg {
 static constexpr std::size_t nwork = 5;
 using settings = solver_settings;
+using options = solver_options;
 static inline work_factory<nwork> make_work;
 
 template<class Work>

@@ -34,6 +34,16 @@ namespace flecsolve::cg_device {
 struct settings : solver_settings {
 	int lag = 2; // iterations the host runs ahead of the residual norm it inspects
 };
+struct options : solver_options {
+	using settings_type = settings;
+	options(const char * pre) : solver_options(pre) {}
+	po::options_description operator()(settings_type & s) {
+		auto desc = solver_options::operator()(s);
+		desc.add_options()(label("lag").c_str(), po::value<int>(&s.lag)->default_value(2),
+		                   "iterations issued ahead of the inspected residual norm");
+		return desc;
+	}
+};
 }
 
 namespace flecsolve::op {

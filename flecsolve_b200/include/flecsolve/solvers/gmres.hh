@@ -279,6 +279,21 @@ gmres(P) -> gmres<P>;
 
 namespace flecsolve::gmres {
 
+// INI keys beside solver_options': max-krylov-dim (-1), pre-side (right), restart (false); reference :406-422
+struct options : solver_options {
+	using settings_type = settings;
+	options(const char * pre) : solver_options(pre) {}
+	po::options_description operator()(settings_type & s) {
+		auto desc = solver_options::operator()(s);
+		desc.add_options()
+			(label("max-krylov-dim").c_str(), po::value<int>(&s.max_krylov_dim)->default_value(-1), "maximum krylov dimension")
+			(label("pre-side").c_str(), po::value<precond_side>(&s.pre_side)->default_value(precond_side::right),
+			 "preconditioner side")
+			(label("restart").c_str(), po::value<bool>(&s.restart)->default_value(false), "should restart");
+		return desc;
+	}
+};
+
 static inline work_factory<nwork> make_work;
 
 template<class Work>

@@ -1,9 +1,8 @@
 // Solver settings, results and work-vector factories.
 //
 // Reference: flecsolve/solvers/solver_settings.hh:31-200.  Field names and types are kept
-// (note rtol/atol and the norms in solve_info are float).  The Boost.program_options
-// `solver_options` parser is configuration plumbing outside the hot path; settings are
-// aggregate-initialised instead.
+// (note rtol/atol and the norms in solve_info are float).  `solver_options` binds them to the
+// INI keys <prefix>.maxiter / rtol / atol / use-zero-guess (reference :37-57) through util/config.hh.
 #ifndef FLECSOLVE_B200_SOLVERS_SOLVER_SETTINGS_HH
 #define FLECSOLVE_B200_SOLVERS_SOLVER_SETTINGS_HH
 
@@ -12,6 +11,7 @@
 #include <tuple>
 #include <type_traits>
 
+#include "flecsolve/util/config.hh"
 #include "flecsolve/vectors/multi.hh"
 #include "flecsolve/vectors/topo_view.hh"
 
@@ -22,6 +22,21 @@ struct solver_settings {
 	float rtol;
 	float atol;
 	bool use_zero_guess;
+};
+
+struct solver_options : with_label {
+	using settings_type = solver_settings;
+	solver_options(const char * pre) : with_label(pre) {}
+
+	po::options_description operator()(settings_type & settings) {
+		po::options_description desc;
+		desc.add_options()
+			(label("maxiter").c_str(), po::value<int>(&settings.maxiter)->required(), "maximum number of iterations")
+			(label("rtol").c_str(), po::value<float>(&settings.rtol)->default_value(0), "relative tolerance")
+			(label("atol").c_str(), po::value<float>(&settings.atol)->default_value(0), "absolute tolerance")
+			(label("use-zero-guess").c_str(), po::value<bool>(&settings.use_zero_guess)->required(), "use zero initial guess");
+		return desc;
+	}
 };
 
 struct solve_stats {};

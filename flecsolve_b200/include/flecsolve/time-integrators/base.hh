@@ -8,6 +8,7 @@
 #include <utility>
 
 #include "flecsolve/operators/handle.hh"
+#include "flecsolve/util/config.hh"
 
 namespace flecsolve::time_integrator {
 
@@ -18,6 +19,25 @@ struct base_settings {
 	double max_dt = std::numeric_limits<double>::max();
 	double min_dt = std::numeric_limits<double>::min();
 	double initial_dt = 0;
+};
+
+// INI keys <prefix>.initial-time / final-time / max-steps (required), max-dt, min-dt, initial-dt
+// (reference time-integrators/parameters.hh:39-56)
+struct base_options : with_label {
+	using settings_type = base_settings;
+	explicit base_options(const char * pre) : with_label(pre) {}
+
+	po::options_description operator()(settings_type & s) {
+		po::options_description desc;
+		desc.add_options()
+			(label("initial-time").c_str(), po::value<double>(&s.initial_time)->required(), "initial time")
+			(label("final-time").c_str(), po::value<double>(&s.final_time)->required(), "final time")
+			(label("max-steps").c_str(), po::value<int>(&s.max_steps)->required(), "maximum number of steps")
+			(label("max-dt").c_str(), po::value<double>(&s.max_dt)->default_value(std::numeric_limits<double>::max()), "")
+			(label("min-dt").c_str(), po::value<double>(&s.min_dt)->default_value(std::numeric_limits<double>::min()), "")
+			(label("initial-dt").c_str(), po::value<double>(&s.initial_dt)->default_value(0), "");
+		return desc;
+	}
 };
 
 // settings + the right-hand-side operator + work vectors

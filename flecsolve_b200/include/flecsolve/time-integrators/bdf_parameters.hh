@@ -4,6 +4,7 @@
 #ifndef FLECSOLVE_B200_TIME_INTEGRATORS_BDF_PARAMETERS_HH
 #define FLECSOLVE_B200_TIME_INTEGRATORS_BDF_PARAMETERS_HH
 
+#include <cctype>
 #include <istream>
 #include <stdexcept>
 #include <string>
@@ -30,10 +31,14 @@ inline short order(method m) {
 }
 
 namespace detail {
+// lower: the reference lower-cases predictor / strategy tokens before comparing (bdf_parameters.cc:9-46)
 template<class E>
-std::istream & parse(std::istream & in, E & out, std::initializer_list<std::pair<const char *, E>> table) {
+std::istream & parse(std::istream & in, E & out, std::initializer_list<std::pair<const char *, E>> table, bool lower = false) {
 	std::string tok;
 	in >> tok;
+	if (lower)
+		for (auto & ch : tok)
+			ch = static_cast<char>(std::tolower(static_cast<unsigned char>(ch)));
 	for (const auto & [name, value] : table)
 		if (tok == name) {
 			out = value;
@@ -44,14 +49,15 @@ std::istream & parse(std::istream & in, E & out, std::initializer_list<std::pair
 }
 }
 inline std::istream & operator>>(std::istream & in, predictor & p) {
-	return detail::parse(in, p, {{"ab2", predictor::ab2}, {"leapfrog", predictor::leapfrog}});
+	return detail::parse(in, p, {{"ab2", predictor::ab2}, {"leapfrog", predictor::leapfrog}}, true);
 }
 inline std::istream & operator>>(std::istream & in, strategy & s) {
 	return detail::parse(in, s,
 	                     {{"truncation-error", strategy::truncation_error},
 	                      {"constant", strategy::constant},
 	                      {"final-constant", strategy::final_constant},
-	                      {"limit-relative-change", strategy::limit_relative_change}});
+	                      {"limit-relative-change", strategy::limit_relative_change}},
+	                     true);
 }
 inline std::istream & operator>>(std::istream & in, method & m) {
 	return detail::parse(in, m,
@@ -127,6 +133,51 @@ struct settings : base_settings {
 			else if (integrator == method::cn)
 				require(predictor == bdf::predictor::ab2, "Valid option for Crank-Nicolson predictor is only ab2 currently");
 		}
+	}
+};
+
+// INI keys of the reference's option table (bdf_parameters.hh:116-151), after base_options'
+struct options : base_options {
+	using settings_type = settings;
+	explicit options(const char * pre) : base_options(pre) {}
+
+	po::options_description operator()(settings_type & s) {
+		auto desc = base_options::operator()(s);
+		desc.add_options()
+			(label("use-predictor").c_str(), po::value<bool>(&s.use_predictor)->default_value(true), "use a predictor")
+			(label("has-source-term").c_str(), po::value<bool>(&s.has_source_term)->default_value(false), "has source term")
+			(label("use-initial-predictor").c_str(), po::value<bool>(&s.use_initial_predictor)->default_value(true),
+			 "use an initial predictor")
+			(label("predictor").c_str(), po::value<bdf::predictor>(&s.predictor)->required(), "ab2 or leapfrog")
+			(label("timestep-selection-strategy").c_str(), po::value<strategy>(&s.timestep_strategy)->required(),
+			 "truncation-error, constant, final-constant or limit-relative-change")
+			(label("dt-cut-lower-bound").c_str(), po::value<double>(&s.dt_cut_lower_bound)->default_value(0.58754407), "")
+			(label("dt-growth-upper-bound").c_str(), po::value<double>(&s.dt_growth_upper_bound)->default_value(1.702), "")
+			(label("number-of-time-intervals").c_str(), po::value<int>(&s.number_of_time_intervals)->default_value(100),
+			 "final-constant strategy")
+			(label("integrator").c_str(), po::value<bdf::method>(&s.integrator)->required(), "BE, CN or BDF2..BDF6")
+			(label("starting-integrator").c_str(),
+			 po::value<bdf::method>(&s.starting_integrator)->required()->notifier([](const bdf::method & m) {
+				 if (memory_size(m) != 1)
+					 throw std::invalid_argument("BE or CN must be used for starting integrator");
+			 }),
+			 "one step integrator (BE or CN)")
+			(label("calculate-time-trunc-error").c_str(), po::value<bool>(&s.calculate_time_trunc_error), "")
+			(label("time-trunc-error-norm").c_str(), po::value<vec::norm_type>(&s.time_trunc_err_norm), "inf, l1 or l2")
+			(label("target-relative-change").c_str(), po::value<double>(&s.target_relative_change), "")
+			(label("use-pi-controller").c_str(), po::value<bool>(&s.use_pi_controller)->default_value(true), "")
+			(label("pi-controller-type").c_str(),
+			 po::value<bdf::controller>(&s.pi_controller_type)->default_value(bdf::controller::pc4_7, "PC.4.7"),
+			 "H211b, PC.4.7, PC11 or Deadbeat")
+			(label("control-timestep-variation").c_str(), po::value<bool>(&s.control_timestep_variation)->default_value(false), "")
+			(label("time-error-scaling").c_str(),
+			 po::value<bdf::error_scaling>(&s.time_error_scaling)->default_value(error_scaling::fixed_scaling, "fixed-scaling"),
+			 "fixed-scaling or fixed-resolution")
+			(label("trunc-error-rtol").c_str(), po::value<double>(&s.time_rtol)->default_value(1e-9), "")
+			(label("trunc-error-atol").c_str(), po::value<double>(&s.time_atol)->default_value(1e-15), "")
+			(label("combine-timestep-estimators").c_str(), po::value<bool>(&s.combine_timestep_estimators)->default_value(false), "")
+			(label("problem-scales").c_str(), po::value<std::vector<double>>(&s.problem_scales)->multitoken(), "");
+		return desc;
 	}
 };
 

@@ -3,6 +3,7 @@
 #ifndef FLECSOLVE_B200_VECTORS_UTIL_HH
 #define FLECSOLVE_B200_VECTORS_UTIL_HH
 
+#include <cctype>
 #include <istream>
 #include <string>
 #include <tuple>
@@ -40,6 +41,8 @@ enum class norm_type { inf, l2, l1 };
 inline std::istream & operator>>(std::istream & in, norm_type & n) {
 	std::string tok;
 	in >> tok;
+	for (auto & ch : tok) // the reference lower-cases the token (vectors/util.cc:13-16)
+		ch = static_cast<char>(std::tolower(static_cast<unsigned char>(ch)));
 	if (tok == "inf")
 		n = norm_type::inf;
 	else if (tok == "l1")

@@ -23,6 +23,7 @@ def main() -> int:
                                               "flecsolve/time-integrators/bdf_parameters.cc",
                                               "flecsolve/vectors/util.cc"]),
         ("refcheck_rk", "refcheck_rk.cpp", []),
+        ("refcheck_mtx", "refcheck_mtx.cpp", []),
     ]
     rc = 0
     for name, driver, ref_units in targets:

@@ -95,6 +95,13 @@ def main():
     m = min(len(hist), len(ohist), 30)
     assert np.allclose(hist[:m], ohist[:m], rtol=1e-8)
     assert ctx.stat("halo_exchanges") > 0 or P == 1
+    # device-scalar CG: every rank raises its halt flag from the same all-rank value, in the same iteration
+    xd, dinfo, dhist = S.solve(b[lo:hi], np.zeros(hi - lo), solver="cg_device", precond="dinv", rtol=1e-9, maxiter=1000,
+                               history_cap=1000, lag=2)
+    assert dinfo.reason == "converged_rtol" and abs(dinfo.iters - info.iters) <= 1, (dinfo.iters, info.iters)
+    m = min(len(hist), len(dhist), 30)
+    assert np.allclose(dhist[:m], hist[:m], rtol=1e-8)
+    assert np.abs(xd - xo[lo:hi]).max() <= 1e-6
     if P > 1 and os.environ.get("FSB_P2P_REDUCE") == "0":
         assert ctx.stat("allreduces") > 0  # the NCCL path really ran
     elif P > 1:
