@@ -290,13 +290,14 @@ def run_reference(args):
     world = D.world_from_env()
     if world.rank != 0:
         return
-    iters = max(1, min(args.steps, args.cpu_iters_cap))
-    base = cpu_baseline(args.workload, sample_iters=iters, warm=max(1, min(args.warmup, 3)))
+    # at least 20 and at most --cpu-iters-cap iterations: a handful of iterations mostly times page faults
+    iters = min(max(args.steps, 20), args.cpu_iters_cap)
+    base = cpu_baseline(args.workload, sample_iters=iters, warm=3)
     kind, nx, ny, nz, precond = WORKLOADS[args.workload]
     line = {
         "impl": "reference",
         "metric": "cg_iterations_per_second", "value": base["value"], "unit": "iterations/s",
-        "n_gpus": args.gpus, "steps": iters, "warmup": min(args.warmup, 3), "ms_per_step": 1000.0 / base["value"],
+        "n_gpus": args.gpus, "steps": iters, "warmup": 3, "ms_per_step": 1000.0 / base["value"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {kind}-point Poisson {nx}x{ny}x{nz}, reference CPU path restated "
                                f"(oracle/oracle.cpp), {'Jacobi' if precond else 'un'}preconditioned CG"},
