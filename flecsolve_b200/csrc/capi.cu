@@ -155,7 +155,6 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 		c->device = device;
 		c->rank = rank;
 		c->nranks = nranks;
-		c->reproducible = nranks == 1;
 		FSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 		FSB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
 		FSB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
@@ -193,6 +192,12 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 		}
 		if (nranks > 1 && !(std::getenv("FSB_P2P_REDUCE") && std::atoi(std::getenv("FSB_P2P_REDUCE")) == 0))
 			setup_peer_reductions(c);
+		// Static row-block schedule (bitwise reproducible, and measured faster: profiles/r1_scaling_final.txt)
+		// unless NCCL kernels share the SMs with the SpMV: a CTA that starts late behind a communication
+		// kernel would otherwise stretch the one-wave grid into two.
+		c->reproducible = nranks == 1 || c->d_xrank != nullptr;
+		if (const char * e = std::getenv("FSB_REPRODUCIBLE")) // measurement override
+			c->reproducible = std::atoi(e) != 0;
 		if (const char * t = std::getenv("FSB_TRACE"))
 			c->trace = std::atoi(t) != 0;
 		if (const char * t = std::getenv("FSB_FUSION"))

@@ -54,9 +54,10 @@ enum fsb_option {
 	FSB_OPT_TRACE = 3, /* 1: print every launched group signature to stderr */
 	FSB_OPT_PROFILE = 4, /* 1: bracket every SpMV kernel with CUDA events (fsb_ctx_profile_read) */
 	FSB_OPT_REPRODUCIBLE = 5 /* 1: SpMV row blocks are assigned to CTAs statically, so a fused dot is bitwise
-	                            reproducible run to run (default on one rank); 0: row blocks are claimed
-	                            dynamically, which tolerates SMs shared with communication kernels
-	                            (default on several ranks; results then vary in the last bits) */
+	                            reproducible run to run (default; the cross-rank fold is in rank order);
+	                            0: row blocks are claimed dynamically, which tolerates SMs shared with
+	                            communication kernels (default when halo and reductions go through NCCL;
+	                            results then vary in the last bits) */
 };
 
 enum fsb_stat {
