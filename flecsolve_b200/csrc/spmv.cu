@@ -442,7 +442,13 @@ static int launch_variant(const spmv_args & a, const spmv_config & k, cudaStream
 		ctas = std::min(ctas, k.grid);
 	const int grid = std::max(1, std::min(a.n_blk, SM_COUNT * ctas));
 	spmv_args b = a;
-	b.chunk = std::max(1, std::min(4, a.n_blk / (grid * 8))); // >= 8 claims per CTA, else finest grain
+	// dynamic claims: CHUNK blocks per atomic, >= 8 claims per CTA, else finest grain.  Static schedule: plain
+	// round-robin of single row blocks -- all CTAs sweep one narrow band of rows, which keeps the x planes a
+	// stencil row needs in L2/L1 (measured: 6.9 TB/s vs 6.5 with 4-block chunks on 7-pt 256^3)
+	b.chunk = a.static_sched ? 1 : std::max(1, std::min(4, a.n_blk / (grid * 8)));
+	static const int env_chunk = env_int("FSB_SPMV_CHUNK", 0);
+	if (env_chunk > 0)
+		b.chunk = std::min(env_chunk, 4);
 	kern<<<grid, k.threads, k.smem, s>>>(b);
 	FSB_CUDA(cudaGetLastError());
 	return grid;
