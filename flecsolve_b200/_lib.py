@@ -131,6 +131,10 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_vec_global_size", C.c_int, _p, _pi64)
     f("fsb_red_get", C.c_int, _p, _i64, _pd)
     f("fsb_red_wait", C.c_int, _p, _i64)
+    f("fsb_vec_create_box", C.c_int, _p, C.c_int, _pi64, _pi64, _pi64, C.POINTER(_p))
+    f("fsb_vec_box_upload_all", C.c_int, _p, _pd)
+    f("fsb_vec_box_download_all", C.c_int, _p, _pd)
+    f("fsb_parcsr_create_box_stencil", C.c_int, _p, C.c_int, _pi64, _pi64, _pi64, _dbl, _pd, C.POINTER(_p))
     f("fsb_scalar_create", C.c_int, _p, C.POINTER(C.c_int32))
     f("fsb_scalar_destroy", C.c_int, _p, C.c_int32)
     f("fsb_scalar_set", C.c_int, _p, C.c_int32, _dbl)
@@ -246,6 +250,24 @@ class Context:
         check(lib().fsb_red_get(self.h, token, C.byref(out)))
         return out.value
 
+    # structured-grid vectors / operators (fsb.h "narray")
+    def box_vector(self, extents, lo, hi) -> "Vector":
+        e, l, h = (np.ascontiguousarray(a, dtype=np.int64) for a in (extents, lo, hi))
+        hnd = _p()
+        check(lib().fsb_vec_create_box(self.h, len(e), e.ctypes.data_as(_pi64), l.ctypes.data_as(_pi64),
+                                       h.ctypes.data_as(_pi64), C.byref(hnd)))
+        v = Vector(self, int(np.prod(h - l)), int(np.prod(e) - np.prod(h - l)), handle=hnd)
+        v.box_extents = tuple(int(x) for x in e)
+        return v
+
+    def box_stencil(self, extents, lo, hi, center: float, off) -> "ParCSR":
+        e, l, h = (np.ascontiguousarray(a, dtype=np.int64) for a in (extents, lo, hi))
+        o = np.ascontiguousarray(off, dtype=np.float64)
+        hnd = _p()
+        check(lib().fsb_parcsr_create_box_stencil(self.h, len(e), e.ctypes.data_as(_pi64), l.ctypes.data_as(_pi64),
+                                                  h.ctypes.data_as(_pi64), center, _dptr(o), C.byref(hnd)))
+        return ParCSR(self, hnd)
+
     # device scalars (fsb.h "device scalars")
     def scalar(self, value: float | None = None) -> int:
         s = C.c_int32()
@@ -288,6 +310,18 @@ class Vector:
         a = np.ascontiguousarray(a, dtype=np.float64)
         check(lib().fsb_vec_upload(self.h, _dptr(a), a.size, offset))
         return self
+
+    def upload_all(self, a):
+        """structured-grid vectors: the whole padded array, boundary layers included"""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.size == self.n + self.n_ghost
+        check(lib().fsb_vec_box_upload_all(self.h, _dptr(a)))
+        return self
+
+    def download_all(self) -> np.ndarray:
+        out = np.empty(self.n + self.n_ghost, dtype=np.float64)
+        check(lib().fsb_vec_box_download_all(self.h, _dptr(out)))
+        return out
 
     def download(self, n: int | None = None, offset: int = 0) -> np.ndarray:
         n = self.n if n is None else n

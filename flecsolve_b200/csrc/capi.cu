@@ -15,6 +15,8 @@ using namespace fsb;
 fsb_parcsr_s * fsb_parcsr_create_impl(fsb_ctx_s *, int64_t, const int64_t *, const int64_t *, const int64_t *,
                                       const double *);
 fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s *, int, int64_t, int64_t, int64_t, double, double);
+fsb_parcsr_s * fsb_parcsr_create_box_stencil_impl(fsb_ctx_s *, int, const int64_t *, const int64_t *, const int64_t *, double,
+                                                  const double *);
 void fsb_parcsr_destroy_impl(fsb_parcsr_s *);
 void fsb_parcsr_jacobi_relax_impl(fsb_parcsr_s *, double, int64_t, fsb_vec_s *, fsb_vec_s *, fsb_vec_s *);
 
@@ -422,10 +424,43 @@ int64_t fsb_vec_local_size(fsb_vec_t v) { return v->n_owned; }
 int64_t fsb_vec_ghost_size(fsb_vec_t v) { return v->n_ghost; }
 double * fsb_vec_device_ptr(fsb_vec_t v) { return v->d; }
 
+// dofs [first, first + n) of a structured-grid vector <-> a packed buffer (colexicographic order)
+__global__ void box_copy_kernel(double * __restrict__ field, double * __restrict__ packed, long long first, long long n,
+                                long long n0, long long n1, long long E0, long long E01, long long origin, bool to_field) {
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
+		const long long i = first + k, t = i / n0, i0 = i - t * n0, i2 = t / n1, i1 = t - i2 * n1;
+		const long long at = origin + i0 + E0 * i1 + E01 * i2;
+		if (to_field)
+			field[at] = packed[k];
+		else
+			packed[k] = field[at];
+	}
+}
+
+static void box_copy(fsb_vec_t v, double * d_packed, int64_t first, int64_t n, bool to_field) {
+	if (n == 0)
+		return;
+	const fsb::box_shape & b = v->shape;
+	const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+	box_copy_kernel<<<grid, 256, 0, v->ctx->stream>>>(v->d, d_packed, first, n, b.n[0], b.n[1], b.ext[0], b.ext[0] * b.ext[1],
+	                                                 b.origin(), to_field);
+	FSB_CUDA(cudaGetLastError());
+}
+
 int fsb_vec_upload(fsb_vec_t v, const double * host, int64_t n, int64_t offset) {
 	return guarded([&] {
 		FSB_REQUIRE(v && host && n >= 0 && offset >= 0 && offset + n <= v->n_owned, "upload range");
 		flush(v->ctx);
+		if (v->box) {
+			double * tmp = nullptr;
+			FSB_CUDA(cudaMalloc(&tmp, std::max<int64_t>(n, 1) * sizeof(double)));
+			FSB_CUDA(cudaMemcpyAsync(tmp, host, n * sizeof(double), cudaMemcpyHostToDevice, v->ctx->stream));
+			box_copy(v, tmp, offset, n, true);
+			FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+			cudaFree(tmp);
+			return;
+		}
 		FSB_CUDA(cudaMemcpyAsync(v->d + offset, host, n * sizeof(double), cudaMemcpyHostToDevice, v->ctx->stream));
 		FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
 		v->halo_valid = false;
@@ -434,11 +469,68 @@ int fsb_vec_upload(fsb_vec_t v, const double * host, int64_t n, int64_t offset) 
 
 int fsb_vec_download(fsb_vec_t v, double * host, int64_t n, int64_t offset) {
 	return guarded([&] {
-		FSB_REQUIRE(v && host && n >= 0 && offset >= 0 && offset + n <= v->n_owned + v->n_ghost, "download range");
+		FSB_REQUIRE(v && host && n >= 0 && offset >= 0, "download range");
 		flush(v->ctx);
+		if (v->box) {
+			FSB_REQUIRE(offset + n <= v->n_owned, "download range");
+			double * tmp = nullptr;
+			FSB_CUDA(cudaMalloc(&tmp, std::max<int64_t>(n, 1) * sizeof(double)));
+			box_copy(v, tmp, offset, n, false);
+			FSB_CUDA(cudaMemcpyAsync(host, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
+			FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+			cudaFree(tmp);
+			v->ctx->stats[FSB_STAT_HOST_SYNCS]++;
+			return;
+		}
+		FSB_REQUIRE(offset + n <= v->n_owned + v->n_ghost, "download range");
 		FSB_CUDA(cudaMemcpyAsync(host, v->d + offset, n * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
 		FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
 		v->ctx->stats[FSB_STAT_HOST_SYNCS]++;
+	});
+}
+
+// ---- structured-grid ("narray") vectors, SURVEY 8(f) N3 ----
+
+int fsb_vec_create_box(fsb_ctx_t c, int dim, const int64_t * extents, const int64_t * lo, const int64_t * hi, fsb_vec_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(c && out && extents && lo && hi && dim >= 1 && dim <= 3, "bad arguments");
+		fsb::box_shape b;
+		for (int k = 0; k < dim; ++k) {
+			FSB_REQUIRE(extents[k] >= 1 && lo[k] >= 0 && lo[k] <= hi[k] && hi[k] <= extents[k], "box: need 0 <= lo <= hi <= extent");
+			b.ext[k] = extents[k];
+			b.lo[k] = lo[k];
+			b.n[k] = hi[k] - lo[k];
+		}
+		FSB_REQUIRE(b.storage() < (1LL << 31), "box: padded array exceeds int32 offsets");
+		auto * v = new fsb_vec_s;
+		v->ctx = c;
+		v->box = true;
+		v->shape = b;
+		v->n_owned = b.dofs();
+		v->n_ghost = b.storage() - b.dofs(); // boundary / padding entries: never touched by vector operations
+		v->id = c->next_vec_id++;
+		const size_t n = static_cast<size_t>(b.storage());
+		FSB_CUDA(cudaMalloc(&v->d, std::max<size_t>(n, 2) * sizeof(double)));
+		FSB_CUDA(cudaMemsetAsync(v->d, 0, std::max<size_t>(n, 2) * sizeof(double), c->stream));
+		*out = v;
+	});
+}
+
+// the whole padded array (boundary layers included), e.g. to place Dirichlet data
+int fsb_vec_box_upload_all(fsb_vec_t v, const double * host) {
+	return guarded([&] {
+		FSB_REQUIRE(v && v->box && host, "bad arguments");
+		flush(v->ctx);
+		FSB_CUDA(cudaMemcpyAsync(v->d, host, v->shape.storage() * sizeof(double), cudaMemcpyHostToDevice, v->ctx->stream));
+		FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+	});
+}
+int fsb_vec_box_download_all(fsb_vec_t v, double * host) {
+	return guarded([&] {
+		FSB_REQUIRE(v && v->box && host, "bad arguments");
+		flush(v->ctx);
+		FSB_CUDA(cudaMemcpyAsync(host, v->d, v->shape.storage() * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
+		FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
 	});
 }
 
@@ -446,6 +538,7 @@ static void check_same(fsb_vec_t a, fsb_vec_t b) {
 	FSB_REQUIRE(a && b, "null vector");
 	FSB_REQUIRE(a->ctx == b->ctx, "vectors belong to different contexts");
 	FSB_REQUIRE(a->n_owned == b->n_owned, "vector sizes differ");
+	FSB_REQUIRE(a->box == b->box && (!a->box || a->shape == b->shape), "vectors live on different index sets");
 }
 
 static void check_coef(fsb_ctx_s * c, const fsb_coef & k) {
@@ -546,6 +639,11 @@ int fsb_vec_set_random(fsb_vec_t z, unsigned seed) {
 		std::vector<double> h(static_cast<size_t>(z->n_owned));
 		for (auto & v : h)
 			v = dis(gen);
+		if (z->box) { // dofs in colexicographic order, like the reference's loop over dofs()
+			if (fsb_vec_upload(z, h.data(), static_cast<int64_t>(h.size()), 0) != FSB_OK)
+				throw fsb::error(FSB_ERR_CUDA, fsb_last_error());
+			return;
+		}
 		flush(z->ctx);
 		if (!h.empty())
 			FSB_CUDA(cudaMemcpyAsync(z->d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, z->ctx->stream));
@@ -559,7 +657,11 @@ int fsb_vec_dump(fsb_vec_t x, const char * prefix) {
 		FSB_REQUIRE(x && prefix, "bad arguments");
 		std::vector<double> h(static_cast<size_t>(x->n_owned));
 		flush(x->ctx);
-		if (!h.empty())
+		if (x->box) {
+			if (fsb_vec_download(x, h.data(), static_cast<int64_t>(h.size()), 0) != FSB_OK)
+				throw fsb::error(FSB_ERR_CUDA, fsb_last_error());
+		}
+		else if (!h.empty())
 			FSB_CUDA(cudaMemcpyAsync(h.data(), x->d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, x->ctx->stream));
 		FSB_CUDA(cudaStreamSynchronize(x->ctx->stream));
 		std::ofstream f(std::string(prefix) + "-" + std::to_string(x->ctx->rank));
@@ -762,6 +864,14 @@ int fsb_parcsr_create_stencil(fsb_ctx_t c, int kind, int64_t nx, int64_t ny, int
 	});
 }
 
+int fsb_parcsr_create_box_stencil(fsb_ctx_t c, int dim, const int64_t * extents, const int64_t * lo, const int64_t * hi,
+                                  double center, const double * off, fsb_parcsr_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(c && extents && lo && hi && off && out, "bad arguments");
+		*out = fsb_parcsr_create_box_stencil_impl(c, dim, extents, lo, hi, center, off);
+	});
+}
+
 int fsb_parcsr_destroy(fsb_parcsr_t A) {
 	return guarded([&] {
 		if (A)
@@ -829,6 +939,11 @@ int fsb_parcsr_spmv(fsb_parcsr_t A, fsb_vec_t x, fsb_vec_t y) {
 		FSB_REQUIRE(x != y && x->d != y->d, "spmv: x and y must be different vectors");
 		FSB_REQUIRE(x->ctx == A->ctx && y->ctx == A->ctx, "spmv: context mismatch");
 		FSB_REQUIRE(x->n_owned == A->n_local && y->n_owned == A->n_local, "spmv: vector length != local rows");
+		if (A->box)
+			FSB_REQUIRE(x->box && y->box && x->shape == A->shape && y->shape == A->shape,
+			            "spmv: a structured-grid operator needs vectors on its own box");
+		else
+			FSB_REQUIRE(!x->box && !y->box, "spmv: structured-grid vectors need a structured-grid operator");
 		FSB_REQUIRE(x->n_ghost >= A->n_ghost, "spmv: x has too few ghost entries for this matrix");
 		pending p{};
 		p.kind = pending::SPMV;
@@ -844,6 +959,7 @@ int fsb_parcsr_spmv(fsb_parcsr_t A, fsb_vec_t x, fsb_vec_t y) {
 int fsb_parcsr_extract_dinv(fsb_parcsr_t A, fsb_vec_t d) {
 	return guarded([&] {
 		FSB_REQUIRE(A && d && d->n_owned == A->n_local, "extract_dinv: bad arguments");
+		FSB_REQUIRE(!A->box, "extract_dinv: not available for structured-grid operators");
 		flush(A->ctx);
 		extract_dinv(A, d->d);
 		d->halo_valid = false;
@@ -853,6 +969,7 @@ int fsb_parcsr_extract_dinv(fsb_parcsr_t A, fsb_vec_t d) {
 int fsb_parcsr_jacobi_relax(fsb_parcsr_t A, double omega, int64_t nrelax, fsb_vec_t b, fsb_vec_t x, fsb_vec_t tmp) {
 	return guarded([&] {
 		FSB_REQUIRE(A && b && x && tmp, "null argument");
+		FSB_REQUIRE(!A->box, "jacobi_relax: not available for structured-grid operators");
 		fsb_parcsr_jacobi_relax_impl(A, omega, nrelax, b, x, tmp);
 	});
 }
@@ -860,6 +977,7 @@ int fsb_parcsr_jacobi_relax(fsb_parcsr_t A, double omega, int64_t nrelax, fsb_ve
 int fsb_parcsr_halo_exchange(fsb_parcsr_t A, fsb_vec_t x) {
 	return guarded([&] {
 		FSB_REQUIRE(A && x, "null argument");
+		FSB_REQUIRE(!A->box && !x->box, "halo_exchange: structured-grid operators are single-rank");
 		halo_exchange(A, x);
 	});
 }

@@ -47,6 +47,11 @@ struct ew_args {
 	const double * sdev;
 	signed char snum[MAXSC], sden[MAXSC];
 	const int * halt; // non-null while a device-scalar solver is running: skip all element work once set
+	// structured-grid vectors (fsb_vec_create_box): element i of the n dofs is the interior point
+	// (i % bn0, (i / bn0) % bn1, i / (bn0 bn1)) of a padded array, stored at boff + i0 + bE0 i1 + bE01 i2.
+	// bn0 == 0: plain contiguous vectors.  Box layouts always run through ew_interp_kernel (one kernel for
+	// every program), so the compiled instantiations keep their register budgets.
+	long long bn0, bn1, bE0, bE01, boff;
 	long long n;
 	double * partials; // [MAXR][MAX_RED_BLOCKS]
 	unsigned * counter;
@@ -358,8 +363,23 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_interp_kernel(const __grid_consta
 		sc[k] = a.snum[k] < 0 ? a.s[k] : __dmul_rn(a.s[k], __ddiv_rn(a.sdev[a.snum[k]], a.sdev[a.sden[k]]));
 	const bool halted = a.halt && *a.halt;
 
-	const long long n2 = halted ? 0 : a.n >> 1;
 	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	if (a.bn0 > 0 && !halted) { // structured-grid vectors (dofs of an narray mesh, reference examples/poisson/mesh.hh:157-161
+		// + index_util.hh:33-71): scalar 8-byte accesses, consecutive threads on consecutive x
+		for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+			const long long t = i / a.bn0, i0 = i - t * a.bn0, i2 = t / a.bn1, i1 = t - i2 * a.bn1;
+			const long long at = a.boff + i0 + a.bE0 * i1 + a.bE01 * i2;
+			double v[MAXV];
+			for (int k = 0; k < P.nv; ++k)
+				if (P.load_mask & (1u << k))
+					v[k] = a.v[k][at];
+			interp_exec(P, sc, v, acc);
+			for (int k = 0; k < P.nv; ++k)
+				if (P.store_mask & (1u << k))
+					a.v[k][at] = v[k];
+		}
+	}
+	const long long n2 = (halted || a.bn0 > 0) ? 0 : a.n >> 1;
 	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2; i += stride) {
 		double lo[MAXV], hi[MAXV];
 		for (int k = 0; k < P.nv; ++k)
@@ -374,7 +394,7 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_interp_kernel(const __grid_consta
 			if (P.store_mask & (1u << k))
 				reinterpret_cast<double2 *>(a.v[k])[i] = make_double2(lo[k], hi[k]);
 	}
-	if (!halted && (a.n & 1) && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+	if (!halted && a.bn0 == 0 && (a.n & 1) && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
 		const long long i = a.n - 1;
 		double t[MAXV];
 		for (int k = 0; k < P.nv; ++k)

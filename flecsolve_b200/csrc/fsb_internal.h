@@ -73,6 +73,20 @@ struct pending {
 	double halt_thr = 0;
 };
 
+// interior sub-box of a padded array (structured-grid vectors); colexicographic dof order, x fastest
+struct box_shape {
+	int64_t ext[3] = {1, 1, 1}, lo[3] = {0, 0, 0}, n[3] = {1, 1, 1};
+	bool operator==(const box_shape & o) const {
+		for (int k = 0; k < 3; ++k)
+			if (ext[k] != o.ext[k] || lo[k] != o.lo[k] || n[k] != o.n[k])
+				return false;
+		return true;
+	}
+	int64_t dofs() const { return n[0] * n[1] * n[2]; }
+	int64_t storage() const { return ext[0] * ext[1] * ext[2]; }
+	int64_t origin() const { return lo[0] + ext[0] * (lo[1] + ext[1] * lo[2]); }
+};
+
 struct red_slot {
 	double * d_value; // device result (post intra-rank reduction)
 	volatile double * h_value; // pinned mapped host mirror
@@ -144,6 +158,8 @@ struct fsb_vec_s {
 	bool halo_valid = false; // ghost entries hold the owners' current values ...
 	const void * halo_for = nullptr; // ... in the ghost numbering of this matrix
 	uint64_t id = 0;
+	bool box = false; // structured-grid vector: n_owned dofs inside `shape`, n_owned + n_ghost == storage
+	fsb::box_shape shape;
 };
 
 namespace fsb {
@@ -195,6 +211,10 @@ struct fsb_parcsr_s {
 	std::vector<void *> halo_opened; // peers' blocks mapped here
 	long long halo_epoch = 0;
 	int halo_push_ctas = 1, halo_unpack_ctas = 1;
+	// structured-grid operator: rows = dofs of `shape`, columns and row_ids are storage offsets into the
+	// padded array, so boundary layers are read like any other entry (one rank only)
+	bool box = false;
+	fsb::box_shape shape;
 };
 
 namespace fsb {

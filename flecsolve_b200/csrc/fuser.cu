@@ -220,6 +220,12 @@ static registry_t & registry() {
 static int64_t length_of(const pending & p) {
 	return p.kind == pending::RED ? p.x->n_owned : p.z->n_owned;
 }
+// statements fuse only over the same index set: equal length and, for structured-grid vectors, equal box
+static const fsb_vec_s * layout_of(const pending & p) { return p.kind == pending::RED ? p.x : p.z; }
+static bool same_layout(const pending & a, const pending & b) {
+	const fsb_vec_s *u = layout_of(a), *v = layout_of(b);
+	return u->n_owned == v->n_owned && u->box == v->box && (!u->box || u->shape == v->shape);
+}
 
 static std::string describe(const pending * q, int n) {
 	static const char * names[] = {"set", "scale", "lin2", "mul", "div", "recip", "abs", "adds"};
@@ -289,12 +295,21 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 	if (it == table.end() && !allow_generic)
 		return false;
 	g.launch = it == table.end() ? nullptr : it->second;
+	if (layout_of(q[0])->box)
+		g.launch = nullptr; // structured-grid layouts are handled by the generic kernel only
 	g.prog = cr.p;
 	g.nr = cr.p.nr;
 	ew_args & a = g.args;
 	for (int k = 0; k < cr.p.nv; ++k)
 		a.v[k] = vecs[cr.id_of_slot[k]]->d;
 	a.n = length_of(q[0]);
+	if (const fsb_vec_s * lay = layout_of(q[0]); lay->box) {
+		a.bn0 = lay->shape.n[0];
+		a.bn1 = lay->shape.n[1];
+		a.bE0 = lay->shape.ext[0];
+		a.bE01 = lay->shape.ext[0] * lay->shape.ext[1];
+		a.boff = lay->shape.origin();
+	}
 	a.partials = c->d_partials;
 	a.counter = c->d_counter;
 	a.partial_stride = MAX_RED_BLOCKS;
@@ -437,7 +452,7 @@ void flush(fsb_ctx_s * c) {
 					return true;
 			return false;
 		};
-		while (j < total && j - i < cap && q[j].kind != pending::SPMV && length_of(q[j]) == n && !needs_result_of_run(j))
+		while (j < total && j - i < cap && q[j].kind != pending::SPMV && same_layout(q[i], q[j]) && !needs_result_of_run(j))
 			++j;
 		// the whole run as one launch: a registered instantiation if there is one, else the generic
 		// program kernel; a run that exceeds the slot limits is cut at the longest prefix that fits
@@ -453,7 +468,7 @@ void flush(fsb_ctx_s * c) {
 		if (c->trace)
 			fprintf(stderr, "[fsb] launch%s: %s\n", g.launch ? "" : " (generic)", describe(&q[i], len).c_str());
 		if (n > 0 || (g.nr > 0 && c->nranks > 1)) {
-			long long packets = (n + 1) / 2;
+			long long packets = layout_of(q[i])->box ? n : (n + 1) / 2; // box layout: one element per thread and trip
 			long long want = (packets + EW_BLOCK - 1) / EW_BLOCK;
 			const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, MAX_RED_BLOCKS)));
 			if (g.launch)

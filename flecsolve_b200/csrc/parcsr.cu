@@ -226,6 +226,11 @@ void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x) {
 void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot) {
 	fsb_parcsr_s * A = sp.A;
 	fsb_vec_s *x = sp.x, *y = sp.y;
+	if (A->box) { // columns and row ids are storage offsets of the padded arrays: one launch, no ghost exchange
+		const double * u = dot ? (dot->x == y ? dot->y : dot->x)->d : nullptr;
+		launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream, dot);
+		return;
+	}
 	const bool multi = c->nranks > 1 && !A->nbrs.empty();
 	bool waited = true, unpack = false;
 	static const bool debug_skip_halo = std::getenv("FSB_DEBUG_SKIP_HALO") != nullptr; // timing experiments only
@@ -618,6 +623,59 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 	FSB_CUDA(cudaStreamSynchronize(c->stream));
 	cudaFree(cnt_d);
 	cudaFree(cnt_o);
+	return A;
+}
+
+// Structured-grid operator: the (2 dim + 1)-point stencil  center * u(i) + sum_axis off[axis] *
+// (u(i - e_axis) + u(i + e_axis))  over the interior sub-box of a padded array, assembled as CSR whose column
+// indices (and row_ids) are storage offsets into the padded array.  Rows follow the dof order (x fastest),
+// entries ascend in storage offset, and every neighbour is stored -- boundary layers hold the Dirichlet data and
+// are read like any other entry, as the reference's matrix-free stencil does on its narray mesh
+// (examples/poisson/mesh.hh:92-134, poisson.cc:44-82).  One rank only.
+fsb_parcsr_s * fsb_parcsr_create_box_stencil_impl(fsb_ctx_s * c, int dim, const int64_t * ext, const int64_t * lo,
+                                                  const int64_t * hi, double center, const double * off) {
+	flush(c);
+	FSB_REQUIRE(c->nranks == 1, "structured-grid operators are single-rank in this version");
+	FSB_REQUIRE(dim >= 1 && dim <= 3, "box stencil: dim must be 1, 2 or 3");
+	box_shape b;
+	for (int k = 0; k < dim; ++k) {
+		FSB_REQUIRE(lo[k] >= 1 && hi[k] <= ext[k] - 1 && lo[k] <= hi[k], "box stencil: the interior needs one boundary layer per side");
+		b.ext[k] = ext[k];
+		b.lo[k] = lo[k];
+		b.n[k] = hi[k] - lo[k];
+	}
+	FSB_REQUIRE(b.storage() < (1LL << 31), "box stencil: padded array exceeds int32 offsets");
+	const int64_t n = b.dofs();
+	const int64_t stride[3] = {1, b.ext[0], b.ext[0] * b.ext[1]};
+	const int width = 2 * dim + 1;
+	std::vector<int64_t> rp(static_cast<size_t>(n) + 1);
+	std::vector<int32_t> col(static_cast<size_t>(n) * width), rows(static_cast<size_t>(n));
+	std::vector<double> val(static_cast<size_t>(n) * width);
+	for (int64_t i = 0; i < n; ++i) {
+		const int64_t t = i / b.n[0], i0 = i - t * b.n[0], i2 = t / b.n[1], i1 = t - i2 * b.n[1];
+		const int64_t at = b.origin() + i0 + stride[1] * i1 + stride[2] * i2;
+		size_t k = static_cast<size_t>(i) * width;
+		rp[i] = static_cast<int64_t>(k);
+		rows[i] = static_cast<int32_t>(at);
+		for (int a = dim - 1; a >= 0; --a) {
+			col[k] = static_cast<int32_t>(at - stride[a]);
+			val[k++] = off[a];
+		}
+		col[k] = static_cast<int32_t>(at);
+		val[k++] = center;
+		for (int a = 0; a < dim; ++a) {
+			col[k] = static_cast<int32_t>(at + stride[a]);
+			val[k++] = off[a];
+		}
+	}
+	rp[n] = n * width;
+	auto * A = new fsb_parcsr_s;
+	A->ctx = c;
+	A->box = true;
+	A->shape = b;
+	A->n_global = A->n_local = n;
+	A->row_part = {0, n};
+	upload_block(c, A->diag, rp, col, val, &rows);
 	return A;
 }
 

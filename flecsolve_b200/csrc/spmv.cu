@@ -456,6 +456,16 @@ static int launch_variant(const spmv_args & a, const spmv_config & k, cudaStream
 
 template<class OffT, int NSTAGE, int GATHER>
 static int launch_flags(const spmv_args & a, const spmv_config & k, bool acc, bool dot, bool rowlist, cudaStream_t s) {
+	if (rowlist && !acc) { // structured-grid operator: rows scatter to storage offsets, plain assignment
+		if constexpr (GATHER == 8 && sizeof(OffT) == 4) {
+			if (dot)
+				return launch_variant<OffT, NSTAGE, false, true, true, GATHER>(a, k, s);
+			else
+				return launch_variant<OffT, NSTAGE, false, false, true, GATHER>(a, k, s);
+		}
+		else
+			throw error(FSB_ERR_STATE, "spmv: row-list assignment is built for int32 offsets, gather 8 only");
+	}
 	if (rowlist) { // off-process block: always accumulates
 		if (dot)
 			return launch_variant<OffT, NSTAGE, true, true, true, GATHER>(a, k, s);

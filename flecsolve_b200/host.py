@@ -114,6 +114,7 @@ def lib() -> C.CDLL:
         L.fsbh_mtx_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
         L.fsbh_config_dump.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
         L.fsbh_solve_config.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, _pd, _pd, C.POINTER(Info), _pd, C.c_int]
+        L.fsbh_poisson_narray.argtypes = [C.c_void_p, C.c_int, C.POINTER(Options), C.c_uint, _pd, C.POINTER(Info), _pd, C.c_int]
         _lib = L
     return _lib
 
@@ -220,6 +221,16 @@ def config_dump(path: str, kind: str, prefix: str) -> dict:
     buf = C.create_string_buffer(4096)
     _check(lib().fsbh_config_dump(path.encode(), CONFIG_KINDS[kind], prefix.encode(), buf, len(buf)))
     return json.loads(buf.value.decode())
+
+
+def poisson_narray(ctx: F.Context, m: int, seed: int = 7, history_cap=0, **kw):
+    """examples/poisson on an narray mesh (fields = padded 2-D arrays, vectors act on the interior)"""
+    opts = make_options(**kw)
+    info = Info()
+    u = np.zeros(m * m)
+    hist = np.zeros(max(history_cap, 1))
+    _check(lib().fsbh_poisson_narray(ctx.h, m, C.byref(opts), seed, _d(u), C.byref(info), _d(hist), history_cap))
+    return u, info, hist[:min(info.callbacks, history_cap)]
 
 
 def solve_multi2(ctx: F.Context, A0: F.ParCSR, A1: F.ParCSR, b, x0, history_cap=0, **kw):

@@ -24,6 +24,7 @@
 #include "flecsolve/solvers/cg_device.hh"
 #include "flecsolve/solvers/factory.hh"
 #include "flecsolve/matrices/io/matrix_market.hh"
+#include "flecsolve/topo/narray.hh"
 #include "flecsolve/solvers/gmres.hh"
 #include "flecsolve/solvers/mg/jacobi.hh"
 #include "flecsolve/time-integrators/bdf.hh"
@@ -821,6 +822,50 @@ int fsbh_solve_config(void * sv, const char * fname, const char * prefix, int pr
 			si = slv(S.b, S.x);
 		}
 		device::check(fsb_vec_download(S.x.data.handle(), x_host, n, 0));
+		fill(info, si, rec.count);
+	});
+}
+
+// ---- structured-grid fields ----------------------------------------------------
+
+// examples/poisson on its own data layout: u and f are fields of a 2-D narray mesh with one boundary layer,
+// A is the 5-point operator {4, -1} over the padded arrays (homogeneous Dirichlet data in the layer),
+// f = 8 pi^2 sin(2 pi x) sin(2 pi y) h^2, x0 = mt19937(seed) drawn in dof order, unpreconditioned CG
+// (poisson.cc:27-84, poisson.cfg).  Returns u (m*m dofs, x fastest) and the usual solve_info.
+int fsbh_poisson_narray(fsb_ctx_t ctx_h, int m, const fsbh_options * o, unsigned seed, double * u_host, fsbh_info * info,
+                        double * history, int history_cap) {
+	return guarded([&] {
+		using mesh_t = topo::narray<double, 2>;
+		static const mesh_t::vec_def<mesh_t::vertices> ud, fd;
+		device::context ctx(ctx_h);
+		mesh_t::topology mesh(ctx, {m, m});
+		mesh.set_geometry({{{0.0, 1.0}, {0.0, 1.0}}});
+		auto u = vec::make(ud(mesh));
+		auto f = vec::make(fd(mesh));
+		const double h = mesh.delta[0], pi = 3.14159265358979323846;
+		std::vector<double> rhs(static_cast<std::size_t>(m) * m);
+		for (int j = 0; j < m; ++j)
+			for (int i = 0; i < m; ++i)
+				rhs[static_cast<std::size_t>(j) * m + i] =
+					8 * pi * pi * std::sin(2 * pi * (i + 1) * h) * std::sin(2 * pi * (j + 1) * mesh.delta[1]) * h * h;
+		device::check(fsb_vec_upload(f.data.handle(), rhs.data(), static_cast<std::int64_t>(rhs.size()), 0));
+		u.set_random(seed);
+		op::core<mat::box_stencil<double, 2>> A(mesh, 4.0, std::array<double, 2>{-1.0, -1.0});
+		recorder rec{ctx_h, history, history_cap, -1, -1};
+		solve_info si;
+		if (o->solver == 4) {
+			cg_device::settings st{{o->maxiter, o->rtol, o->atol, o->use_zero_guess != 0}, o->lag};
+			si = cg_device::solver(st, cg_device::make_work(u))(op::ref(A), op::I, std::ref(rec))(f, u);
+		}
+		else if (o->solver == 2) {
+			bicgstab::settings st{{o->maxiter, o->rtol, o->atol, o->use_zero_guess != 0}};
+			si = bicgstab::solver(st, bicgstab::make_work(u))(op::ref(A), op::I, std::ref(rec))(f, u);
+		}
+		else {
+			si = cg::solver(cg::settings{o->maxiter, o->rtol, o->atol, o->use_zero_guess != 0}, cg::make_work(u))(
+				op::ref(A), op::I, std::ref(rec))(f, u);
+		}
+		device::check(fsb_vec_download(u.data.handle(), u_host, static_cast<std::int64_t>(rhs.size()), 0));
 		fill(info, si, rec.count);
 	});
 }

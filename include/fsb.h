@@ -206,6 +206,27 @@ int fsb_vec_dot_opts(fsb_vec_t x, fsb_vec_t y, const fsb_red_opts * opts, fsb_to
 int fsb_ctx_halt_arm(fsb_ctx_t ctx);
 int fsb_ctx_halt_disarm(fsb_ctx_t ctx, int * was_halted);
 
+/* ---- structured-grid ("narray") vectors and operators ----
+ * The reference's example applications keep their fields on a FleCSI narray mesh: a padded N-d
+ * array per colour whose vector operations run over dofs() = the interior sub-box, in
+ * colexicographic order, x fastest (examples/poisson/mesh.hh:157-161, index_util.hh:33-71);
+ * the layers around it hold boundary data that operators read but vector operations never touch.
+ * fsb_vec_create_box makes such a field: extents[dim] of the padded array, dofs = [lo, hi) per axis.
+ * Every element-wise call and reduction above works on these handles (operands of one call must
+ * share the box); fsb_vec_local_size is the number of dofs; upload/download move dofs in dof order;
+ * the *_all calls move the whole padded array (boundary data).
+ * fsb_parcsr_create_box_stencil assembles the (2 dim + 1)-point operator
+ *     (A u)(i) = center u(i) + sum_axis off[axis] (u(i - e_axis) + u(i + e_axis))
+ * over the dofs of such a box as CSR whose column indices are storage offsets of the padded array,
+ * so boundary layers take part exactly as in the reference's stencil operators
+ * (examples/poisson/poisson.cc:44-82); fsb_parcsr_spmv runs it through the same SpMV kernel
+ * (fused dot included).  One rank only in this version.                                            */
+int fsb_vec_create_box(fsb_ctx_t ctx, int dim, const int64_t * extents, const int64_t * lo, const int64_t * hi, fsb_vec_t * out);
+int fsb_vec_box_upload_all(fsb_vec_t v, const double * host);
+int fsb_vec_box_download_all(fsb_vec_t v, double * host);
+int fsb_parcsr_create_box_stencil(fsb_ctx_t ctx, int dim, const int64_t * extents, const int64_t * lo, const int64_t * hi,
+                                  double center, const double * off, fsb_parcsr_t * out);
+
 /* ---- parallel CSR matrix ------------------------------------------------
  * Device image of mat::parcsr (matrices/parcsr.hh:101-177) on the topology
  * topo::csr (topo/csr.hh): per rank a `diag' CSR over owned columns and an
