@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-1 final single-GPU evidence: tests, bench (ours + reference arm), launch list, full ncu captures, configs
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 python -m pytest tests -q -m gpu 2>&1 | tail -15 > $O/pytest_gpu.log
 python bench.py --steps 200 --warmup 10 > $O/bench_n1.json 2> $O/bench_n1.err

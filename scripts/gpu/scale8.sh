@@ -1,6 +1,6 @@
 #!/bin/bash
 # strong-scaling sweep on one 8-GPU box
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 summ() { grep '^{' | python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('$1', 'N', d['n_gpus'], 'it/s', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'spmv', round(r['avg_launch_ms'],4), 'diag', round(r['diag_block_avg_ms'] or 0,4), 'offd', round(r['offd_block_avg_ms'] or 0,4), 'iterfrac', round(r['iteration']['frac'],3), 'e2e', round(d['e2e']['value'],1), 'e2e_iters', d['e2e']['iterations'])"; }
 python -m pytest tests/test_multi_gpu.py -q -m gpu 2>&1 | tail -3
 for wl in poisson7_256 poisson27_512; do

@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: scale_final.sh N [N...]: bench both workloads at the given rank counts on this box
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 run() { # N workload
   if [ "$1" = 1 ]; then

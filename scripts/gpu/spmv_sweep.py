@@ -1,6 +1,6 @@
 """Scratch: one SpMV configuration (env-selected) timed; prints GB/s."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from flecsolve_b200 import _lib as F
 kind = int(sys.argv[1]); nn = int(sys.argv[2]); nz = int(sys.argv[3]) if len(sys.argv) > 3 else nn

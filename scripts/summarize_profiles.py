@@ -1,5 +1,5 @@
 """Turns the raw captures a GPU run left in gpurun_out/ into the tracked summaries under profiles/.
-Usage (in the build container, after scratch/final_n1.sh ran under gpurun): python scripts/summarize_profiles.py"""
+Usage (in the build container, after scripts/gpu/final_n1.sh ran under gpurun): python scripts/summarize_profiles.py"""
 import csv
 import json
 import os
