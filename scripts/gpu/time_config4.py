@@ -1,4 +1,5 @@
-import sys, time, numpy as np
+import os, sys, time
+import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from flecsolve_b200 import _lib as F, host as H
 ctx = F.Context(0)
