@@ -1,0 +1,41 @@
+"""The example applications (examples/): flecsolve-shaped user code over the header layer.
+Building them needs no GPU and is part of the CPU suite; running them is done when the whole suite runs on
+a GPU box (not selected by `-m gpu`: first exercised on hardware in round 2)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from flecsolve_b200 import _lib as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "examples", "_build")
+
+
+def _build():
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), f"CXX={cxx}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_examples_build():
+    _build()
+    assert os.path.exists(os.path.join(OUT, "poisson")) and os.path.exists(os.path.join(OUT, "implicit"))
+
+
+def test_examples_run():
+    if F.device_count() == 0:
+        pytest.skip("no CUDA device")
+    _build()
+    r = subprocess.run([os.path.join(OUT, "poisson"), "64", os.path.join(ROOT, "examples", "poisson", "poisson.cfg")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"converged after (\d+) iterations.*max error.*= ([0-9.e+-]+)", r.stdout)
+    assert m and 100 < int(m.group(1)) < 400 and float(m.group(2)) < 1.2e-3, r.stdout
+    r = subprocess.run([os.path.join(OUT, "implicit"), "24", os.path.join(ROOT, "examples", "heat_equation", "implicit.cfg")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"(\d+) steps \((\d+) attempts, (\d+) rejected\), max u = ([0-9.]+), heat ([0-9.]+) -> ([0-9.]+)", r.stdout)
+    assert m, r.stdout
+    assert int(m.group(1)) >= 10 and 0.0 < float(m.group(4)) <= 50.0 and float(m.group(6)) <= float(m.group(5)) * (1 + 1e-9)
