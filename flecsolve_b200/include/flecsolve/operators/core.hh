@@ -58,47 +58,58 @@ protected:
 	params_t params;
 };
 
-template<class P>
-struct core : P {
-	static constexpr auto input_var = P::input_var;
-	static constexpr auto output_var = P::output_var;
-	using params_t = typename P::params_t;
-	using policy_type = P;
+// The public face of an operator: everything callers use (solvers, integrators, user code) is here, and all
+// of it funnels into the policy's apply(x, y) after both vectors have been narrowed to the variables the
+// operator declares (a plain vector is its own subset; a vec::multi hands out the matching components).
+template<class Policy>
+struct core : Policy {
+	using policy_type = Policy;
+	using params_t = typename Policy::params_t;
+	static constexpr auto input_var = Policy::input_var;
+	static constexpr auto output_var = Policy::output_var;
 
-	template<class Head, class... Tail,
-	         std::enable_if_t<!std::is_same_v<std::decay_t<Head>, core<P>>, bool> = true,
-	         std::enable_if_t<std::is_constructible_v<P, Head, Tail...>, bool> = true>
-	core(Head && h, Tail &&... t) : P{std::forward<Head>(h), std::forward<Tail>(t)...} {}
+private:
+	template<class First, class... Rest>
+	static constexpr bool builds_policy_from =
+		!std::is_same_v<std::decay_t<First>, core> && std::is_constructible_v<Policy, First, Rest...>;
+	template<class V>
+	using if_vector = std::enable_if_t<is_vector_v<V>, bool>;
 
-	template<class Head, class... Tail,
-	         std::enable_if_t<std::is_constructible_v<P, std::initializer_list<Head>, Tail...>, bool> = true>
-	core(std::initializer_list<Head> h, Tail &&... t) : P{h, std::forward<Tail>(t)...} {}
+public:
+	// whatever constructs the policy constructs the operator (copying an operator is left to the compiler)
+	template<class First, class... Rest, std::enable_if_t<builds_policy_from<First, Rest...>, bool> = true>
+	core(First && first, Rest &&... rest) : Policy{std::forward<First>(first), std::forward<Rest>(rest)...} {}
 
-	template<class D, class R, std::enable_if_t<is_vector_v<D> && is_vector_v<R>, bool> = true>
-	decltype(auto) apply(const D & x, R & y) const {
-		decltype(auto) ys = y.subset(output_var);
-		decltype(auto) xs = x.subset(input_var);
-		return P::apply(xs, ys);
+	template<class Elem, class... Rest,
+	         std::enable_if_t<std::is_constructible_v<Policy, std::initializer_list<Elem>, Rest...>, bool> = true>
+	core(std::initializer_list<Elem> list, Rest &&... rest) : Policy{list, std::forward<Rest>(rest)...} {}
+
+	// y = Op(x)
+	template<class X, class Y, if_vector<X> = true, if_vector<Y> = true>
+	decltype(auto) apply(const X & x, Y & y) const {
+		decltype(auto) out = y.subset(output_var);
+		decltype(auto) in = x.subset(input_var);
+		return Policy::apply(in, out);
+	}
+	template<class X, class Y, if_vector<X> = true, if_vector<Y> = true>
+	decltype(auto) operator()(const X & x, Y & y) const {
+		return this->apply(x, y);
 	}
 
-	template<class D, class R, std::enable_if_t<is_vector_v<D> && is_vector_v<R>, bool> = true>
-	decltype(auto) operator()(const D & x, R & y) const {
-		return apply(x, y);
-	}
-
-	// r = b - A x
-	template<class B, class X, class R, std::enable_if_t<is_vector_v<B> && is_vector_v<X> && is_vector_v<R>, bool> = true>
+	// r = b - Op(x): Op(x) lands in r, then r is subtracted from b in place (the aliased subtract of
+	// the reference, operators/core.hh:133-142, so the device sees one fused statement after the SpMV)
+	template<class B, class X, class R, if_vector<B> = true, if_vector<X> = true, if_vector<R> = true>
 	void residual(const B & b, const X & x, R & r) const {
-		apply(x, r);
-		decltype(auto) bs = b.subset(output_var);
-		decltype(auto) rs = r.subset(output_var);
-		rs.subtract(bs, rs);
+		this->apply(x, r);
+		decltype(auto) rhs = b.subset(output_var);
+		decltype(auto) res = r.subset(output_var);
+		res.subtract(rhs, res);
 	}
 };
 
 template<class P>
-auto make(P && p) {
-	return core<std::decay_t<P>>(std::forward<P>(p));
+auto make(P && policy) {
+	return core<std::decay_t<P>>(std::forward<P>(policy));
 }
 template<class P, class... Args>
 auto make_shared1(Args &&... args) {

@@ -19,6 +19,9 @@
 
 namespace flecsolve::op {
 
+// The iteration is written as a prologue plus one `sweep` per iteration that reports whether the solve is
+// over; the order of vector operations and host reads inside a sweep is the reference's (it decides both the
+// rounding and which statements the queue can fuse).
 template<class Params>
 struct bicgstab : base<Params, typename Params::input_var_t, typename Params::output_var_t> {
 	using base_t = base<Params, typename Params::input_var_t, typename Params::output_var_t>;
@@ -30,122 +33,126 @@ struct bicgstab : base<Params, typename Params::input_var_t, typename Params::ou
 	const auto & get_operator() const { return params.A(); }
 
 	template<class DomainVec, class RangeVec>
-	solve_info apply(const RangeVec & b, DomainVec & x) const {
+	solve_info apply(const RangeVec & rhs, DomainVec & sol) const {
 		using stop = solve_info::stop_reason;
-		solve_info info;
 		const auto & A = params.A();
-		const auto & P = params.P();
-		auto & diagnostic = params.ops.diagnostic;
-		const auto & settings = params.settings;
-		auto & [res, r_tilde, p, v, p_hat, s, s_hat, t] = params.work;
+		const auto & M = params.P();
+		const auto & cfg = params.settings;
+		auto & monitor = params.ops.diagnostic;
+		// work vectors, in the reference's order: residual, shadow residual, direction, A*direction,
+		// preconditioned direction, half-step residual, its preconditioned copy, A*that
+		// (named references rather than a structured binding: the sweep lambda below captures them)
+		auto & w = params.work;
+		auto &resid = w[0], &shadow = w[1], &dir = w[2], &a_dir = w[3], &dir_pc = w[4], &half = w[5], &half_pc = w[6],
+		     &a_half = w[7];
 
-		real b_norm = b.l2norm().get();
-		if (b_norm == 0.)
-			b_norm = 1.;
-		const real terminate_tol = settings.rtol * b_norm;
-		info.rhs_norm = b_norm;
+		solve_info out;
+		real rhs_norm = rhs.l2norm().get();
+		if (rhs_norm == 0.)
+			rhs_norm = 1.;
+		out.rhs_norm = rhs_norm;
+		const real goal = cfg.rtol * rhs_norm; // float rtol times |b|, as everywhere in flecsolve
 
-		if (settings.use_zero_guess) {
-			info.sol_norm_initial = 0;
-			res.copy(b);
-			x.set_scalar(0.);
+		if (!cfg.use_zero_guess) {
+			out.sol_norm_initial = sol.l2norm().get();
+			A.residual(rhs, sol, resid);
 		}
 		else {
-			info.sol_norm_initial = x.l2norm().get();
-			A.residual(b, x, res);
+			out.sol_norm_initial = 0;
+			resid.copy(rhs);
+			sol.set_scalar(0.);
 		}
 
-		real res_norm = res.l2norm().get();
-		real r_tilde_norm = res_norm;
-		info.res_norm_initial = res_norm;
-		if (res_norm < terminate_tol) {
-			info.status = stop::converged_rtol;
-			info.res_norm_final = res_norm;
-			return info;
+		real resid_norm = resid.l2norm().get();
+		out.res_norm_initial = resid_norm;
+		if (resid_norm < goal) {
+			out.res_norm_final = resid_norm;
+			out.status = stop::converged_rtol;
+			return out;
 		}
 
-		real alpha = 1.0, beta = 0.0, omega = 1.0;
-		real rho_old = 2.0, rho_new = 1.0; // the reference starts from std::vector<real> rho{2, 1.0}
-		r_tilde.copy(res); // shadow residual: the initial residual
-		p.zero();
-		v.zero();
+		// scalars of the recurrence; rho starts from the pair {2, 1} like the reference's vector
+		struct {
+			real alpha = 1.0, beta = 0.0, omega = 1.0, rho_prev = 2.0, rho = 1.0;
+		} k;
+		real shadow_norm = resid_norm;
+		shadow.copy(resid);
+		dir.zero();
+		a_dir.zero();
 
-		for (int iter = 0; iter < settings.maxiter; iter++) {
-			rho_new = r_tilde.dot(res).get();
+		auto finish = [&out](int iterations, stop why) {
+			out.iters = iterations;
+			out.status = why;
+			return true;
+		};
 
-			const real angle = std::sqrt(std::fabs(rho_new));
-			if (angle < std::numeric_limits<real>::epsilon() * r_tilde_norm) {
-				// r~ has become orthogonal to the residual: restart from the true residual
-				A.residual(b, x, res);
-				r_tilde.copy(res);
-				res_norm = res.l2norm().get();
-				rho_new = r_tilde_norm = res_norm;
-				p.copy(res);
-				++info.restarts;
-				continue;
+		// one iteration; true when the solve is over
+		auto sweep = [&](int it) -> bool {
+			k.rho = shadow.dot(resid).get();
+			if (std::sqrt(std::fabs(k.rho)) < std::numeric_limits<real>::epsilon() * shadow_norm) {
+				// the shadow residual lost its grip on the residual: start over from the true residual
+				// (rho_prev is deliberately left alone, as in the reference)
+				A.residual(rhs, sol, resid);
+				shadow.copy(resid);
+				resid_norm = resid.l2norm().get();
+				k.rho = shadow_norm = resid_norm;
+				dir.copy(resid);
+				++out.restarts;
+				return false;
 			}
 
-			if (iter == 0) {
-				p.copy(res);
+			if (it > 0) {
+				k.beta = (k.rho / k.rho_prev) * (k.alpha / k.omega);
+				dir.axpy(-k.omega, a_dir, dir);
+				dir.axpy(k.beta, dir, resid);
 			}
-			else {
-				beta = (rho_new / rho_old) * (alpha / omega);
-				p.axpy(-omega, v, p);
-				p.axpy(beta, p, res);
-			}
+			else
+				dir.copy(resid);
 
-			P.apply(p, p_hat);
-			A.apply(p_hat, v);
-
-			alpha = r_tilde.dot(v).get();
-			if (alpha == 0.)
+			M.apply(dir, dir_pc);
+			A.apply(dir_pc, a_dir);
+			const real shadow_dot = shadow.dot(a_dir).get();
+			if (shadow_dot == 0.)
 				throw std::runtime_error("BiCGSTAB: encountered alpha = 0");
-			alpha = rho_new / alpha;
+			k.alpha = k.rho / shadow_dot;
 
-			s.axpy(-alpha, v, res);
-			const real s_norm = s.l2norm().get();
-			if (s_norm < settings.rtol) { // early convergence on the half step
-				x.axpy(alpha, p_hat, x);
-				info.iters = iter;
-				info.status = stop::converged_rtol;
-				break;
+			// first half step; note the test against the bare rtol and the iteration count it reports
+			half.axpy(-k.alpha, a_dir, resid);
+			if (half.l2norm().get() < cfg.rtol) {
+				sol.axpy(k.alpha, dir_pc, sol);
+				return finish(it, stop::converged_rtol);
 			}
 
-			P.apply(s, s_hat);
-			A.apply(s_hat, t);
+			M.apply(half, half_pc);
+			A.apply(half_pc, a_half);
+			const real denom = a_half.dot(a_half).get();
+			const real numer = a_half.dot(half).get();
+			k.omega = denom == 0.0 ? real(0.0) : numer / denom;
 
-			const real t_sqnorm = t.dot(t).get();
-			const real t_dot_s = t.dot(s).get();
-			omega = (t_sqnorm == 0.0) ? 0.0 : t_dot_s / t_sqnorm;
+			sol.axpy(k.alpha, dir_pc, sol);
+			sol.axpy(k.omega, half_pc, sol);
+			resid.axpy(-k.omega, a_half, half);
+			resid_norm = resid.l2norm().get();
 
-			x.axpy(alpha, p_hat, x);
-			x.axpy(omega, s_hat, x);
-			res.axpy(-omega, t, s);
+			if (monitor(sol, resid_norm))
+				return finish(it + 1, stop::converged_user);
+			if (resid_norm < goal)
+				return finish(it + 1, stop::converged_rtol);
+			if (k.omega == 0.0)
+				return finish(it + 1, stop::diverged_breakdown);
+			k.rho_prev = k.rho;
+			return false;
+		};
 
-			res_norm = res.l2norm().get();
-			if (diagnostic(x, res_norm)) {
-				info.status = stop::converged_user;
-				info.iters = iter + 1;
+		for (int it = 0; it < cfg.maxiter; ++it)
+			if (sweep(it))
 				break;
-			}
-			if (res_norm < terminate_tol) {
-				info.status = stop::converged_rtol;
-				info.iters = iter + 1;
-				break;
-			}
-			if (omega == 0.0) {
-				info.iters = iter + 1;
-				info.status = stop::diverged_breakdown;
-				break;
-			}
-			rho_old = rho_new;
-		}
 
-		info.res_norm_final = res_norm;
-		info.sol_norm_final = x.l2norm().get();
-		if (info.iters == 0)
-			info.status = stop::diverged_iters;
-		return info;
+		out.res_norm_final = resid_norm;
+		out.sol_norm_final = sol.l2norm().get();
+		if (out.iters == 0) // also what an exhausted iteration budget looks like
+			out.status = stop::diverged_iters;
+		return out;
 	}
 };
 template<class P>

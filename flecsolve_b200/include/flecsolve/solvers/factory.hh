@@ -1,14 +1,23 @@
-// krylov_factory: the Krylov solver named by "type = cg | gmres | bicgstab | cg-device" in a
-// configuration file, built over the caller's operator / preconditioner / diagnostic handles.
+// krylov_factory: the Krylov solver a configuration file names,
+//     [linear-solver]            type = cg | gmres | bicgstab | cg-device
+//     [linear-solver.options]    maxiter = ...   (the chosen solver's own option table)
+// built over the caller's operator / preconditioner / diagnostic handles:
+//     auto s   = read_config(file, krylov_factory::options("linear-solver"));
+//     auto slv = krylov_factory::make_shared(s, u, A, P, diagnostic);     // u: any vector of the solve space
 //
-// Reference: flecsolve/solvers/factory.hh:28-89.  `cg-device` is the extra target of SURVEY 8(f) N1
-// (solvers/cg_device.hh); the reference's fourth target, nka, is a nonlinear accelerator outside
-// the scoped solve loop and is reported as unavailable rather than silently mapped to something else.
+// Same surface as the reference (flecsolve/solvers/factory.hh:28-89: krylov_target, krylov_registry<T>,
+// krylov_factory_policy, krylov_factory = op::factory<policy>).  `cg-device` is the extra target of
+// SURVEY 8(f) N1 (solvers/cg_device.hh).  The reference's fourth target, nka, is a nonlinear accelerator
+// outside the scoped solve loop: its name is rejected as an invalid value rather than mapped to something else.
 #ifndef FLECSOLVE_B200_SOLVERS_FACTORY_HH
 #define FLECSOLVE_B200_SOLVERS_FACTORY_HH
 
+#include <array>
 #include <istream>
+#include <ostream>
 #include <string>
+#include <string_view>
+#include <utility>
 
 #include "flecsolve/operators/factory.hh"
 #include "flecsolve/solvers/bicgstab.hh"
@@ -20,54 +29,61 @@ namespace flecsolve {
 
 enum class krylov_target { cg, gmres, bicgstab, cg_device };
 
-template<krylov_target T>
-struct krylov_registry {};
+namespace detail {
+// spelling of each target in configuration files, indexed by the enum value
+inline constexpr std::array<std::string_view, 4> krylov_target_names{"cg", "gmres", "bicgstab", "cg-device"};
 
-template<template<class> class Solver, class Settings, class Options, class Workgen>
-struct krylov_opreg {
+// what the operator factory needs to know about one solver family: its settings and option types and
+// how to bind it; WorkFactory is the family's `make_work` object type
+template<template<class> class Bound, class Settings, class Options, class WorkFactory>
+struct krylov_family {
 	using settings = Settings;
 	using options = Options;
-	using workgen = Workgen;
-	// v: any vector of the space the solver works in (work vectors are made like it)
-	template<class V, class... Args>
-	static auto make(const settings & s, const V & v, Args &&... args) {
-		return Solver(s, workgen{}(v))(std::forward<Args>(args)...);
+	using workgen = WorkFactory;
+
+	// like_this: a vector of the space the solver works in; the work vectors are made to match it
+	template<class Vec, class... Handles>
+	static auto make(const Settings & with, const Vec & like_this, Handles &&... handles) {
+		auto unbound = Bound(with, WorkFactory{}(like_this));
+		return std::move(unbound)(std::forward<Handles>(handles)...);
 	}
 };
+}
 
-template<>
-struct krylov_registry<krylov_target::cg> : krylov_opreg<cg::solver, cg::settings, cg::options, decltype(cg::make_work)> {};
-template<>
-struct krylov_registry<krylov_target::gmres>
-	: krylov_opreg<gmres::solver, gmres::settings, gmres::options, decltype(gmres::make_work)> {};
-template<>
-struct krylov_registry<krylov_target::bicgstab>
-	: krylov_opreg<bicgstab::solver, bicgstab::settings, bicgstab::options, decltype(bicgstab::make_work)> {};
-template<>
-struct krylov_registry<krylov_target::cg_device>
-	: krylov_opreg<cg_device::solver, cg_device::settings, cg_device::options, decltype(cg_device::make_work)> {};
+template<krylov_target>
+struct krylov_registry; // one specialisation per target, below
 
-inline std::istream & operator>>(std::istream & in, krylov_target & reg) {
-	std::string tok;
-	in >> tok;
-	if (tok == "cg")
-		reg = krylov_target::cg;
-	else if (tok == "gmres")
-		reg = krylov_target::gmres;
-	else if (tok == "bicgstab")
-		reg = krylov_target::bicgstab;
-	else if (tok == "cg-device")
-		reg = krylov_target::cg_device;
-	else
-		in.setstate(std::ios_base::failbit); // includes "nka"
-	return in;
+#define FLECSOLVE_KRYLOV_FAMILY(TARGET, NS)                                                                    \
+	template<>                                                                                                 \
+	struct krylov_registry<krylov_target::TARGET>                                                              \
+		: detail::krylov_family<NS::solver, NS::settings, NS::options, std::decay_t<decltype(NS::make_work)>> {}
+FLECSOLVE_KRYLOV_FAMILY(cg, cg);
+FLECSOLVE_KRYLOV_FAMILY(gmres, gmres);
+FLECSOLVE_KRYLOV_FAMILY(bicgstab, bicgstab);
+FLECSOLVE_KRYLOV_FAMILY(cg_device, cg_device);
+#undef FLECSOLVE_KRYLOV_FAMILY
+
+inline std::ostream & operator<<(std::ostream & os, krylov_target t) {
+	return os << detail::krylov_target_names[static_cast<std::size_t>(t)];
+}
+
+inline std::istream & operator>>(std::istream & is, krylov_target & t) {
+	std::string word;
+	is >> word;
+	for (std::size_t k = 0; k < detail::krylov_target_names.size(); ++k)
+		if (word == detail::krylov_target_names[k]) {
+			t = static_cast<krylov_target>(k);
+			return is;
+		}
+	is.setstate(std::ios_base::failbit); // "nka" ends here too
+	return is;
 }
 
 struct krylov_factory_policy {
 	using target = krylov_target;
 	using targets = includes<target::cg, target::gmres, target::bicgstab, target::cg_device>;
-	template<target V>
-	using registry = krylov_registry<V>;
+	template<target T>
+	using registry = krylov_registry<T>;
 };
 
 using krylov_factory = op::factory<krylov_factory_policy>;

@@ -1,5 +1,7 @@
-// Compile-time variable tags selecting components of multi-vectors
-// (same vocabulary as the reference: flecsolve/vectors/variable.hh:26-77).
+// Compile-time variable tags: which physical variable a vector (or a component of a vec::multi) stands
+// for, and which variables an operator reads and writes.  Vocabulary of the reference
+// (flecsolve/vectors/variable.hh:26-77): variable<V>, multivariable<Vs...>, anon_var::anonymous for
+// vectors that carry no name; tags compare equal iff their values do.
 #ifndef FLECSOLVE_B200_VECTORS_VARIABLE_HH
 #define FLECSOLVE_B200_VECTORS_VARIABLE_HH
 
@@ -9,49 +11,54 @@
 
 namespace flecsolve {
 
+// the tag of vectors and operators that do not name their variable
 enum class anon_var : std::size_t { anonymous = std::numeric_limits<std::size_t>::max() };
 
-template<auto V>
+// optional printable name of a tag value; specialise for your own enumerators
+template<auto Tag>
 struct variable_name {
 	static constexpr const char * value = "";
 };
 
-template<auto V>
+// ---- one variable
+template<auto Tag>
 struct variable_t {
-	static constexpr auto value = V;
-	static constexpr const char * name = variable_name<V>::value;
+	static constexpr auto value = Tag;
+	static constexpr const char * name = variable_name<Tag>::value;
+
+	template<auto Other>
+	constexpr bool operator==(variable_t<Other>) const {
+		return Tag == Other;
+	}
+	template<auto Other>
+	constexpr bool operator!=(variable_t<Other>) const {
+		return !(Tag == Other);
+	}
 };
-template<auto A, auto B>
-constexpr bool operator==(const variable_t<A> &, const variable_t<B> &) {
-	return A == B;
-}
-template<auto A, auto B>
-constexpr bool operator!=(const variable_t<A> &, const variable_t<B> &) {
-	return !(A == B);
-}
-template<auto V>
-inline variable_t<V> variable{};
+template<auto Tag>
+inline variable_t<Tag> variable{};
 
 template<class T>
-struct is_variable : std::false_type {};
-template<auto V>
-struct is_variable<variable_t<V>> : std::true_type {};
+inline constexpr bool is_variable_v = false;
+template<auto Tag>
+inline constexpr bool is_variable_v<variable_t<Tag>> = true;
 template<class T>
-inline constexpr bool is_variable_v = is_variable<T>::value;
+struct is_variable : std::bool_constant<is_variable_v<T>> {};
 
-template<auto... Vs>
-struct multivariable_t {};
-template<auto... Vs>
-inline multivariable_t<Vs...> multivariable{};
-
-template<auto... A, auto... B>
-constexpr bool operator==(const multivariable_t<A...> &, const multivariable_t<B...> &) {
-	return (... && (A == B));
-}
-template<auto... A, auto... B>
-constexpr bool operator!=(const multivariable_t<A...> &, const multivariable_t<B...> &) {
-	return (... || (A != B));
-}
+// ---- an ordered set of variables (operators on vec::multi)
+template<auto... Tags>
+struct multivariable_t {
+	template<auto... Others>
+	constexpr bool operator==(multivariable_t<Others...>) const {
+		return ((Tags == Others) && ...);
+	}
+	template<auto... Others>
+	constexpr bool operator!=(multivariable_t<Others...>) const {
+		return ((Tags != Others) || ...);
+	}
+};
+template<auto... Tags>
+inline multivariable_t<Tags...> multivariable{};
 
 }
 #endif
