@@ -82,40 +82,44 @@ _pd = C.POINTER(C.c_double)
 _pl = C.POINTER(C.c_int64)
 
 
+def declare(L: C.CDLL) -> C.CDLL:
+    """argument types of the fsbh_* entry points (flecsolve_b200/host/driver.cpp)"""
+    L.fsbh_last_error.restype = C.c_char_p
+    L.fsbh_session_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.fsbh_session_destroy.argtypes = [C.c_void_p]
+    L.fsbh_session_b.restype = C.c_void_p
+    L.fsbh_session_b.argtypes = [C.c_void_p]
+    L.fsbh_session_x.restype = C.c_void_p
+    L.fsbh_session_x.argtypes = [C.c_void_p]
+    L.fsbh_solve.argtypes = [C.c_void_p, C.POINTER(Options), _pd, _pd, C.POINTER(Info), _pd, C.c_int]
+    L.fsbh_adapter_apply.argtypes = [C.c_void_p, C.c_double, _pd, _pd]
+    L.fsbh_solve_multi2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Options), _pd, _pd,
+                                    C.POINTER(Info), _pd, C.c_int]
+    L.fsbh_solve_subset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Options), _pd, _pd,
+                                    C.POINTER(Info)]
+    L.fsbh_vector_selftest.argtypes = [C.c_void_p, _pd]
+    _pi = C.POINTER(C.c_int)
+    L.fsbh_bdf_rate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BdfOptions), C.c_double, C.c_double,
+                                C.POINTER(BdfResult), _pd, _pi, _pd, C.c_int]
+    L.fsbh_rk_rate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RkOptions), C.c_double, C.c_double,
+                               C.POINTER(BdfResult), _pd, _pi, _pd, C.c_int]
+    L.fsbh_bdf_heat.argtypes = [C.c_void_p, C.POINTER(BdfOptions), C.POINTER(Options), _pd, _pd,
+                                C.POINTER(BdfResult), _pd, _pi, _pi, C.c_int]
+    L.fsbh_mtx_read.argtypes = [C.c_char_p, _pl, _pl, _pl, _pi, _pl, _pl, _pd]
+    L.fsbh_mtx_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.fsbh_config_dump.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    L.fsbh_solve_config.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, _pd, _pd, C.POINTER(Info), _pd, C.c_int]
+    L.fsbh_poisson_narray.argtypes = [C.c_void_p, C.c_int, C.POINTER(Options), C.c_uint, _pd, C.POINTER(Info), _pd, C.c_int]
+    return L
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         F.lib()  # libfsb.so first (and the NCCL preload)
         if not os.path.exists(LIB_PATH):
             raise F.FsbError(-1, f"{LIB_PATH} is missing: run __graft_entry__.build()")
-        L = C.CDLL(LIB_PATH)
-        L.fsbh_last_error.restype = C.c_char_p
-        L.fsbh_session_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
-        L.fsbh_session_destroy.argtypes = [C.c_void_p]
-        L.fsbh_session_b.restype = C.c_void_p
-        L.fsbh_session_b.argtypes = [C.c_void_p]
-        L.fsbh_session_x.restype = C.c_void_p
-        L.fsbh_session_x.argtypes = [C.c_void_p]
-        L.fsbh_solve.argtypes = [C.c_void_p, C.POINTER(Options), _pd, _pd, C.POINTER(Info), _pd, C.c_int]
-        L.fsbh_adapter_apply.argtypes = [C.c_void_p, C.c_double, _pd, _pd]
-        L.fsbh_solve_multi2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Options), _pd, _pd,
-                                        C.POINTER(Info), _pd, C.c_int]
-        L.fsbh_solve_subset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Options), _pd, _pd,
-                                        C.POINTER(Info)]
-        L.fsbh_vector_selftest.argtypes = [C.c_void_p, _pd]
-        _pi = C.POINTER(C.c_int)
-        L.fsbh_bdf_rate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BdfOptions), C.c_double, C.c_double,
-                                    C.POINTER(BdfResult), _pd, _pi, _pd, C.c_int]
-        L.fsbh_rk_rate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RkOptions), C.c_double, C.c_double,
-                                   C.POINTER(BdfResult), _pd, _pi, _pd, C.c_int]
-        L.fsbh_bdf_heat.argtypes = [C.c_void_p, C.POINTER(BdfOptions), C.POINTER(Options), _pd, _pd,
-                                    C.POINTER(BdfResult), _pd, _pi, _pi, C.c_int]
-        L.fsbh_mtx_read.argtypes = [C.c_char_p, _pl, _pl, _pl, _pi, _pl, _pl, _pd]
-        L.fsbh_mtx_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
-        L.fsbh_config_dump.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
-        L.fsbh_solve_config.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, _pd, _pd, C.POINTER(Info), _pd, C.c_int]
-        L.fsbh_poisson_narray.argtypes = [C.c_void_p, C.c_int, C.POINTER(Options), C.c_uint, _pd, C.POINTER(Info), _pd, C.c_int]
-        _lib = L
+        _lib = declare(C.CDLL(LIB_PATH))
     return _lib
 
 

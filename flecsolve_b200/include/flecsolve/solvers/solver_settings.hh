@@ -54,9 +54,10 @@ struct solve_info {
 	stop_reason status = stop_reason::unknown;
 	int iters = 0;
 	int restarts = 0;
-	float res_norm_initial, res_norm_final;
-	float sol_norm_initial, sol_norm_final;
-	float rhs_norm;
+	// zero until a solver fills them in (the reference leaves them indeterminate; not every solver sets every field)
+	float res_norm_initial = 0, res_norm_final = 0;
+	float sol_norm_initial = 0, sol_norm_final = 0;
+	float rhs_norm = 0;
 
 	bool success() const {
 		return status == stop_reason::converged_atol || status == stop_reason::converged_rtol ||
