@@ -61,59 +61,59 @@ struct cg : base<Params, typename Params::input_var_t, typename Params::output_v
 	const auto & get_operator() const { return params.A(); }
 
 	template<class DomainVec, class RangeVec>
-	solve_info apply(const RangeVec & b, DomainVec & x) const {
+	solve_info apply(const RangeVec & rhs, DomainVec & sol) const {
 		using scalar = typename DomainVec::scalar;
 		using real = typename DomainVec::real;
 		using stop = solve_info::stop_reason;
 
-		solve_info info;
 		const auto & A = params.A();
-		const auto & P = params.P();
-		auto & diagnostic = params.ops.diagnostic;
-		const auto & settings = params.settings;
-		auto & [r, z, p, w] = params.work;
+		const auto & M = params.P();
+		const auto & cfg = params.settings;
+		auto & monitor = params.ops.diagnostic;
+		// work vectors: residual, preconditioned residual, search direction, A * direction
+		auto & w = params.work;
+		auto &resid = w[0], &precond = w[1], &dir = w[2], &a_dir = w[3];
 
-		real terminate_tol, current_res;
-		if (detail::krylov_start(A, settings, b, x, r, info, terminate_tol, current_res))
-			return info;
+		solve_info out;
+		real goal, resid_norm;
+		if (detail::krylov_start(A, cfg, rhs, sol, resid, out, goal, resid_norm))
+			return out;
 
-		P.apply(r, z);
-		scalar rho_prev, rho = z.dot(r).get();
-		p.copy(z);
+		M.apply(resid, precond);
+		scalar rho = precond.dot(resid).get();
+		dir.copy(precond);
 
-		for (int iter = 0; iter < settings.maxiter; iter++) {
-			A.apply(p, w);
-			scalar curvature = w.dot(p).get(); // p' A p
+		// one iteration = three host reads: <Ap, p>, |r|, <r, z> -- each closes one fused kernel
+		for (int it = 0; it < cfg.maxiter; ++it) {
+			A.apply(dir, a_dir);
+			const scalar curvature = a_dir.dot(dir).get();
 			if (curvature <= 0.0)
 				std::cerr << "PCG: negative curvature encountered!" << std::endl;
-			const scalar alpha = rho / curvature;
+			const scalar step = rho / curvature;
 
-			x.axpy(alpha, p, x);
-			r.axpy(-alpha, w, r);
+			sol.axpy(step, dir, sol);
+			resid.axpy(-step, a_dir, resid);
+			resid_norm = resid.l2norm().get();
 
-			current_res = r.l2norm().get();
-			if (diagnostic(x, current_res)) {
-				info.iters = iter + 1;
-				info.status = stop::converged_user;
-				break;
-			}
-			if (current_res < terminate_tol) {
-				info.iters = iter + 1;
-				info.status = stop::converged_rtol;
+			// the callback sees the updated iterate and may end the solve; then the tolerance test
+			const bool user_stop = monitor(sol, resid_norm);
+			if (user_stop || resid_norm < goal) {
+				out.iters = it + 1;
+				out.status = user_stop ? stop::converged_user : stop::converged_rtol;
 				break;
 			}
 
-			P.apply(r, z);
-			rho_prev = rho;
-			rho = r.dot(z).get();
-			p.axpy(rho / rho_prev, p, z); // p = beta p + z
+			M.apply(resid, precond);
+			const scalar rho_before = rho;
+			rho = resid.dot(precond).get();
+			dir.axpy(rho / rho_before, dir, precond); // direction = beta * direction + z
 		}
 
-		info.res_norm_final = current_res;
-		info.sol_norm_final = x.l2norm().get();
-		if (info.iters == 0)
-			info.status = stop::diverged_iters;
-		return info;
+		out.res_norm_final = resid_norm;
+		out.sol_norm_final = sol.l2norm().get();
+		if (out.iters == 0) // an exhausted iteration budget leaves iters at 0, as in the reference
+			out.status = stop::diverged_iters;
+		return out;
 	}
 };
 template<class P>
