@@ -1,11 +1,14 @@
-// op::handle: how solvers hold operators -- shared ownership or a plain reference, never a copy.
-// Reference: flecsolve/operators/handle.hh:11-56.
+// op::handle<T>: how solvers, integrators and factories hold operators -- by shared ownership
+// (op::make_shared<Policy>(args...)) or by plain reference to an object the caller keeps alive
+// (op::ref(A), op::cref(A)) -- never by copy: an operator may own device matrices and work vectors.
+// Interface of the reference class (flecsolve/operators/handle.hh:11-56): `type`, get(), conversion to
+// T&, call forwarding, and the three factory functions.
 #ifndef FLECSOLVE_B200_OPERATORS_HANDLE_HH
 #define FLECSOLVE_B200_OPERATORS_HANDLE_HH
 
-#include <functional>
 #include <memory>
-#include <variant>
+#include <type_traits>
+#include <utility>
 
 #include "flecsolve/operators/core.hh"
 #include "flecsolve/util/traits.hh"
@@ -13,40 +16,47 @@
 namespace flecsolve::op {
 
 template<class T>
-struct handle {
+class handle {
+	std::shared_ptr<T> keep_alive_; // empty for borrowed operators
+	T * target_ = nullptr;
+
+public:
 	using type = T;
-	using var_t = std::variant<std::shared_ptr<type>, std::reference_wrapper<type>>;
-	var_t store;
 
-	constexpr type & get() const {
-		if (auto * sp = std::get_if<std::shared_ptr<type>>(&store))
-			return **sp;
-		return std::get<std::reference_wrapper<type>>(store).get();
-	}
-	constexpr operator type &() const { return get(); }
+	// borrow: the caller guarantees the operator outlives every solver bound to it
+	explicit constexpr handle(T & borrowed) : target_(&borrowed) {}
+	// share
+	explicit handle(std::shared_ptr<T> owned) : keep_alive_(std::move(owned)), target_(keep_alive_.get()) {}
 
-	template<class D, class R>
-	decltype(auto) operator()(const D & x, R & y) const {
-		return get()(x, y);
+	constexpr T & get() const { return *target_; }
+	constexpr operator T &() const { return *target_; }
+	bool owns() const { return static_cast<bool>(keep_alive_); }
+
+	// a handle to an operator can be applied like the operator
+	template<class X, class Y>
+	decltype(auto) operator()(const X & x, Y & y) const {
+		return (*target_)(x, y);
 	}
 };
 
 template<class T>
-constexpr auto ref(T & o) {
-	return handle<T>{std::ref(o)};
+constexpr handle<T> ref(T & op) {
+	return handle<T>(op);
 }
 template<class T>
-constexpr auto cref(const T & o) {
-	return handle<const T>{std::ref(o)};
+constexpr handle<const T> cref(const T & op) {
+	return handle<const T>(op);
 }
 
-template<class T, std::enable_if_t<!is_operator_v<T>, bool> = false, class... Args>
-constexpr auto make_shared(Args &&... args) {
-	return handle<core<T>>{std::make_shared<core<T>>(std::forward<Args>(args)...)};
+// construct op::core<Policy> from the policy's constructor arguments, shared
+template<class Policy, std::enable_if_t<!is_operator_v<Policy>, bool> = false, class... Args>
+handle<core<Policy>> make_shared(Args &&... args) {
+	return handle<core<Policy>>(std::make_shared<core<Policy>>(std::forward<Args>(args)...));
 }
-template<class T>
-constexpr auto make_shared(core<T> && o) {
-	return handle<core<T>>{std::make_shared<core<T>>(std::move(o))};
+// move an existing operator into shared ownership
+template<class Policy>
+handle<core<Policy>> make_shared(core<Policy> && op) {
+	return handle<core<Policy>>(std::make_shared<core<Policy>>(std::move(op)));
 }
 
 }
