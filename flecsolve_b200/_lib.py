@@ -103,6 +103,7 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_ctx_event_elapsed_ms", C.c_int, _p, C.c_int, C.c_int, _pd)
     f("fsb_ctx_profile_read", C.c_int, _p, _pd, _pi64)
     f("fsb_ctx_profile_read_split", C.c_int, _p, _pd, _pi64)
+    f("fsb_debug_jit_compile", C.c_int, _pi32, C.c_int, C.c_int, C.c_int, _pi64, C.c_char_p, C.c_int)
     f("fsb_vec_create", C.c_int, _p, _i64, _i64, C.POINTER(_p))
     f("fsb_vec_wrap", C.c_int, _p, _p, _i64, _i64, C.POINTER(_p))
     f("fsb_vec_destroy", C.c_int, _p)
@@ -171,8 +172,8 @@ def device_count() -> int:
 
 
 STAT = {"launches": 0, "fused_statements": 1, "halo_exchanges": 2, "allreduces": 3, "host_syncs": 4,
-        "unmatched_groups": 5, "wait_ns": 6, "flush_ns": 7}
-OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3, "profile": 4, "reproducible": 5}
+        "unmatched_groups": 5, "wait_ns": 6, "flush_ns": 7, "jit_groups": 8}
+OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3, "profile": 4, "reproducible": 5, "jit": 6}
 
 
 class Context:

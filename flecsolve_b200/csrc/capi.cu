@@ -200,6 +200,8 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 		c->reproducible = nranks == 1 || c->d_xrank != nullptr;
 		if (const char * e = std::getenv("FSB_REPRODUCIBLE")) // measurement override
 			c->reproducible = std::atoi(e) != 0;
+		if (const char * t = std::getenv("FSB_JIT"))
+			c->jit = std::atoi(t) != 0;
 		if (const char * t = std::getenv("FSB_TRACE"))
 			c->trace = std::atoi(t) != 0;
 		if (const char * t = std::getenv("FSB_FUSION"))
@@ -290,15 +292,40 @@ int fsb_ctx_set_option(fsb_ctx_t c, int option, int64_t value) {
 		case FSB_OPT_REPRODUCIBLE:
 			c->reproducible = value != 0;
 			break;
+		case FSB_OPT_JIT:
+			c->jit = value != 0;
+			break;
 		default:
 			throw fsb::error(FSB_ERR_ARG, "unknown option");
 		}
 	});
 }
 
+int fsb_debug_jit_compile(const int32_t * raw, int n, int device_coefficients, int box_layout, int64_t * cubin_bytes,
+                          char * log, int log_capacity) {
+	return guarded([&] {
+		FSB_REQUIRE(raw && n >= 1 && n <= fsb::MAXS && cubin_bytes, "bad arguments");
+		fsb::raw_stmt rs[fsb::MAXS];
+		for (int i = 0; i < n; ++i)
+			rs[i] = fsb::raw_stmt{raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]};
+		const fsb::canon_result cr = fsb::canonicalize(rs, n);
+		FSB_REQUIRE(cr.ok, "statement list exceeds the program limits");
+		std::vector<char> cubin;
+		std::string text;
+		const bool ok = fsb::jit_compile(cr.p, device_coefficients != 0, box_layout != 0, cubin, text);
+		if (log && log_capacity > 0) {
+			std::strncpy(log, text.c_str(), static_cast<size_t>(log_capacity) - 1);
+			log[log_capacity - 1] = 0;
+		}
+		if (!ok)
+			throw fsb::error(FSB_ERR_STATE, "run-time compilation failed: " + text.substr(0, 400));
+		*cubin_bytes = static_cast<int64_t>(cubin.size());
+	});
+}
+
 int fsb_ctx_get_stat(fsb_ctx_t c, int stat, int64_t * out) {
 	return guarded([&] {
-		FSB_REQUIRE(stat >= 0 && stat < 8 && out, "bad stat");
+		FSB_REQUIRE(stat >= 0 && stat < 16 && out, "bad stat");
 		*out = c->stats[stat];
 	});
 }

@@ -6,8 +6,9 @@
 // per-CTA partials in a fixed order (bitwise reproducible) and publishes the result to
 // pinned host memory so the host can poll instead of synchronising the stream.
 #pragma once
+#ifndef __CUDACC_RTC__ // NVRTC (csrc/jit.cu) has the CUDA built-ins without headers
 #include <cuda_runtime.h>
-#include <utility>
+#endif
 
 #include "program.h"
 
@@ -195,9 +196,9 @@ __device__ __forceinline__ void exec_stmt(double (&v)[MAXV], double (&acc)[MAXR]
 
 template<class PT, class SC>
 __device__ __forceinline__ void exec_all(double (&v)[MAXV], double (&acc)[MAXR], const SC & sc) {
-	[&]<size_t... I>(std::index_sequence<I...>) {
-		(exec_stmt<PT, static_cast<int>(I)>(v, acc, sc), ...);
-	}(std::make_index_sequence<PT::value.n>{});
+	[&]<int... I>(iseq<I...>) {
+		(exec_stmt<PT, I>(v, acc, sc), ...);
+	}(make_iseq<PT::value.n>{});
 }
 
 // the element loops of a program; SC is either the kernel-parameter array (immediate coefficients,
@@ -249,14 +250,45 @@ constexpr int red_fold() {
 	return 0;
 }
 
-// DEV: some coefficients live in device memory (and the halt flag is honoured)
-template<class PT, bool DEV = false>
-__global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_constant__ ew_args a) {
+// the same loop over the interior sub-box of padded arrays (dofs of an narray mesh, reference
+// examples/poisson/mesh.hh:157-161 + index_util.hh:33-71): scalar 8-byte accesses, consecutive threads on
+// consecutive x, rows of the box need not be 16-byte aligned
+template<class PT, class SC>
+__device__ __forceinline__ void run_elements_box(const ew_args & a, const SC & sc, double (&acc)[MAXR]) {
 	constexpr program P = PT::value;
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+		const long long t = i / a.bn0, i0 = i - t * a.bn0, i2 = t / a.bn1, i1 = t - i2 * a.bn1;
+		const long long at = a.boff + i0 + a.bE0 * i1 + a.bE01 * i2;
+		double v[MAXV];
+#pragma unroll
+		for (int k = 0; k < P.nv; ++k)
+			if (P.load_mask & (1u << k))
+				v[k] = a.v[k][at];
+		exec_all<PT>(v, acc, sc);
+#pragma unroll
+		for (int k = 0; k < P.nv; ++k)
+			if (P.store_mask & (1u << k))
+				a.v[k][at] = v[k];
+	}
+}
+
+// Body of every program kernel.  DEV: some coefficients live in device memory (and the halt flag is
+// honoured); BOX: structured-grid layout.  The ahead-of-time instantiations below use BOX = false only (box
+// layouts cost registers); the run-time compiler (csrc/jit.cu) instantiates whatever a statement group needs.
+template<class PT, bool DEV, bool BOX>
+__device__ __forceinline__ void ew_program_body(const ew_args & a) {
+	constexpr program P = PT::value;
+	auto run = [&](const auto & sc, double (&acc)[MAXR]) {
+		if constexpr (BOX)
+			run_elements_box<PT>(a, sc, acc);
+		else
+			run_elements<PT>(a, sc, acc);
+	};
 	double acc[MAXR];
-	[&]<size_t... R>(std::index_sequence<R...>) {
-		((acc[R] = fold_identity<red_fold<PT, static_cast<int>(R)>()>()), ...);
-	}(std::make_index_sequence<(P.nr > 0 ? P.nr : 0)>{});
+	[&]<int... R>(iseq<R...>) {
+		((acc[R] = fold_identity<red_fold<PT, R>()>()), ...);
+	}(make_iseq<(P.nr > 0 ? P.nr : 0)>{});
 
 	if constexpr (DEV) {
 		if (!(a.halt && *a.halt)) { // once halted, vectors stay as they are; reductions publish identities
@@ -264,18 +296,18 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_const
 #pragma unroll
 			for (int k = 0; k < P.ns; ++k)
 				sc[k] = a.snum[k] < 0 ? a.s[k] : __dmul_rn(a.s[k], __ddiv_rn(a.sdev[a.snum[k]], a.sdev[a.sden[k]]));
-			run_elements<PT>(a, sc, acc);
+			run(sc, acc);
 		}
 	}
 	else
-		run_elements<PT>(a, a.s, acc);
+		run(a.s, acc);
 
 	if constexpr (P.nr > 0) {
 		__shared__ double scratch[32];
 		__shared__ bool is_last;
-		[&]<size_t... R>(std::index_sequence<R...>) {
-			((acc[R] = block_fold<red_fold<PT, static_cast<int>(R)>()>(acc[R], scratch)), ...);
-		}(std::make_index_sequence<P.nr>{});
+		[&]<int... R>(iseq<R...>) {
+			((acc[R] = block_fold<red_fold<PT, R>()>(acc[R], scratch)), ...);
+		}(make_iseq<P.nr>{});
 		if (threadIdx.x == 0) {
 #pragma unroll
 			for (int r = 0; r < P.nr; ++r)
@@ -287,9 +319,9 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_const
 		__syncthreads();
 		if (is_last) {
 			__threadfence();
-			[&]<size_t... R>(std::index_sequence<R...>) {
+			[&]<int... R>(iseq<R...>) {
 				(([&] {
-					 constexpr int F = red_fold<PT, static_cast<int>(R)>();
+					 constexpr int F = red_fold<PT, R>();
 					 double t = fold_identity<F>();
 					 for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += blockDim.x)
 						 t = fold<F>(t, __ldcg(&a.partials[R * a.partial_stride + b]));
@@ -300,11 +332,16 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_const
 						 publish(a.r[R], t);
 				 }()),
 				 ...);
-			}(std::make_index_sequence<P.nr>{});
+			}(make_iseq<P.nr>{});
 			if (threadIdx.x == 0)
 				*a.counter = 0u;
 		}
 	}
+}
+
+template<class PT, bool DEV = false>
+__global__ void __launch_bounds__(EW_BLOCK) ew_program_kernel(const __grid_constant__ ew_args a) {
+	ew_program_body<PT, DEV, false>(a);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -133,6 +133,7 @@ struct fsb_ctx_s {
 	bool fusion = true;
 	bool trace = false;
 	bool reproducible = true; // SpMV row blocks statically assigned to CTAs (set from nranks at creation)
+	bool jit = false; // statement groups without a compiled instantiation: compile one at run time (jit.cu)
 	int spmv_rows_per_cta = 0; // 0 = auto
 	int spmv_threads = 0;
 
@@ -146,7 +147,7 @@ struct fsb_ctx_s {
 	void * d_flush = nullptr;
 	size_t flush_bytes = 0;
 
-	int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	int64_t stats[16] = {};
 	uint64_t next_vec_id = 1;
 };
 
@@ -230,6 +231,11 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y
                 const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s,
                 const pending * fold = nullptr);
 void fill_red_out(fsb_ctx_s * c, const pending & red, red_out & r);
+// run-time compiled program kernels (jit.cu)
+struct ew_args;
+bool jit_compile(const program & p, bool dev, bool box, std::vector<char> & cubin, std::string & log);
+const void * jit_kernel(const program & p, bool dev, bool box, int * resident);
+void jit_launch(const void * kernel, int resident, const ew_args & a, int want, cudaStream_t s);
 void finish_reduction_nccl(fsb_ctx_s * c, const pending & red);
 void finalize_reduction(fsb_ctx_s * c, int n_partials, const pending & red);
 void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x);

@@ -246,10 +246,12 @@ static std::string describe(const pending * q, int n) {
 }
 
 struct bound_group {
-	launcher_t launch = nullptr; // registered instantiation, or nullptr => generic kernel with `prog`
+	launcher_t launch = nullptr; // registered instantiation, or nullptr => run-time compiled / generic kernel with `prog`
 	ew_args args{};
 	program prog{};
 	int nr = 0;
+	bool dev = false; // device-resident coefficients or halt flag in play
+	bool box = false; // structured-grid layout
 };
 
 static void launch_interp(const bound_group & g, int want, cudaStream_t s) {
@@ -295,8 +297,10 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 	if (it == table.end() && !allow_generic)
 		return false;
 	g.launch = it == table.end() ? nullptr : it->second;
-	if (layout_of(q[0])->box)
-		g.launch = nullptr; // structured-grid layouts are handled by the generic kernel only
+	g.dev = dev;
+	g.box = layout_of(q[0])->box;
+	if (g.box)
+		g.launch = nullptr; // no ahead-of-time instantiation carries the structured-grid loop
 	g.prog = cr.p;
 	g.nr = cr.p.nr;
 	ew_args & a = g.args;
@@ -471,8 +475,14 @@ void flush(fsb_ctx_s * c) {
 			long long packets = layout_of(q[i])->box ? n : (n + 1) / 2; // box layout: one element per thread and trip
 			long long want = (packets + EW_BLOCK - 1) / EW_BLOCK;
 			const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, MAX_RED_BLOCKS)));
+			int resident = 0;
+			const void * jk = (!g.launch && c->jit) ? jit_kernel(g.prog, g.dev, g.box, &resident) : nullptr;
 			if (g.launch)
 				g.launch(g.args, grid, c->stream);
+			else if (jk) {
+				jit_launch(jk, resident, g.args, grid, c->stream);
+				c->stats[FSB_STAT_JIT_GROUPS]++;
+			}
 			else
 				launch_interp(g, grid, c->stream);
 			FSB_CUDA(cudaGetLastError());

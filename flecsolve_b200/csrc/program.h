@@ -7,7 +7,7 @@
 // so a queued group matches a registered kernel iff their canonical forms are
 // byte-identical.
 #pragma once
-#include <cstdint>
+// (no standard headers: this file is also compiled by NVRTC at run time, csrc/jit.cu)
 
 namespace fsb {
 
@@ -49,9 +49,22 @@ struct raw_stmt {
 	int z, x, y; // -1 when unused; for reductions z is ignored
 };
 
+typedef signed char slot_t; // small indices; -1 = unused
 struct stmt {
-	int8_t op, z, x, y, a, b;
+	slot_t op, z, x, y, a, b;
 };
+
+// compile-time integer sequences (std::index_sequence without <utility>)
+template<int... I>
+struct iseq {};
+template<int N, int... I>
+struct make_iseq_impl : make_iseq_impl<N - 1, N - 1, I...> {};
+template<int... I>
+struct make_iseq_impl<0, I...> {
+	using type = iseq<I...>;
+};
+template<int N>
+using make_iseq = typename make_iseq_impl<N>::type;
 
 struct program {
 	int n = 0;
@@ -88,18 +101,18 @@ constexpr canon_result canonicalize(const raw_stmt * rs, int n) {
 		c.id_of_slot[nv] = id;
 		return nv++;
 	};
-	auto rd = [&](int id) -> int8_t {
+	auto rd = [&](int id) -> slot_t {
 		int k = slot(id);
 		if (!touched[k]) {
 			c.p.load_mask |= 1u << k; // first touch is a read: value comes from memory
 			touched[k] = true;
 		}
-		return static_cast<int8_t>(k);
+		return static_cast<slot_t>(k);
 	};
 	for (int i = 0; i < n; ++i) {
 		const raw_stmt & r = rs[i];
 		stmt s{};
-		s.op = static_cast<int8_t>(r.op);
+		s.op = static_cast<slot_t>(r.op);
 		s.x = s.y = s.z = s.a = s.b = -1;
 		if (reads_x(r.op))
 			s.x = rd(r.x);
@@ -110,13 +123,13 @@ constexpr canon_result canonicalize(const raw_stmt * rs, int n) {
 				c.ok = false;
 				return c;
 			}
-			s.z = static_cast<int8_t>(c.p.nr++);
+			s.z = static_cast<slot_t>(c.p.nr++);
 		}
 		else {
 			int k = slot(r.z);
 			touched[k] = true;
 			c.p.store_mask |= 1u << k;
-			s.z = static_cast<int8_t>(k);
+			s.z = static_cast<slot_t>(k);
 		}
 		int k = scalars_of(r.op);
 		if (c.p.ns + k > MAXSC) {
@@ -124,9 +137,9 @@ constexpr canon_result canonicalize(const raw_stmt * rs, int n) {
 			return c;
 		}
 		if (k >= 1)
-			s.a = static_cast<int8_t>(c.p.ns++);
+			s.a = static_cast<slot_t>(c.p.ns++);
 		if (k >= 2)
-			s.b = static_cast<int8_t>(c.p.ns++);
+			s.b = static_cast<slot_t>(c.p.ns++);
 		if (!c.ok)
 			return c;
 		c.p.st[i] = s;

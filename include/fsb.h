@@ -58,6 +58,10 @@ enum fsb_option {
 	                            0: row blocks are claimed dynamically, which tolerates SMs shared with
 	                            communication kernels (default when halo and reductions go through NCCL;
 	                            results then vary in the last bits) */
+	,
+	FSB_OPT_JIT = 6 /* 1: a statement group without an ahead-of-time kernel gets one compiled at run time
+	                   (NVRTC, cached per process) instead of the generic program kernel; 0 (default in this
+	                   version; FSB_JIT=1 in the environment turns it on) */
 };
 
 enum fsb_stat {
@@ -68,7 +72,8 @@ enum fsb_stat {
 	FSB_STAT_HOST_SYNCS = 4,
 	FSB_STAT_UNMATCHED_GROUPS = 5, /* groups launched through the generic program kernel (no compile-time instantiation) */
 	FSB_STAT_WAIT_NS = 6, /* host time spent waiting for reduction results (fsb_red_get / fsb_red_wait) */
-	FSB_STAT_FLUSH_NS = 7 /* host time spent turning queued statements into launches */
+	FSB_STAT_FLUSH_NS = 7, /* host time spent turning queued statements into launches */
+	FSB_STAT_JIT_GROUPS = 8 /* groups launched through a run-time compiled kernel */
 };
 
 const char * fsb_last_error(void);
@@ -105,6 +110,12 @@ int fsb_ctx_event_elapsed_ms(fsb_ctx_t ctx, int slot_start, int slot_stop, doubl
 int fsb_ctx_profile_read(fsb_ctx_t ctx, double * spmv_ms, int64_t * spmv_launches);
 /* same, split by block: index 0 = diag (owned columns) launches, 1 = offd (ghost columns) launches */
 int fsb_ctx_profile_read_split(fsb_ctx_t ctx, double * ms2, int64_t * launches2);
+
+/* diagnostics: canonicalise the statement list raw[4 n] = {op, z, x, y} (ops as in csrc/program.h, vector ids
+ * arbitrary small integers, -1 = unused) and compile its kernel for sm_100a with the run-time compiler.
+ * Needs no GPU.  Returns FSB_OK and the cubin size, or FSB_ERR_STATE with the compiler log in `log`.   */
+int fsb_debug_jit_compile(const int32_t * raw, int n, int device_coefficients, int box_layout, int64_t * cubin_bytes,
+                          char * log, int log_capacity);
 
 /* ---- vectors -----------------------------------------------------------
  * A vector is the device image of one field on the reference's `cols' index

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "jit_hw: run-time compiled kernels on hardware (opt-in, not part of -m gpu yet)")
     # make sure the native pieces exist (no-op when up to date; nvcc cross-compiles without a GPU)
     from flecsolve_b200 import build
     build.build_all()
