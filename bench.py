@@ -278,9 +278,22 @@ def cpu_baseline(workload: str, sample_iters: int, warm: int = 2) -> dict:
     t0 = time.perf_counter()
     _, info, _ = M.cg(b, dinv=dinv, maxiter=sample_iters, rtol=0.0)
     dt = time.perf_counter() - t0
-    return {"value": sample_iters / dt, "unit": "iterations/s", "cores": threads, "kind": "port",
-            "sample": f"first {sample_iters} CG iterations of the same system (x0 = 0), {threads} OpenMP threads = colours, "
-                      f"{dt:.1f} s", "seconds": dt}
+    out = {"value": sample_iters / dt, "unit": "iterations/s", "cores": threads, "kind": "port",
+           "sample": f"first {sample_iters} CG iterations of the same system (x0 = 0), {threads} OpenMP threads = colours, "
+                     f"{dt:.1f} s", "seconds": dt, "host_cores": os.cpu_count()}
+    if threads > 1:  # the serial figure beside it (one colour, one thread), on a shorter sample
+        one_iters = max(3, sample_iters // 8)
+        M1 = O.ParCSR(rp, col, val, colours=1)
+        O.set_threads(1)
+        try:
+            M1.cg(b, dinv=dinv, maxiter=1, rtol=0.0)
+            t0 = time.perf_counter()
+            M1.cg(b, dinv=dinv, maxiter=one_iters, rtol=0.0)
+            d1 = time.perf_counter() - t0
+        finally:
+            O.set_threads(threads)
+        out["one_thread"] = {"value": one_iters / d1, "iterations": one_iters, "seconds": d1}
+    return out
 
 
 def run_reference(args):
