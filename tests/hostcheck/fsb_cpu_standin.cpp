@@ -366,8 +366,37 @@ int fsb_parcsr_create(fsb_ctx_t c, int64_t n, const int64_t * part, const int64_
 	*out = A;
 	return FSB_OK;
 }
-int fsb_parcsr_create_stencil(fsb_ctx_t, int, int64_t, int64_t, int64_t, double, double, fsb_parcsr_t *) {
-	return fail(FSB_ERR_STATE, "stand-in: build stencil matrices on the caller's side and use fsb_parcsr_create");
+// the synthetic operators of SURVEY 8(d): rows g = i + nx (j + ny k), Dirichlet truncation, columns ascending,
+// centre (4 | 6 | 26 + diag_shift) * scale, neighbours -scale
+int fsb_parcsr_create_stencil(fsb_ctx_t c, int kind, int64_t nx, int64_t ny, int64_t nz, double diag_shift, double scale,
+                              fsb_parcsr_t * out) {
+	if (kind != 5 && kind != 7 && kind != 27)
+		return fail(FSB_ERR_ARG, "stencil kind must be 5, 7 or 27");
+	if (kind == 5)
+		nz = 1;
+	auto * A = new fsb_parcsr_s;
+	A->ctx = c;
+	A->n = nx * ny * nz;
+	const double dv = ((kind == 27 ? 26.0 : kind == 7 ? 6.0 : 4.0) + diag_shift) * scale, ov = -1.0 * scale;
+	A->rowptr.push_back(0);
+	for (int64_t g = 0; g < A->n; ++g) {
+		const int64_t i = g % nx, j = (g / nx) % ny, k = g / (nx * ny);
+		for (int dk = -1; dk <= 1; ++dk)
+			for (int dj = -1; dj <= 1; ++dj)
+				for (int di = -1; di <= 1; ++di) {
+					const int64_t ii = i + di, jj = j + dj, kk = k + dk;
+					if (ii < 0 || ii >= nx || jj < 0 || jj >= ny || kk < 0 || kk >= nz)
+						continue;
+					const int nonzero = (di != 0) + (dj != 0) + (dk != 0);
+					if (kind != 27 && nonzero > 1)
+						continue; // 5- and 7-point: axis neighbours only
+					A->col.push_back(ii + nx * (jj + ny * kk));
+					A->val.push_back(nonzero == 0 ? dv : ov);
+				}
+		A->rowptr.push_back(static_cast<int64_t>(A->col.size()));
+	}
+	*out = A;
+	return FSB_OK;
 }
 int fsb_parcsr_create_box_stencil(fsb_ctx_t c, int dim, const int64_t * ext, const int64_t * lo, const int64_t * hi,
                                   double center, const double * off, fsb_parcsr_t * out) {

@@ -236,3 +236,22 @@ def test_config_chosen_solver_and_narray_example(hc, tmp_path):
     assert np.allclose(hist, fhist, rtol=1e-10) and np.abs(u - xf).max() <= 1e-10
     assert np.abs(u - exact).max() < 8e-3
     S.close()
+
+
+def test_example_applications_run_on_the_stand_in(tmp_path):
+    """examples/poisson and examples/heat_equation: flecsolve-shaped user programs (read_config, krylov_factory,
+    bdf::integrator, narray mesh); linked against the stand-in their host logic runs here end to end"""
+    import re
+    import subprocess
+    ex = os.path.join(os.path.dirname(HERE), "examples")
+    exe = HB.build_example("poisson_standin", os.path.join("poisson", "poisson.cc"))
+    r = subprocess.run([exe, "40", os.path.join(ex, "poisson", "poisson.cfg")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"converged after (\d+) iterations.*max error.*= ([0-9.e+-]+)", r.stdout)
+    assert m and 50 < int(m.group(1)) < 300 and float(m.group(2)) < 3e-3, r.stdout
+    exe = HB.build_example("implicit_standin", os.path.join("heat_equation", "implicit.cc"))
+    r = subprocess.run([exe, "16", os.path.join(ex, "heat_equation", "implicit.cfg")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"(\d+) steps \((\d+) attempts, (\d+) rejected\), max u = ([0-9.]+), heat ([0-9.]+) -> ([0-9.]+)", r.stdout)
+    assert m, r.stdout
+    assert int(m.group(1)) >= 10 and 0.0 < float(m.group(4)) <= 50.0 and float(m.group(6)) <= float(m.group(5)) * (1 + 1e-9)
