@@ -19,13 +19,25 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DIR = os.environ.get("FSB_SUITESPARSE_DIR", os.path.join(HERE, "golden", "suitesparse"))
 
 # (file, solver, settings as in the reference's cfg files, accepted iteration counts or upper bound)
+# right-hand side / initial guess: cg.cc, bicgstab.cc: b = 0, x0 = mt19937(7); gmres.cc:58-62: b = mt19937(0),
+# x0 = mt19937(1); matrices/test/par_csr.cc:23-34: b = 0, x0 = 2 (3 colours there: 167 iterations)
 CASES = [
     ("494_bus.mtx", "cg", dict(maxiter=2000, rtol=1e-9), {1822, 1829}, None),
     ("Chem97ZtZ.mtx", "cg", dict(maxiter=2000, rtol=1e-9), {161}, None),
-    ("Chem97ZtZ.mtx", "gmres", dict(maxiter=100, rtol=1e-4), {73}, None),
+    ("Chem97ZtZ.mtx", "cg", dict(maxiter=2000, rtol=1e-9, x0=2.0), {167}, None),
+    ("Chem97ZtZ.mtx", "gmres", dict(maxiter=100, rtol=1e-4, bseed=0, xseed=1), {73}, None),
+    ("Chem97ZtZ.mtx", "gmres", dict(maxiter=100, rtol=1e-4, bseed=0, xseed=1, precond="dinv"), {18}, None),
     ("Chem97ZtZ.mtx", "bicgstab", dict(maxiter=200, rtol=1e-9), None, 92),
     ("psmigr_3.mtx", "bicgstab", dict(maxiter=200, rtol=1e-9), None, 33),
 ]
+
+
+def _vectors(n, kw, random):
+    """(b, x0, remaining solver keywords); random(seed) draws the library's mt19937 uniform(0,1) stream"""
+    kw = dict(kw)
+    bseed, xseed, x0 = kw.pop("bseed", None), kw.pop("xseed", 7), kw.pop("x0", None)
+    b = np.zeros(n) if bseed is None else random(bseed)
+    return b, (np.full(n, x0) if x0 is not None else random(xseed)), kw
 
 
 def _need(name):
@@ -55,8 +67,11 @@ def test_reference_goldens_on_the_host_layer(monkeypatch, name, solver, kw, acce
     s = Standin(L)
     S = H.Session(s.ctx, s.from_csr(nr, rp, col, val))
     import oracle as O
-    x0 = O.ParCSR(rp, col, val, colours=1).set_random(7)
-    _, info, _ = S.solve(np.zeros(nr), x0, solver=solver, **kw)
+    M = O.ParCSR(rp, col, val, colours=1)
+    b, x0, kw = _vectors(nr, kw, M.set_random)
+    _, info, _ = S.solve(b, x0, solver=solver, **kw)
+    if kw.get("x0") is None and accepted == {167}:  # counted on 3 colours in the reference: rounding may move it by one
+        accepted = {166, 167, 168}
     _check(info, accepted, bound)
     S.close(); s.close()
 
@@ -67,8 +82,11 @@ def test_reference_goldens_on_the_device(ctx, name, solver, kw, accepted, bound)
     path = _need(name)
     A = H.mtx_create(ctx, path)
     S = H.Session(ctx, A)
-    S.x.set_random(7)
-    _, info, _ = S.solve(np.zeros(A.local_rows), S.x.download(), solver=solver, **kw)
+    def random(seed):
+        S.x.set_random(seed)
+        return S.x.download()
+    b, x0, kw = _vectors(A.local_rows, kw, random)
+    _, info, _ = S.solve(b, x0, solver=solver, **kw)
     assert info.reason == "converged_rtol"
     if accepted is not None:
         assert min(abs(info.iters - a) for a in accepted) <= max(1, 0.02 * max(accepted)), (info.iters, accepted)
