@@ -98,6 +98,7 @@ def declare(L: C.CDLL) -> C.CDLL:
     L.fsbh_solve_subset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Options), _pd, _pd,
                                     C.POINTER(Info)]
     L.fsbh_vector_selftest.argtypes = [C.c_void_p, _pd]
+    L.fsbh_multivector_selftest.argtypes = [C.c_void_p, _pd]
     _pi = C.POINTER(C.c_int)
     L.fsbh_bdf_rate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BdfOptions), C.c_double, C.c_double,
                                 C.POINTER(BdfResult), _pd, _pi, _pd, C.c_int]
@@ -191,6 +192,12 @@ class Session:
                                    good.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)), cap))
         k = min(res.attempts, cap)
         return u, res, dts[:k], good[:k], iters[:k]
+
+    def multivector_selftest(self) -> np.ndarray:
+        """closed forms of vectors/test/flecsi_multivector.cc on a four-component vec::multi (see driver.cpp)"""
+        out = np.zeros(18)
+        _check(lib().fsbh_multivector_selftest(self.h, _d(out)))
+        return out
 
     def vector_selftest(self) -> np.ndarray:
         out = np.zeros(16)

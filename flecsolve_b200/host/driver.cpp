@@ -12,6 +12,8 @@
 #include <memory>
 #include <optional>
 #include <string>
+#include <algorithm>
+#include <array>
 #include <vector>
 #include <variant>
 #include <sstream>
@@ -867,6 +869,124 @@ int fsbh_poisson_narray(fsb_ctx_t ctx_h, int m, const fsbh_options * o, unsigned
 		}
 		device::check(fsb_vec_download(u.data.handle(), u_host, static_cast<std::int64_t>(rhs.size()), 0));
 		fill(info, si, rec.count);
+	});
+}
+
+// The closed forms of the reference's multi-vector test (vectors/test/flecsi_multivector.cc:84-241) on a
+// four-component vec::multi over the session's topology: component i of x, y, z holds (i+1) gid, (i+2) gid,
+// (i+3) gid.  out[0..10]: max |error| of add, subtract, multiply, add_scalar, divide, scale, reciprocal,
+// linear_sum, axpy, axpby, abs; out[11]: min check (== -7 expected, returns the value); out[12..16]: 1 when the
+// combined max / l1 / l2 / inf norm / dot equals the combination of the component reductions EXACTLY, else 0;
+// out[17]: 1 when subset() by variable and by multivariable hands back the named components (by field id).
+int fsbh_multivector_selftest(void * sv, double * out18) {
+	return guarded([&] {
+		session & S = *static_cast<session *>(sv);
+		auto & topo = S.A.data.topo();
+		static const std::array<vec_def, 4> xs, ys, zs, ts;
+		static const vec_def pd, td, dd;
+		const std::int64_t n = fsb_vec_local_size(S.b.data.handle());
+		const std::int64_t g0 = topo.meta().rows.beg;
+		auto family = [&](const std::array<vec_def, 4> & defs, int offset, bool fill) {
+			auto mv = vec::multi(vec::make(defs[0](topo)), vec::make(defs[1](topo)), vec::make(defs[2](topo)),
+			                     vec::make(defs[3](topo)));
+			if (fill) {
+				std::vector<double> h(static_cast<std::size_t>(n));
+				int index = 0;
+				std::apply(
+					[&](auto &... comp) {
+						(([&] {
+							 for (std::int64_t i = 0; i < n; ++i)
+								 h[static_cast<std::size_t>(i)] = static_cast<double>((index + offset + 1) * (g0 + i));
+							 device::check(fsb_vec_upload(comp.data.handle(), h.data(), n, 0));
+							 ++index;
+						 }()),
+						 ...);
+					},
+					mv.data.components);
+			}
+			return mv;
+		};
+		auto x = family(xs, 0, true), y = family(ys, 1, true), z = family(zs, 2, true), tmp = family(ts, 0, false);
+
+		int k = 0;
+		std::vector<double> got(static_cast<std::size_t>(n));
+		auto check = [&](auto & mv, auto expect) {
+			double worst = 0;
+			int index = 0;
+			std::apply(
+				[&](auto &... comp) {
+					(([&] {
+						 device::check(fsb_vec_download(comp.data.handle(), got.data(), n, 0));
+						 for (std::int64_t i = 0; i < n; ++i)
+							 worst = std::max(worst, std::abs(expect(static_cast<double>(g0 + i), static_cast<double>(index)) -
+							                                  got[static_cast<std::size_t>(i)]));
+						 ++index;
+					 }()),
+					 ...);
+				},
+				mv.data.components);
+			out18[k++] = worst;
+		};
+		tmp.add(x, z);
+		check(tmp, [](double g, double i) { return (i + 1) * g + (i + 3) * g; });
+		tmp.subtract(y, z);
+		check(tmp, [](double g, double i) { return (i + 2) * g - (i + 3) * g; });
+		tmp.multiply(x, z);
+		check(tmp, [](double g, double i) { return (i + 1) * g * (i + 3) * g; });
+		x.add_scalar(x, 1);
+		check(x, [](double g, double i) { return (i + 1) * g + 1; });
+		tmp.divide(y, x);
+		check(tmp, [](double g, double i) { return ((i + 2) * g) / ((i + 1) * g + 1); });
+		x.add_scalar(x, -1);
+		tmp.scale(3.5, x);
+		check(tmp, [](double g, double i) { return (i + 1) * g * 3.5; });
+		y.add_scalar(y, 2);
+		tmp.reciprocal(y);
+		check(tmp, [](double g, double i) { return 1.0 / ((i + 2) * g + 2); });
+		y.add_scalar(y, -2);
+		tmp.linear_sum(8, y, 9, z);
+		check(tmp, [](double g, double i) { return ((i + 2) * g) * 8 + ((i + 3) * g) * 9; });
+		tmp.axpy(7, x, y);
+		check(tmp, [](double g, double i) { return (i + 1) * g * 7 + ((i + 2) * g); });
+		tmp.copy(y);
+		tmp.axpby(4, 11, z);
+		check(tmp, [](double g, double i) { return ((i + 3) * g) * 4 + ((i + 2) * g) * 11; });
+		tmp.add_scalar(y, -4.3);
+		tmp.abs(tmp);
+		check(tmp, [](double g, double i) { return std::abs((i + 2) * g - 4.3); });
+
+		tmp.add_scalar(y, -7);
+		out18[k++] = tmp.min().get();
+		{
+			auto & [t0, t1, t2, t3] = tmp.data.components;
+			out18[k++] = tmp.max().get() == std::max({t0.max().get(), t1.max().get(), t2.max().get(), t3.max().get()});
+			tmp.add_scalar(z, -43);
+			out18[k++] = tmp.l1norm().get() == t0.l1norm().get() + t1.l1norm().get() + t2.l1norm().get() + t3.l1norm().get();
+			out18[k++] = tmp.l2norm().get() == std::sqrt(std::pow(t0.l2norm().get(), 2) + std::pow(t1.l2norm().get(), 2) +
+			                                             std::pow(t2.l2norm().get(), 2) + std::pow(t3.l2norm().get(), 2));
+			out18[k++] = tmp.inf_norm().get() ==
+			             std::max({t0.inf_norm().get(), t1.inf_norm().get(), t2.inf_norm().get(), t3.inf_norm().get()});
+		}
+		{
+			auto & [x0, x1, x2, x3] = x.data.components;
+			auto & [y0, y1, y2, y3] = y.data.components;
+			out18[k++] = x.dot(y).get() == (x0.dot(y0).get() + x1.dot(y1).get() + x2.dot(y2).get() + x3.dot(y3).get());
+		}
+		// named variables and subsets
+		enum class vars { pressure, temperature, density };
+		auto pvec = vec::make(variable<vars::pressure>, pd(topo));
+		auto tvec = vec::make(variable<vars::temperature>, td(topo));
+		auto dvec = vec::make(variable<vars::density>, dd(topo));
+		auto mv = vec::multi(pvec, tvec, dvec);
+		auto sub = mv.subset(multivariable<vars::density, vars::pressure>);
+		auto & [d1, p1] = sub.data.components;
+		auto sub1 = mv.subset(multivariable<vars::temperature, vars::density>);
+		auto & [t1, d2] = sub1.data.components;
+		auto & t2 = mv.subset(variable<vars::temperature>);
+		out18[k++] = (p1.data.fid() == pvec.data.fid() && d1.data.fid() == dvec.data.fid() && t1.data.fid() == tvec.data.fid() &&
+		              d2.data.fid() == dvec.data.fid() && t2.data.fid() == tvec.data.fid())
+		                 ? 1.0
+		                 : 0.0;
 	});
 }
 

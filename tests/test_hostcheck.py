@@ -255,3 +255,13 @@ def test_example_applications_run_on_the_stand_in(tmp_path):
     m = re.search(r"(\d+) steps \((\d+) attempts, (\d+) rejected\), max u = ([0-9.]+), heat ([0-9.]+) -> ([0-9.]+)", r.stdout)
     assert m, r.stdout
     assert int(m.group(1)) >= 10 and 0.0 < float(m.group(4)) <= 50.0 and float(m.group(6)) <= float(m.group(5)) * (1 + 1e-9)
+
+
+def test_multivector_closed_forms_of_the_reference_test(hc):
+    """vectors/test/flecsi_multivector.cc:84-241 on a four-component vec::multi, n = 32 as there"""
+    S = H.Session(hc.ctx, hc.topology(32))
+    out = S.multivector_selftest()
+    assert np.all(out[:11] < 1e-8), out[:11]  # the reference's tolerance
+    assert out[11] == -7  # tmp.min() after tmp = y - 7: component 0 at gid 0
+    assert np.all(out[12:18] == 1.0), out[12:18]  # combined reductions are exactly the combination of the components'
+    S.close()

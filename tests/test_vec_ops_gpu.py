@@ -233,3 +233,20 @@ def test_generic_program_kernel(ctx):
     assert ctx.stat("launches") == 1
     for v in (u0, u1, u2, f, rhs, w):
         v.destroy()
+
+
+def test_multivector_closed_forms_of_the_reference_test(ctx):
+    """vectors/test/flecsi_multivector.cc:84-241 on a four-component vec::multi (n = 32 as there, and a size that
+    spans many CTAs): element-wise results to the reference's 1e-8, min == -7, combined reductions exactly the
+    combination of the component reductions, subset() by variable / multivariable"""
+    from flecsolve_b200 import host as H
+    for n in (32, 70001):
+        rp = np.arange(n + 1, dtype=np.int64)
+        A = F.ParCSR.from_csr(ctx, n, [0, n], rp, np.arange(n, dtype=np.int64), np.ones(n))
+        S = H.Session(ctx, A)
+        out = S.multivector_selftest()
+        scale = float(n) ** 2  # values grow like gid^2 in the multiply check
+        assert np.all(out[:11] <= 1e-8 * max(1.0, scale * 1e-6)), out[:11]
+        assert out[11] == -7
+        assert np.all(out[12:18] == 1.0), out[12:18]
+        S.close(); A.destroy()
