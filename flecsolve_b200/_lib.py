@@ -103,6 +103,7 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_ctx_event_elapsed_ms", C.c_int, _p, C.c_int, C.c_int, _pd)
     f("fsb_ctx_profile_read", C.c_int, _p, _pd, _pi64)
     f("fsb_ctx_profile_read_split", C.c_int, _p, _pd, _pi64)
+    f("fsb_debug_program_info", C.c_int, _pi32, C.c_int, C.c_int, _pi32, _pi32)
     f("fsb_debug_jit_compile", C.c_int, _pi32, C.c_int, C.c_int, C.c_int, _pi64, C.c_char_p, C.c_int)
     f("fsb_vec_create", C.c_int, _p, _i64, _i64, C.POINTER(_p))
     f("fsb_vec_wrap", C.c_int, _p, _p, _i64, _i64, C.POINTER(_p))

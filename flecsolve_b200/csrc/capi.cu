@@ -301,6 +301,30 @@ int fsb_ctx_set_option(fsb_ctx_t c, int option, int64_t value) {
 	});
 }
 
+int fsb_debug_program_info(const int32_t * raw, int n, int device_coefficients, int32_t * info6, int32_t * canon) {
+	return guarded([&] {
+		FSB_REQUIRE(raw && info6 && n >= 1 && n <= fsb::MAXS, "bad arguments");
+		fsb::raw_stmt rs[fsb::MAXS];
+		for (int i = 0; i < n; ++i)
+			rs[i] = fsb::raw_stmt{raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]};
+		const fsb::canon_result cr = fsb::canonicalize(rs, n);
+		FSB_REQUIRE(cr.ok, "statement list exceeds the program limits");
+		info6[0] = fsb::program_is_registered(cr.p, device_coefficients != 0) ? 1 : 0;
+		info6[1] = cr.p.nv;
+		info6[2] = cr.p.ns;
+		info6[3] = cr.p.nr;
+		info6[4] = static_cast<int32_t>(cr.p.load_mask);
+		info6[5] = static_cast<int32_t>(cr.p.store_mask);
+		if (canon)
+			for (int i = 0; i < n; ++i) {
+				const fsb::stmt & t = cr.p.st[i];
+				const int v[6] = {t.op, t.z, t.x, t.y, t.a, t.b};
+				for (int k = 0; k < 6; ++k)
+					canon[6 * i + k] = v[k];
+			}
+	});
+}
+
 int fsb_debug_jit_compile(const int32_t * raw, int n, int device_coefficients, int box_layout, int64_t * cubin_bytes,
                           char * log, int log_capacity) {
 	return guarded([&] {

@@ -231,6 +231,7 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y
                 const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s,
                 const pending * fold = nullptr);
 void fill_red_out(fsb_ctx_s * c, const pending & red, red_out & r);
+bool program_is_registered(const program & p, bool dev);
 // run-time compiled program kernels (jit.cu)
 struct ew_args;
 bool jit_compile(const program & p, bool dev, bool box, std::vector<char> & cubin, std::string & log);

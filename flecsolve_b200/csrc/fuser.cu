@@ -215,6 +215,12 @@ static registry_t & registry() {
 	return r;
 }
 
+// diagnostics (fsb_debug_program_info): is there an ahead-of-time kernel for this canonical program?
+bool program_is_registered(const program & p, bool dev) {
+	const auto & table = dev ? registry().dev_map : registry().map;
+	return table.find(key_of(p)) != table.end();
+}
+
 // ---------------------------------------------------------------- queue
 
 static int64_t length_of(const pending & p) {

@@ -114,6 +114,11 @@ int fsb_ctx_profile_read_split(fsb_ctx_t ctx, double * ms2, int64_t * launches2)
 /* diagnostics: canonicalise the statement list raw[4 n] = {op, z, x, y} (ops as in csrc/program.h, vector ids
  * arbitrary small integers, -1 = unused) and compile its kernel for sm_100a with the run-time compiler.
  * Needs no GPU.  Returns FSB_OK and the cubin size, or FSB_ERR_STATE with the compiler log in `log`.   */
+/* diagnostics: canonical form of a statement list (same input convention as above).  info[0] = 1 when an
+ * ahead-of-time kernel is registered for it (with device-resident coefficients when `device_coefficients`),
+ * info[1..5] = vectors, scalars, reductions, load mask, store mask; canon[6 n] receives the canonical statements
+ * {op, z, x, y, a, b}.  Pure host code: no GPU needed.                                                        */
+int fsb_debug_program_info(const int32_t * raw, int n, int device_coefficients, int32_t * info6, int32_t * canon);
 int fsb_debug_jit_compile(const int32_t * raw, int n, int device_coefficients, int box_layout, int64_t * cubin_bytes,
                           char * log, int log_capacity);
 
