@@ -182,6 +182,21 @@ FSB_PROGRAM(p_bicg2_update, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), S_LIN2(1, 4, 1), S
 FSB_PROGRAM(p_bicg2_dir_copy, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), S_LIN2(1, 4, 1), S_LIN2(3, 5, 3), S_SCALE(6, 1),
             S_SCALE(7, 3))
 
+// Groups found by replaying the drivers' call traces through the queue's grouping rules
+// (scripts/statement_groups.py -> profiles/r1_statement_groups.txt): once per iteration each.
+// bicgstab.hh:132-134 on two components: s = -a v + res per component ; |s|^2 per component
+FSB_PROGRAM(p_bicg2_half, S_LIN2(2, 0, 1), S_LIN2(5, 3, 4), R_DOT(5, 5), R_DOT(2, 2))
+// cg.hh:108-111 on two components: x += a p ; r -= a w (both) ; |r|^2 (both)
+FSB_PROGRAM(p_cg2_update, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), S_LIN2(5, 4, 5), S_LIN2(7, 6, 7), R_DOT(7, 7), R_DOT(5, 5))
+// cg.hh:124-127 on two components, identity preconditioner: z = r (both) ; r.z (both)
+FSB_PROGRAM(p_cg2_copy_dot, S_SCALE(1, 0), S_SCALE(3, 2), R_DOT(2, 3), R_DOT(0, 1))
+// fcg (cg.hh:196-203): d = -g/rho d + v ; q = -g/rho q + w ; u += a/rho d ; r -= a/rho q ; |r|^2
+FSB_PROGRAM(p_fcg_update, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), S_LIN2(4, 1, 4), S_LIN2(5, 3, 5), R_DOT(5, 5))
+// bdf.hh source term + residual norm of the inner solve's right-hand side: two aliased axpys and a norm
+FSB_PROGRAM(p_axpy2_same_sumsq, S_LIN2(1, 0, 1), S_LIN2(1, 2, 1), R_DOT(1, 1))
+// bdf.hh:763-801 scaled truncation-error norm: max | (u - u_pred) / (rtol |u| + atol) |
+FSB_PROGRAM(p_bdf_error_norm, S_SCALE(1, 0), S_SCALE(2, 0), S_ADDS(2, 2), S_LIN2(4, 0, 3), S_DIV(4, 4, 2), R_AMAX(4))
+
 // Device-scalar CG (solvers/cg_device.hh): no host read separates the update from the preconditioner, so
 //   x = a p + x ; r = -a w + r ; |r|^2 ; z = dinv * r ; r.z     is ONE pass (64 B/row)
 FSB_PROGRAM(p_cgdev_update_jacobi, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), R_DOT(3, 3), S_MUL(5, 4, 3), R_DOT(3, 5))
@@ -208,6 +223,8 @@ static registry_t & registry() {
 		g.add<p_dot2>(); g.add<p_mul_sumsq>(); g.add<p_sumsq2>(); g.add<p_dot_dot>();
 		g.add<p_lin2_lin2>(); g.add<p_scale2>(); g.add<p_set2>();
 		g.add<p_bicg2_s>(); g.add<p_bicg2_update>(); g.add<p_bicg2_dir_copy>();
+		g.add<p_bicg2_half>(); g.add<p_cg2_update>(); g.add<p_cg2_copy_dot>(); g.add<p_fcg_update>();
+		g.add<p_axpy2_same_sumsq>(); g.add<p_bdf_error_norm>();
 		g.add_dev<p_cgdev_update_jacobi>(); g.add_dev<p_cgdev_update_copy>(); g.add_dev<p_lin2_zy>();
 		g.add_dev<p_cg_update>(); g.add_dev<p_axpy2>();
 		return g;

@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <limits>
@@ -53,6 +55,26 @@ struct fsb_parcsr_s {
 };
 
 namespace {
+// FSB_STANDIN_TRACE=<file>: append one line per C-ABI call that the real library would queue or that flushes its
+// queue, so that tests/hostcheck/groups.py can replay the fuser's grouping on the host (which statement groups
+// does a solver produce, and do they have ahead-of-time kernels?)
+FILE * trace_file() {
+	static FILE * f = [] {
+		const char * p = std::getenv("FSB_STANDIN_TRACE");
+		return p ? std::fopen(p, "a") : nullptr;
+	}();
+	return f;
+}
+std::intptr_t tid(const void * p) { return reinterpret_cast<std::intptr_t>(p); }
+extern bool g_quiet;
+void trace_ew(int op, const fsb_vec_s * z, const fsb_vec_s * x, const fsb_vec_s * y, bool dev = false);
+void trace_red(int op, const fsb_vec_s * x, const fsb_vec_s * y, int store);
+void trace_mark(const char * what) {
+	if (FILE * f = trace_file()) {
+		std::fprintf(f, "%s\n", what);
+		std::fflush(f);
+	}
+}
 thread_local std::string g_error;
 int fail(int code, const char * msg) {
 	g_error = msg;
@@ -62,6 +84,18 @@ bool same_space(const fsb_vec_s * a, const fsb_vec_s * b) {
 	return a->ctx == b->ctx && a->n == b->n && a->box == b->box && a->map == b->map;
 }
 bool skip(fsb_ctx_s * c) { return c->armed && c->halted; }
+bool g_quiet = false;
+void trace_ew(int op, const fsb_vec_s * z, const fsb_vec_s * x, const fsb_vec_s * y, bool dev) {
+	if (g_quiet)
+		return;
+	if (FILE * f = trace_file())
+		std::fprintf(f, "EW %d %ld %ld %ld %ld %d\n", op, (long)tid(z), (long)tid(x), (long)tid(y), (long)z->n,
+		             (dev || z->ctx->armed) ? 1 : 0);
+}
+void trace_red(int op, const fsb_vec_s * x, const fsb_vec_s * y, int store) {
+	if (FILE * f = trace_file())
+		std::fprintf(f, "RED %d %ld %ld %ld %d %d\n", op, (long)tid(x), (long)tid(y), (long)x->n, store, x->ctx->armed ? 1 : 0);
+}
 
 template<class F>
 int each(fsb_vec_t z, F && f) {
@@ -109,21 +143,32 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 	delete c;
 	return FSB_OK;
 }
-int fsb_ctx_flush(fsb_ctx_t) { return FSB_OK; }
-int fsb_ctx_sync(fsb_ctx_t) { return FSB_OK; }
+int fsb_ctx_flush(fsb_ctx_t) {
+	trace_mark("FLUSH");
+	return FSB_OK;
+}
+int fsb_ctx_sync(fsb_ctx_t) {
+	trace_mark("FLUSH");
+	return FSB_OK;
+}
 int fsb_ctx_rank(fsb_ctx_t) { return 0; }
 int fsb_ctx_nranks(fsb_ctx_t) { return 1; }
 int fsb_ctx_get_stat(fsb_ctx_t c, int s, int64_t * out) {
 	*out = c->stats[s & 7];
 	return FSB_OK;
 }
-int fsb_ctx_event_record(fsb_ctx_t, int) { return FSB_OK; }
+int fsb_ctx_event_record(fsb_ctx_t, int) {
+	trace_mark("FLUSH");
+	return FSB_OK;
+}
 int fsb_ctx_halt_arm(fsb_ctx_t c) {
+	trace_mark("FLUSH");
 	c->armed = true;
 	c->halted = false;
 	return FSB_OK;
 }
 int fsb_ctx_halt_disarm(fsb_ctx_t c, int * was) {
+	trace_mark("FLUSH");
 	if (was)
 		*was = c->halted ? 1 : 0;
 	c->armed = c->halted = false;
@@ -170,11 +215,13 @@ int fsb_vec_destroy(fsb_vec_t v) {
 int64_t fsb_vec_local_size(fsb_vec_t v) { return v->n; }
 int64_t fsb_vec_ghost_size(fsb_vec_t v) { return v->n_ghost; }
 int fsb_vec_upload(fsb_vec_t v, const double * h, int64_t n, int64_t off) {
+	trace_mark("FLUSH");
 	for (int64_t k = 0; k < n; ++k)
 		v->at(off + k) = h[k];
 	return FSB_OK;
 }
 int fsb_vec_download(fsb_vec_t v, double * h, int64_t n, int64_t off) {
+	trace_mark("FLUSH");
 	for (int64_t k = 0; k < n; ++k)
 		h[k] = v->at(off + k);
 	return FSB_OK;
@@ -190,70 +237,91 @@ int fsb_vec_global_size(fsb_vec_t v, int64_t * out) {
 
 int fsb_vec_copy(fsb_vec_t z, fsb_vec_t x) {
 	NEED_SAME(z, x);
+	if (z != x)
+		trace_ew(1, z, x, nullptr);
 	return each(z, [&](int64_t k) { z->at(k) = x->at(k); });
 }
 int fsb_vec_set(fsb_vec_t z, double a) {
+	trace_ew(0, z, nullptr, nullptr);
 	return each(z, [&](int64_t k) { z->at(k) = a; });
 }
 int fsb_vec_scale(fsb_vec_t z, double a, fsb_vec_t x) {
 	NEED_SAME(z, x);
+	trace_ew(1, z, x, nullptr);
 	return each(z, [&](int64_t k) { z->at(k) = x->at(k) * a; });
 }
 int fsb_vec_add(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y) {
 	NEED_SAME(z, x);
 	NEED_SAME(z, y);
+	trace_ew(2, z, x, y);
 	return each(z, [&](int64_t k) { z->at(k) = x->at(k) + y->at(k); });
 }
 int fsb_vec_sub(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y) {
 	NEED_SAME(z, x);
 	NEED_SAME(z, y);
+	trace_ew(2, z, x, y);
 	return each(z, [&](int64_t k) { z->at(k) = x->at(k) - y->at(k); });
 }
 int fsb_vec_mul(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y) {
 	NEED_SAME(z, x);
 	NEED_SAME(z, y);
+	trace_ew(3, z, x, y);
 	return each(z, [&](int64_t k) { z->at(k) = x->at(k) * y->at(k); });
 }
 int fsb_vec_div(fsb_vec_t z, fsb_vec_t x, fsb_vec_t y) {
 	NEED_SAME(z, x);
 	NEED_SAME(z, y);
+	trace_ew(4, z, x, y);
 	return each(z, [&](int64_t k) { z->at(k) = x->at(k) / y->at(k); });
 }
 int fsb_vec_recip(fsb_vec_t z, fsb_vec_t x) {
 	NEED_SAME(z, x);
+	trace_ew(5, z, x, nullptr);
 	return each(z, [&](int64_t k) { z->at(k) = 1.0 / x->at(k); });
 }
 int fsb_vec_linear_sum(fsb_vec_t z, double a, fsb_vec_t x, double b, fsb_vec_t y) {
 	NEED_SAME(z, x);
 	NEED_SAME(z, y);
+	trace_ew(2, z, x, y);
 	return each(z, [&](int64_t k) { z->at(k) = a * x->at(k) + b * y->at(k); });
 }
 int fsb_vec_linear_sum_c(fsb_vec_t z, fsb_coef a, fsb_vec_t x, fsb_coef b, fsb_vec_t y) {
 	NEED_SAME(z, x);
 	NEED_SAME(z, y);
-	if (skip(z->ctx)) // coefficients of a halted solve may be meaningless (0/0): do not even form them
+	trace_ew(2, z, x, y, a.num != 0 || a.den != 0 || b.num != 0 || b.den != 0);
+	g_quiet = true;
+	if (skip(z->ctx)) { // coefficients of a halted solve may be meaningless (0/0): do not even form them
+		g_quiet = false;
 		return FSB_OK;
-	return fsb_vec_linear_sum(z, coef(z->ctx, a), x, coef(z->ctx, b), y);
+	}
+	const int rc = fsb_vec_linear_sum(z, coef(z->ctx, a), x, coef(z->ctx, b), y);
+	g_quiet = false;
+	return rc;
 }
 // a x + y: the reference's axpy body has no multiplication on y (topo_tasks.hh:174-191); 1.0 * y is exact anyway
 int fsb_vec_axpy(fsb_vec_t z, double a, fsb_vec_t x, fsb_vec_t y) {
 	NEED_SAME(z, x);
 	NEED_SAME(z, y);
+	trace_ew(2, z, x, y);
 	return each(z, [&](int64_t k) { z->at(k) = a * x->at(k) + y->at(k); });
 }
 int fsb_vec_axpby(fsb_vec_t z, double a, double b, fsb_vec_t x) {
 	NEED_SAME(z, x);
+	trace_ew(2, z, x, z);
 	return each(z, [&](int64_t k) { z->at(k) = a * x->at(k) + b * z->at(k); });
 }
 int fsb_vec_abs(fsb_vec_t z, fsb_vec_t x) {
 	NEED_SAME(z, x);
+	trace_ew(6, z, x, nullptr);
 	return each(z, [&](int64_t k) { z->at(k) = std::fabs(x->at(k)); });
 }
 int fsb_vec_add_scalar(fsb_vec_t z, fsb_vec_t x, double a) {
 	NEED_SAME(z, x);
+	trace_ew(7, z, x, nullptr);
 	return each(z, [&](int64_t k) { z->at(k) = x->at(k) + a; });
 }
 int fsb_vec_set_random(fsb_vec_t z, unsigned seed) {
+	trace_mark("FLUSH");
 	std::mt19937 gen(seed);
 	std::uniform_real_distribution<double> dis(0., 1.);
 	for (int64_t k = 0; k < z->n; ++k)
@@ -261,6 +329,7 @@ int fsb_vec_set_random(fsb_vec_t z, unsigned seed) {
 	return FSB_OK;
 }
 int fsb_vec_dump(fsb_vec_t x, const char * prefix) {
+	trace_mark("FLUSH");
 	std::ofstream f(std::string(prefix) + "-0");
 	for (int64_t k = 0; k < x->n; ++k)
 		f << x->at(k) << '\n';
@@ -277,16 +346,22 @@ static double dot_of(fsb_vec_t x, fsb_vec_t y) {
 }
 int fsb_vec_dot(fsb_vec_t x, fsb_vec_t y, fsb_token_t * t) {
 	NEED_SAME(x, y);
+	trace_red(16, x, y, 0);
 	return finish(x->ctx, dot_of(x, y), t);
 }
 int fsb_vec_dot_opts(fsb_vec_t x, fsb_vec_t y, const fsb_red_opts * o, fsb_token_t * t) {
 	NEED_SAME(x, y);
+	trace_red(16, x, y, o ? o->store : 0);
 	if (skip(x->ctx))
 		return finish(x->ctx, 0.0, t); // nothing is stored or tested after the halt
 	return finish(x->ctx, dot_of(x, y), t, o);
 }
-int fsb_vec_sumsq(fsb_vec_t x, fsb_token_t * t) { return finish(x->ctx, dot_of(x, x), t); }
+int fsb_vec_sumsq(fsb_vec_t x, fsb_token_t * t) {
+	trace_red(16, x, x, 0);
+	return finish(x->ctx, dot_of(x, x), t);
+}
 int fsb_vec_asum(fsb_vec_t x, fsb_token_t * t) {
+	trace_red(17, x, nullptr, 0);
 	double s = 0.0;
 	if (!skip(x->ctx))
 		for (int64_t k = 0; k < x->n; ++k)
@@ -294,6 +369,7 @@ int fsb_vec_asum(fsb_vec_t x, fsb_token_t * t) {
 	return finish(x->ctx, s, t);
 }
 int fsb_vec_powsum(fsb_vec_t x, int p, fsb_token_t * t) {
+	trace_red(21, x, nullptr, 0);
 	double s = 0.0;
 	if (!skip(x->ctx))
 		for (int64_t k = 0; k < x->n; ++k)
@@ -301,6 +377,7 @@ int fsb_vec_powsum(fsb_vec_t x, int p, fsb_token_t * t) {
 	return finish(x->ctx, s, t);
 }
 int fsb_vec_amax(fsb_vec_t x, fsb_token_t * t) {
+	trace_red(18, x, nullptr, 0);
 	double s = -std::numeric_limits<double>::infinity();
 	if (!skip(x->ctx))
 		for (int64_t k = 0; k < x->n; ++k)
@@ -308,6 +385,7 @@ int fsb_vec_amax(fsb_vec_t x, fsb_token_t * t) {
 	return finish(x->ctx, s, t);
 }
 int fsb_vec_min(fsb_vec_t x, fsb_token_t * t) {
+	trace_red(19, x, nullptr, 0);
 	double s = std::numeric_limits<double>::infinity();
 	if (!skip(x->ctx))
 		for (int64_t k = 0; k < x->n; ++k)
@@ -315,6 +393,7 @@ int fsb_vec_min(fsb_vec_t x, fsb_token_t * t) {
 	return finish(x->ctx, s, t);
 }
 int fsb_vec_max(fsb_vec_t x, fsb_token_t * t) {
+	trace_red(20, x, nullptr, 0);
 	double s = -std::numeric_limits<double>::infinity();
 	if (!skip(x->ctx))
 		for (int64_t k = 0; k < x->n; ++k)
@@ -322,12 +401,16 @@ int fsb_vec_max(fsb_vec_t x, fsb_token_t * t) {
 	return finish(x->ctx, s, t);
 }
 int fsb_red_get(fsb_ctx_t c, fsb_token_t t, double * out) {
+	trace_mark("FLUSH");
 	if (t <= 0 || t >= static_cast<fsb_token_t>(c->results.size()))
 		return fail(FSB_ERR_ARG, "unknown reduction token");
 	*out = c->results[static_cast<size_t>(t)];
 	return FSB_OK;
 }
-int fsb_red_wait(fsb_ctx_t, fsb_token_t) { return FSB_OK; }
+int fsb_red_wait(fsb_ctx_t, fsb_token_t) {
+	trace_mark("FLUSH");
+	return FSB_OK;
+}
 
 // ---- device scalars
 int fsb_scalar_create(fsb_ctx_t c, fsb_scalar_t * out) {
@@ -344,10 +427,12 @@ int fsb_scalar_destroy(fsb_ctx_t c, fsb_scalar_t s) {
 	return FSB_OK;
 }
 int fsb_scalar_set(fsb_ctx_t c, fsb_scalar_t s, double v) {
+	trace_mark("FLUSH");
 	c->scalars[s] = v;
 	return FSB_OK;
 }
 int fsb_scalar_get(fsb_ctx_t c, fsb_scalar_t s, double * out) {
+	trace_mark("FLUSH");
 	*out = c->scalars[s];
 	return FSB_OK;
 }
@@ -442,6 +527,8 @@ int fsb_parcsr_spmv(fsb_parcsr_t A, fsb_vec_t x, fsb_vec_t y) {
 		return fail(FSB_ERR_ARG, "spmv: x and y must be different vectors");
 	if (x->n != A->n || y->n != A->n || x->box != A->box || y->box != A->box)
 		return fail(FSB_ERR_ARG, "spmv: vector does not fit the matrix");
+	if (FILE * f = trace_file())
+		std::fprintf(f, "SPMV %ld %ld %ld\n", (long)tid(x), (long)tid(y), (long)x->n);
 	for (int64_t r = 0; r < A->n; ++r) {
 		double s = 0.0;
 		for (int64_t p = A->rowptr[r]; p < A->rowptr[r + 1]; ++p)
@@ -451,6 +538,7 @@ int fsb_parcsr_spmv(fsb_parcsr_t A, fsb_vec_t x, fsb_vec_t y) {
 	return FSB_OK;
 }
 int fsb_parcsr_extract_dinv(fsb_parcsr_t A, fsb_vec_t d) {
+	trace_mark("FLUSH");
 	if (A->box)
 		return fail(FSB_ERR_ARG, "extract_dinv: not available for structured-grid operators");
 	for (int64_t r = 0; r < A->n; ++r) {
