@@ -49,6 +49,13 @@ KRYLOV_GROUPS = {
     "bicgstab direction + identity": ([(LIN2, p, v, p), (LIN2, p, r, p), (SCALE, ph, p, -1)], False),
     "bicgstab half step": ([(LIN2, s, v, r), (DOT, -1, s, s)], False),
     "bicgstab update": ([(LIN2, x, ph, x), (LIN2, x, sh, x), (LIN2, r, t, s), (DOT, -1, r, r)], False),
+    # the same loops on a two-component vec::multi (every call fans out per component; reductions per component)
+    "cg update, 2 components": ([(LIN2, x, p, x), (LIN2, 20 + x, 20 + p, 20 + x), (LIN2, r, w, r), (LIN2, 20 + r, 20 + w, 20 + r),
+                                 (DOT, -1, 20 + r, 20 + r), (DOT, -1, r, r)], False),
+    "cg identity + r.z, 2 components": ([(SCALE, z, r, -1), (SCALE, 20 + z, 20 + r, -1), (DOT, -1, 20 + r, 20 + z), (DOT, -1, r, z)], False),
+    "bicgstab half step, 2 components": ([(LIN2, s, v, r), (LIN2, 20 + s, 20 + v, 20 + r), (DOT, -1, 20 + s, 20 + s), (DOT, -1, s, s)], False),
+    # fcg: d, q recurrences + iterate and residual updates + norm
+    "fcg update": ([(LIN2, 30, v, 30), (LIN2, 31, w, 31), (LIN2, x, 30, x), (LIN2, r, 31, r), (DOT, -1, r, r)], False),
 }
 
 
