@@ -58,3 +58,31 @@ def test_product_does_not_import_oracle():
                 if "import oracle" in txt or "from oracle" in txt or "liboracle" in txt:
                     bad.append(os.path.join(base, f))
     assert not bad, bad
+
+
+def test_documents_name_real_entry_points():
+    """every fsb_* / fsbh_* function INTEGRATION.md, DESIGN.md and README.md mention exists"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set(F.declared_symbols()) | {"fsb_ctx_s", "fsb_vec_s", "fsb_parcsr_s", "fsb_status", "fsb_option", "fsb_stat",
+                                            "fsb_coef", "fsb_red_opts", "fsb_scalar_t", "fsb_token_t", "fsb_ctx_t", "fsb_vec_t",
+                                            "fsb_parcsr_t"}
+    driver = open(os.path.join(root, "flecsolve_b200", "host", "driver.cpp")).read()
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        text = open(os.path.join(root, doc)).read()
+        for name in set(re.findall(r"\bfsb_[a-z0-9_]+\b", text)):
+            if name.endswith("_") or name in ("fsb_vec_", "fsb_scalar_"):
+                continue  # prefixes such as `fsb_vec_*`
+            assert name in declared, f"{doc} mentions {name}, which include/fsb.h does not declare"
+        for name in set(re.findall(r"\bfsbh_[a-z0-9_]+\b", text)):
+            assert f"int {name}(" in driver or f"{name}(" in driver, f"{doc} mentions {name}, which the driver does not define"
+
+
+def test_test_infrastructure_stays_out_of_the_product():
+    """the CPU stand-in for the C ABI (tests/hostcheck) is for the test suite only"""
+    root = os.path.dirname(F.LIB_PATH)
+    for base, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hh", ".cpp", ".inc")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "hostcheck" not in txt and "fsb_cpu_standin" not in txt, os.path.join(base, f)
