@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import oracle as O
+from flecsolve_b200 import _lib as F
 
 pytestmark = pytest.mark.gpu
 
