@@ -14,6 +14,9 @@ def pytest_configure(config):
     # make sure the native pieces exist (no-op when up to date; nvcc cross-compiles without a GPU)
     from flecsolve_b200 import build
     build.build_all()
+    # the drop-in proof library (reference headers over the device policies): needs /root/reference, no-op elsewhere
+    from tests.dropin import build as dropin_build
+    dropin_build.main()
 
 
 def _device_count() -> int:
