@@ -103,6 +103,7 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_ctx_event_elapsed_ms", C.c_int, _p, C.c_int, C.c_int, _pd)
     f("fsb_ctx_profile_read", C.c_int, _p, _pd, _pi64)
     f("fsb_ctx_profile_read_split", C.c_int, _p, _pd, _pi64)
+    f("fsb_ctx_timeline_read", C.c_int, _p, C.POINTER(C.c_uint64), _i64, _pi64)
     f("fsb_debug_program_info", C.c_int, _pi32, C.c_int, C.c_int, _pi32, _pi32)
     f("fsb_debug_jit_compile", C.c_int, _pi32, C.c_int, C.c_int, C.c_int, _pi64, C.c_char_p, C.c_int)
     f("fsb_vec_create", C.c_int, _p, _i64, _i64, C.POINTER(_p))
@@ -151,6 +152,7 @@ def _declare(L: C.CDLL) -> None:
     for n in ("local_rows", "global_rows", "num_ghosts", "row_begin"):
         f(f"fsb_parcsr_{n}", _i64, _p)
     f("fsb_parcsr_local_nnz", _i64, _p, C.c_int)
+    f("fsb_parcsr_info", _i64, _p, C.c_int)
     f("fsb_parcsr_download", C.c_int, _p, C.c_int, _pi64, _pi32, _pd)
     f("fsb_parcsr_download_colmap", C.c_int, _p, _pi64)
     f("fsb_parcsr_spmv", C.c_int, _p, _p, _p)
@@ -174,7 +176,8 @@ def device_count() -> int:
 
 STAT = {"launches": 0, "fused_statements": 1, "halo_exchanges": 2, "allreduces": 3, "host_syncs": 4,
         "unmatched_groups": 5, "wait_ns": 6, "flush_ns": 7, "jit_groups": 8}
-OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3, "profile": 4, "reproducible": 5, "jit": 6}
+OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3, "profile": 4, "reproducible": 5, "jit": 6,
+       "timeline": 7}
 
 
 class Context:
@@ -212,6 +215,14 @@ class Context:
         out = _dbl()
         check(lib().fsb_ctx_event_elapsed_ms(self.h, a, b, C.byref(out)))
         return out.value
+
+    def timeline_read(self, max_slots: int = 65536):
+        """the device-side timeline since the last read: uint64 array [launch, 16] (see fsb_ctx_timeline_read in fsb.h);
+        needs set_option('timeline', capacity)"""
+        buf = np.zeros((max_slots, 16), dtype=np.uint64)
+        n = C.c_int64()
+        check(lib().fsb_ctx_timeline_read(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), max_slots, C.byref(n)))
+        return buf[:n.value].copy()
 
     def profile_read_split(self):
         """((diag ms, offd ms), (diag launches, offd launches)) since the last read."""
@@ -422,6 +433,10 @@ class ParCSR:
     @property
     def row_begin(self): return lib().fsb_parcsr_row_begin(self.h)
     def nnz(self, which=0): return lib().fsb_parcsr_local_nnz(self.h, which)
+
+    INFO = {"window_format": 0, "row_blocks": 1, "window_x": 2, "fused_halo": 3, "wide_offsets": 4}
+
+    def info(self, key: str) -> int: return lib().fsb_parcsr_info(self.h, self.INFO[key])
 
     def vector(self, data=None) -> Vector:
         return self.ctx.vector(self.local_rows, self.num_ghosts, data)

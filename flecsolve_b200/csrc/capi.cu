@@ -23,6 +23,25 @@ void fsb_parcsr_jacobi_relax_impl(fsb_parcsr_s *, double, int64_t, fsb_vec_s *, 
 namespace fsb {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string & m) { g_last_error = m; }
+
+// the host only hands out slots (and stamps the kind); the kernels write the times
+unsigned long long * timeline_slot(fsb_ctx_s * c, int kind) {
+	if (!c->d_timeline || c->timeline_used >= c->timeline_cap)
+		return nullptr;
+	unsigned long long * slot = c->d_timeline + c->timeline_used * TL_WORDS;
+	c->timeline_kind.push_back(kind); // merged into word 2 when the timeline is read: no extra work on the stream
+	++c->timeline_used;
+	return slot;
+}
+
+static void timeline_reset(fsb_ctx_s * c) {
+	std::vector<unsigned long long> init(static_cast<size_t>(c->timeline_cap) * TL_WORDS, 0ull);
+	for (int64_t i = 0; i < c->timeline_cap; ++i)
+		init[i * TL_WORDS + 0] = init[i * TL_WORDS + 4] = init[i * TL_WORDS + 6] = ~0ull;
+	FSB_CUDA(cudaMemcpy(c->d_timeline, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+	c->timeline_used = 0;
+	c->timeline_kind.clear();
+}
 } // namespace fsb
 
 // run `body`, translate exceptions into status codes
@@ -176,12 +195,11 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 		}
 		FSB_CUDA(cudaMalloc(&c->d_halt, sizeof(int)));
 		FSB_CUDA(cudaMemset(c->d_halt, 0, sizeof(int)));
-		FSB_CUDA(cudaHostAlloc(&c->h_results, sizeof(double) * FSB_RED_RING, cudaHostAllocMapped));
-		FSB_CUDA(cudaHostAlloc(&c->h_flags, sizeof(int64_t) * FSB_RED_RING, cudaHostAllocMapped));
+		FSB_CUDA(cudaHostAlloc(&c->h_results, sizeof(double) * FSB_RED_RING, cudaHostAllocDefault));
+		FSB_CUDA(cudaHostAlloc(&c->h_ll, sizeof(fsb::ll_word) * FSB_RED_RING, cudaHostAllocMapped));
 		std::memset(c->h_results, 0, sizeof(double) * FSB_RED_RING);
-		std::memset(c->h_flags, 0, sizeof(int64_t) * FSB_RED_RING);
-		FSB_CUDA(cudaHostGetDevicePointer(&c->h_results_dev, c->h_results, 0));
-		FSB_CUDA(cudaHostGetDevicePointer(&c->h_flags_dev, c->h_flags, 0));
+		std::memset(c->h_ll, 0, sizeof(fsb::ll_word) * FSB_RED_RING);
+		FSB_CUDA(cudaHostGetDevicePointer(&c->h_ll_dev, c->h_ll, 0));
 		c->token_op.assign(FSB_RED_RING, 0);
 		c->token_event.resize(FSB_RED_RING, nullptr);
 		if (nranks > 1) {
@@ -243,8 +261,9 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 		cudaFree(c->d_scalars);
 		cudaFree(c->d_halt);
 		cudaFree(c->d_flush);
+		cudaFree(c->d_timeline);
 		cudaFreeHost(c->h_results);
-		cudaFreeHost(c->h_flags);
+		cudaFreeHost(c->h_ll);
 		cudaEventDestroy(c->ev_main);
 		cudaEventDestroy(c->ev_comm);
 		cudaStreamDestroy(c->stream);
@@ -294,6 +313,16 @@ int fsb_ctx_set_option(fsb_ctx_t c, int option, int64_t value) {
 			break;
 		case FSB_OPT_JIT:
 			c->jit = value != 0;
+			break;
+		case FSB_OPT_TIMELINE:
+			FSB_CUDA(cudaStreamSynchronize(c->stream));
+			cudaFree(c->d_timeline);
+			c->d_timeline = nullptr;
+			c->timeline_cap = value > 0 ? value : 0;
+			if (value > 0) {
+				FSB_CUDA(cudaMalloc(&c->d_timeline, static_cast<size_t>(value) * TL_WORDS * sizeof(unsigned long long)));
+				timeline_reset(c);
+			}
 			break;
 		default:
 			throw fsb::error(FSB_ERR_ARG, "unknown option");
@@ -411,6 +440,24 @@ int fsb_ctx_profile_read_split(fsb_ctx_t c, double * ms2, int64_t * launches2) {
 	});
 }
 
+int fsb_ctx_timeline_read(fsb_ctx_t c, uint64_t * out, int64_t max_slots, int64_t * n_slots) {
+	return guarded([&] {
+		FSB_REQUIRE(c && n_slots, "bad arguments");
+		flush(c);
+		FSB_CUDA(cudaStreamSynchronize(c->stream));
+		FSB_CUDA(cudaStreamSynchronize(c->comm_stream));
+		const int64_t n = std::min<int64_t>(c->timeline_used, max_slots);
+		*n_slots = n;
+		if (out && n > 0) {
+			FSB_CUDA(cudaMemcpy(out, c->d_timeline, static_cast<size_t>(n) * TL_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+			for (int64_t i = 0; i < n; ++i)
+				out[i * TL_WORDS + 2] = static_cast<uint64_t>(c->timeline_kind[static_cast<size_t>(i)]);
+		}
+		if (c->d_timeline)
+			timeline_reset(c);
+	});
+}
+
 int fsb_ctx_profile_read(fsb_ctx_t c, double * spmv_ms, int64_t * spmv_launches) {
 	double ms2[2];
 	int64_t n2[2];
@@ -432,9 +479,11 @@ int fsb_vec_create(fsb_ctx_t c, int64_t n_owned, int64_t n_ghost, fsb_vec_t * ou
 		v->n_owned = n_owned;
 		v->n_ghost = n_ghost;
 		v->id = c->next_vec_id++;
-		const size_t n = static_cast<size_t>(n_owned + n_ghost);
-		FSB_CUDA(cudaMalloc(&v->d, std::max<size_t>(n, 2) * sizeof(double)));
-		FSB_CUDA(cudaMemsetAsync(v->d, 0, std::max<size_t>(n, 2) * sizeof(double), c->stream));
+		// two doubles of slack: 16-byte bulk copies of the SpMV kernels may read one entry past an odd length
+		const size_t n = static_cast<size_t>(n_owned + n_ghost) + 2;
+		FSB_CUDA(cudaMalloc(&v->d, n * sizeof(double)));
+		FSB_CUDA(cudaMemsetAsync(v->d, 0, n * sizeof(double), c->stream));
+		v->padded = true;
 		*out = v;
 	});
 }
@@ -864,19 +913,22 @@ static void wait_token(fsb_ctx_t c, fsb_token_t tok) {
 		FSB_CUDA(cudaEventSynchronize(c->token_event[slot]));
 	}
 	else {
-		// the producing kernel stores the value, then the token, into mapped pinned memory
-		volatile int64_t * flag = c->h_flags + slot;
+		// the producing kernel publishes value and token as one flagged word in mapped pinned memory
+		const fsb::ll_word * w = c->h_ll + slot;
+		const uint32_t flag = static_cast<uint32_t>(tok);
+		double v;
 		unsigned spins = 0;
-		while (*flag != tok) {
+		while (!fsb::host_ll_load(w, flag, &v)) {
 			_mm_pause();
 			if ((++spins & 0xfffffu) == 0) { // every ~1M spins make sure the stream is still alive
 				cudaError_t q = cudaStreamQuery(c->stream);
 				if (q != cudaSuccess && q != cudaErrorNotReady)
 					FSB_CUDA(q);
-				if (q == cudaSuccess && *flag != tok)
+				if (q == cudaSuccess && !fsb::host_ll_load(w, flag, &v))
 					throw fsb::error(FSB_ERR_STATE, "reduction result never arrived");
 			}
 		}
+		c->h_results[slot] = v;
 		if (c->h_xrank_error && *(volatile int *)c->h_xrank_error)
 			throw fsb::error(FSB_ERR_STATE, "cross-rank reduction timed out waiting for a peer");
 	}
@@ -935,6 +987,16 @@ int64_t fsb_parcsr_global_rows(fsb_parcsr_t A) { return A->n_global; }
 int64_t fsb_parcsr_num_ghosts(fsb_parcsr_t A) { return A->n_ghost; }
 int64_t fsb_parcsr_row_begin(fsb_parcsr_t A) { return A->row_begin; }
 int64_t fsb_parcsr_local_nnz(fsb_parcsr_t A, int which) { return which == 0 ? A->diag.nnz : A->offd.nnz; }
+int64_t fsb_parcsr_info(fsb_parcsr_t A, int key) {
+	switch (key) {
+	case FSB_INFO_WINDOW_FORMAT: return A->diag.lcol != nullptr;
+	case FSB_INFO_ROW_BLOCKS: return A->diag.n_blk;
+	case FSB_INFO_WINDOW_X: return A->diag.win_xcap;
+	case FSB_INFO_FUSED_HALO: return A->halo_p2p != nullptr && A->diag.has_offd_map && !A->nbrs.empty();
+	case FSB_INFO_WIDE_OFFSETS: return A->diag.wide;
+	default: return -1;
+	}
+}
 
 int fsb_parcsr_download(fsb_parcsr_t A, int which, int64_t * rowptr, int32_t * col, double * val) {
 	return guarded([&] {

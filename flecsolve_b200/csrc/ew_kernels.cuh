@@ -18,8 +18,7 @@ constexpr int EW_BLOCK = 256; // threads per CTA of every element-wise kernel
 
 struct red_out {
 	double * d_value; // device result slot
-	double * h_value; // mapped host slot or nullptr (multi-rank: NCCL finishes the job)
-	long long * h_flag;
+	void * h_ll; // mapped host slot (16-byte flagged word, see ll_store) or nullptr (NCCL transport finishes the job)
 	long long token;
 	// device-scalar solvers (fsb.h, "device scalars"): keep the value on the device for later
 	// coefficients, and raise the context's halt flag when the convergence test passes
@@ -29,17 +28,76 @@ struct red_out {
 	int halt_mode; // 0 none, 1: sqrt(value) < thr, 2: value < thr
 };
 
+// Flagged 16-byte words ("LL" protocol, as NCCL's low-latency path): a double travels as two 8-byte halves
+// {32 data bits, 32 flag bits}.  8-byte stores are single-copy atomic over NVLink and PCIe, so a reader that finds the
+// expected flag in BOTH halves has the data -- no fence between payload and flag, no separate flag word: the cost of
+// a cross-GPU hand-over is one store latency instead of store + system fence (~6 us under load, measured in
+// profiles/r2_timeline_*.txt) + flag store.
+__device__ __forceinline__ void ll_store(void * dst, double v, unsigned flag) {
+	const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+	asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(static_cast<unsigned>(bits)), "r"(flag),
+	             "r"(static_cast<unsigned>(bits >> 32)), "r"(flag)
+	             : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const void * src, unsigned flag, double & v) {
+	unsigned lo, f0, hi, f1;
+	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
+	v = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo));
+	return f0 == flag && f1 == flag;
+}
+// spin until the word carries `flag`; false (and NaN) after ~10 s: the writer is gone
+__device__ __forceinline__ bool ll_load(const void * src, unsigned flag, double & v) {
+	if (ll_try_load(src, flag, v))
+		return true;
+	const long long t0 = clock64();
+	while (!ll_try_load(src, flag, v)) {
+		if (clock64() - t0 > 20000000000LL) {
+			v = __longlong_as_double(0x7ff8000000000000LL);
+			return false;
+		}
+	}
+	return true;
+}
+
 // Cross-rank all-reduce of one scalar over NVLink peer memory, executed by the CTA that finishes
-// a reduction: every rank stores its partial (then the token) into slot [token % ring][me] of every
-// rank's mailbox, waits for the P tokens in its own mailbox and folds the P values in rank order --
-// the same bits on every rank, no NCCL launch, no extra kernel.  Mailboxes are cudaIpc-mapped.
+// a reduction: every rank stores its partial as a flagged word into slot [token % ring][me] of every
+// rank's mailbox, waits for the P words of its own mailbox and folds the P values in rank order --
+// the same bits on every rank, no NCCL launch, no extra kernel, no fence.  Mailboxes are cudaIpc-mapped.
 constexpr int XRANK_MAX = 8;
 constexpr int XRANK_RING = 256; // == FSB_RED_RING
 struct xrank_info {
 	int me, nranks;
-	double * mailbox[XRANK_MAX]; // [ring][nranks]{value, token}
+	double * mailbox[XRANK_MAX]; // [ring][nranks] flagged 16-byte words
 	int * error_flag; // mapped host int: set when a peer never showed up
 };
+
+// Device-side timeline (FSB_OPT_TIMELINE): one slot of TL_WORDS 64-bit words per kernel launch, written with
+// %globaltimer (ns).  [0] earliest CTA start (atomicMin, initialised to ~0), [1] latest CTA end, [2] kind (host),
+// [3] ghost push complete, [4] first CTA has its ghosts, [5] longest wait of a CTA for them (ns), [6] all-reduce begins,
+// [7] result published, [8] push: acknowledgements seen, [9] push: stores issued (latest CTA each); rest spare.
+constexpr int TL_WORDS = 16;
+__device__ __forceinline__ unsigned long long tl_now() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+__device__ __forceinline__ void tl_begin(unsigned long long * tl) {
+	if (tl && threadIdx.x == 0)
+		atomicMin(tl, tl_now());
+}
+__device__ __forceinline__ void tl_end(unsigned long long * tl) {
+	if (tl && threadIdx.x == 0)
+		atomicMax(tl + 1, tl_now());
+}
+// words 0, 4, 6 are minima (slots are initialised to ~0 there), the others maxima (initialised to 0)
+__device__ __forceinline__ void tl_mark_min(unsigned long long * tl, int word) {
+	if (tl)
+		atomicMin(tl + word, tl_now());
+}
+__device__ __forceinline__ void tl_mark_max(unsigned long long * tl, int word) {
+	if (tl)
+		atomicMax(tl + word, tl_now());
+}
 
 struct ew_args {
 	double * v[MAXV];
@@ -58,6 +116,7 @@ struct ew_args {
 	unsigned * counter;
 	int partial_stride;
 	const xrank_info * xr; // nullptr on one rank
+	unsigned long long * tl; // timeline slot of this launch or nullptr
 	red_out r[MAXR];
 };
 
@@ -111,6 +170,7 @@ template<int FOLD>
 __device__ __forceinline__ double xrank_allreduce(const xrank_info * xr, double local, long long token, double * scratch) {
 	const int P = xr->nranks, me = xr->me;
 	const size_t slot = static_cast<size_t>(token % XRANK_RING);
+	const unsigned flag = static_cast<unsigned>(token);
 	__syncthreads();
 	if (threadIdx.x == 0)
 		scratch[0] = local;
@@ -119,23 +179,11 @@ __device__ __forceinline__ double xrank_allreduce(const xrank_info * xr, double 
 	__syncthreads();
 	if (threadIdx.x < P) {
 		const int q = threadIdx.x;
-		volatile double * dst = xr->mailbox[q] + (slot * P + me) * 2;
-		dst[0] = local;
-		__threadfence_system();
-		reinterpret_cast<volatile long long *>(dst)[1] = token;
-		volatile double * src = xr->mailbox[me] + (slot * P + q) * 2;
-		const long long t0 = clock64();
-		bool ok = true;
-		while (reinterpret_cast<volatile long long *>(src)[1] != token) {
-			if (clock64() - t0 > 20000000000LL) { // ~10 s: a peer is gone
-				ok = false;
-				break;
-			}
-		}
-		__threadfence_system();
-		scratch[q] = ok ? src[0] : __longlong_as_double(0x7ff8000000000000LL);
-		if (!ok)
+		ll_store(xr->mailbox[q] + (slot * P + me) * 2, local, flag);
+		double v;
+		if (!ll_load(xr->mailbox[me] + (slot * P + q) * 2, flag, v))
 			*reinterpret_cast<volatile int *>(xr->error_flag) = 1;
+		scratch[q] = v;
 	}
 	__syncthreads();
 	double r = fold_identity<FOLD>();
@@ -145,18 +193,15 @@ __device__ __forceinline__ double xrank_allreduce(const xrank_info * xr, double 
 	return r;
 }
 
-// publish a finished reduction: device slot, then mapped host value + token (thread 0 only)
+// publish a finished reduction: device slot, then the mapped host slot (thread 0 only)
 __device__ __forceinline__ void publish(const red_out & r, double t) {
 	*r.d_value = t;
 	if (r.d_extra)
 		*r.d_extra = t;
 	if (r.halt_mode != 0 && (r.halt_mode == 1 ? sqrt(t) : t) < r.halt_thr)
 		*reinterpret_cast<volatile int *>(r.halt) = 1;
-	if (r.h_value) {
-		*reinterpret_cast<volatile double *>(r.h_value) = t;
-		__threadfence_system();
-		*reinterpret_cast<volatile long long *>(r.h_flag) = r.token;
-	}
+	if (r.h_ll) // value and token in one flagged word: the host polls it, no fence needed
+		ll_store(r.h_ll, t, static_cast<unsigned>(r.token));
 }
 
 template<class PT, int I, class SC>
@@ -279,6 +324,7 @@ __device__ __forceinline__ void run_elements_box(const ew_args & a, const SC & s
 template<class PT, bool DEV, bool BOX>
 __device__ __forceinline__ void ew_program_body(const ew_args & a) {
 	constexpr program P = PT::value;
+	tl_begin(a.tl);
 	auto run = [&](const auto & sc, double (&acc)[MAXR]) {
 		if constexpr (BOX)
 			run_elements_box<PT>(a, sc, acc);
@@ -326,10 +372,14 @@ __device__ __forceinline__ void ew_program_body(const ew_args & a) {
 					 for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += blockDim.x)
 						 t = fold<F>(t, __ldcg(&a.partials[R * a.partial_stride + b]));
 					 t = block_fold<F>(t, scratch);
+					 if (threadIdx.x == 0)
+						 tl_mark_min(a.tl, 6);
 					 if (a.xr)
 						 t = xrank_allreduce<F>(a.xr, t, a.r[R].token, scratch);
-					 if (threadIdx.x == 0)
+					 if (threadIdx.x == 0) {
 						 publish(a.r[R], t);
+						 tl_mark_max(a.tl, 7);
+					 }
 				 }()),
 				 ...);
 			}(make_iseq<P.nr>{});
@@ -337,6 +387,7 @@ __device__ __forceinline__ void ew_program_body(const ew_args & a) {
 				*a.counter = 0u;
 		}
 	}
+	tl_end(a.tl);
 }
 
 template<class PT, bool DEV = false>
@@ -386,6 +437,7 @@ template<int UNUSED = 0> // template only so the header may be included by sever
 __global__ void __launch_bounds__(EW_BLOCK) ew_interp_kernel(const __grid_constant__ interp_args ia) {
 	const ew_args & a = ia.a;
 	const program & P = ia.p;
+	tl_begin(a.tl);
 	__shared__ int rfold[MAXR];
 	if (threadIdx.x == 0)
 		for (int i = 0; i < P.n; ++i)
@@ -475,6 +527,7 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_interp_kernel(const __grid_consta
 				*a.counter = 0u;
 		}
 	}
+	tl_end(a.tl);
 }
 
 } // namespace fsb

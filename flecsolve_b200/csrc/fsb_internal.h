@@ -87,12 +87,25 @@ struct box_shape {
 	int64_t origin() const { return lo[0] + ext[0] * (lo[1] + ext[1] * lo[2]); }
 };
 
-struct red_slot {
-	double * d_value; // device result (post intra-rank reduction)
-	volatile double * h_value; // pinned mapped host mirror
-	volatile int64_t * h_flag; // token written after the value
-	int nccl_op; // 0 sum 1 max 2 min
+// host view of a flagged 16-byte word (ew_kernels.cuh: ll_store): two 8-byte halves {32 data bits, 32 flag bits}
+struct ll_word {
+	volatile uint64_t half[2];
 };
+inline void host_ll_store(ll_word * w, double v, uint32_t flag) {
+	uint64_t bits;
+	static_assert(sizeof(bits) == sizeof(v), "double is 64 bits");
+	__builtin_memcpy(&bits, &v, 8);
+	w->half[0] = (bits & 0xffffffffull) | (static_cast<uint64_t>(flag) << 32);
+	w->half[1] = (bits >> 32) | (static_cast<uint64_t>(flag) << 32);
+}
+inline bool host_ll_load(const ll_word * w, uint32_t flag, double * v) {
+	const uint64_t a = w->half[0], b = w->half[1];
+	if (static_cast<uint32_t>(a >> 32) != flag || static_cast<uint32_t>(b >> 32) != flag)
+		return false;
+	const uint64_t bits = (a & 0xffffffffull) | (b << 32);
+	__builtin_memcpy(v, &bits, 8);
+	return true;
+}
 
 } // namespace fsb
 
@@ -110,10 +123,9 @@ struct fsb_ctx_s {
 	unsigned * d_counter = nullptr;
 	unsigned * d_sched = nullptr; // SpMV dynamic scheduler words {next block, finished CTAs}
 	double * d_results = nullptr; // [FSB_RED_RING]
-	double * h_results = nullptr; // pinned+mapped [FSB_RED_RING]
-	double * h_results_dev = nullptr; // device alias of h_results
-	int64_t * h_flags = nullptr; // pinned+mapped [FSB_RED_RING]
-	int64_t * h_flags_dev = nullptr;
+	double * h_results = nullptr; // pinned [FSB_RED_RING]: NCCL transport (device-to-host copy + event)
+	fsb::ll_word * h_ll = nullptr; // pinned+mapped [FSB_RED_RING] flagged words the reduction kernels publish into
+	fsb::ll_word * h_ll_dev = nullptr; // device alias of h_ll
 	int64_t next_token = 1;
 	// cross-rank reductions over peer memory (nranks > 1, when cudaIpc mapping succeeded)
 	double * d_mailbox = nullptr; // this rank's mailbox [ring][nranks]{value, token}
@@ -143,12 +155,18 @@ struct fsb_ctx_s {
 	std::vector<char> prof_tag; // per pair: 0 diag block, 1 offd block
 	size_t prof_used = 0;
 
+	// device-side timeline (FSB_OPT_TIMELINE): one slot of 8 x 64-bit words per launch, see ew_kernels.cuh
+	unsigned long long * d_timeline = nullptr;
+	int64_t timeline_cap = 0, timeline_used = 0;
+	std::vector<int> timeline_kind; // per used slot
+
 	// L2 flush scratch
 	void * d_flush = nullptr;
 	size_t flush_bytes = 0;
 
 	int64_t stats[16] = {};
 	uint64_t next_vec_id = 1;
+	uint64_t next_mat_id = 1;
 };
 
 struct fsb_vec_s {
@@ -157,8 +175,9 @@ struct fsb_vec_s {
 	int64_t n_owned = 0, n_ghost = 0;
 	bool owns = true;
 	bool halo_valid = false; // ghost entries hold the owners' current values ...
-	const void * halo_for = nullptr; // ... in the ghost numbering of this matrix
+	uint64_t halo_for = 0; // ... in the ghost numbering of the matrix with this id
 	uint64_t id = 0;
+	bool padded = false; // the allocation extends >= 2 doubles past n_owned + n_ghost (bulk copies may over-read one entry)
 	bool box = false; // structured-grid vector: n_owned dofs inside `shape`, n_owned + n_ghost == storage
 	fsb::box_shape shape;
 };
@@ -180,6 +199,13 @@ struct csr_block {
 	int max_blk_nnz = 0; // max nnz staged by one CTA (smem sizing)
 	int max_blk_rows = 0;
 	int32_t * row_ids = nullptr; // compressed row list (offd): row index per compressed row, or null
+	bool has_giant_rows = false; // some row exceeds a pipeline stage (streamed from global memory by a whole CTA)
+	bool has_offd_map = false; // descriptors carry the rows of the off-process block (fused ghost exchange possible)
+	// window format (spmv.cu: spmv_window_kernel), null when the block is in the gather format only
+	uint16_t * lcol = nullptr; // [nnz] position of x[col] inside the row block's staged x segments (+ diagonal mark)
+	uint16_t * rp16 = nullptr; // [n_rows + n_blk] row offsets relative to the block's first nonzero
+	void * segs = nullptr; // [n_blk][16] x segments per row block
+	int win_xcap = 0; // max x entries staged by one row block
 };
 
 struct neighbour {
@@ -194,6 +220,7 @@ struct neighbour {
 
 struct fsb_parcsr_s {
 	fsb_ctx_s * ctx = nullptr;
+	uint64_t id = 0; // unique per context: vectors remember whose ghost numbering they hold (a raw pointer could be reused)
 	int64_t n_global = 0, n_local = 0, n_ghost = 0, row_begin = 0;
 	fsb::csr_block diag, offd;
 	int64_t * d_colmap = nullptr;
@@ -220,16 +247,34 @@ struct fsb_parcsr_s {
 
 namespace fsb {
 
+// timeline slot for the next launch (nullptr when the timeline is off or full); kinds below
+enum { TL_KIND_SPMV = 1, TL_KIND_SPMV_OFFD = 2, TL_KIND_SPMV_FUSED = 3, TL_KIND_EW = 16, TL_KIND_HALO_PUSH = 32, TL_KIND_HALO_UNPACK = 33 };
+unsigned long long * timeline_slot(fsb_ctx_s * c, int kind);
+
 // queue / fuser (fuser.cu)
 void enqueue(fsb_ctx_s * c, const pending & p);
 void flush(fsb_ctx_s * c);
 int64_t new_token(fsb_ctx_s * c, int nccl_op);
 
 // kernels (declared here, defined in their .cu)
-// `fold`: the queued dot whose partials the last CTA of this launch folds and publishes (or nullptr)
-int launch_spmv(fsb_ctx_s * c, const csr_block & B, const double * x, double * y, bool accumulate,
-                const double * dot_u, double * d_partials, int partial_offset, cudaStream_t s,
-                const pending * fold = nullptr);
+// one SpMV launch: y (+)= B x with optional fused epilogues
+struct spmv_call {
+	const double * x = nullptr;
+	double * y = nullptr;
+	bool x_padded = false; // x may be over-read by one entry (window format needs it for an odd number of columns)
+	bool accumulate = false; // y += B x (off-process block as its own launch)
+	bool acc_continue = false; // accumulate: the row's running sum continues from y (Jacobi) instead of being added at the end
+	const double * dot_u = nullptr; // CTA b writes its partial of sum y_i u_i to partials[partial_offset + b]
+	double * partials = nullptr;
+	int partial_offset = 0;
+	const pending * fold = nullptr; // the queued dot whose partials the last CTA of this launch folds and publishes
+	const fsb_parcsr_s * halo = nullptr; // fused ghost exchange over peer memory: push, interior, boundary rows, acknowledge
+	long long epoch = 0;
+	int jacobi = 0; // 0 product; 1 weighted-Jacobi sweep (x = old iterate, y = new); 2 product without the diagonal entries
+	const double * jacobi_b = nullptr;
+	double omega = 0;
+};
+int launch_spmv(fsb_ctx_s * c, const csr_block & B, const spmv_call & call, cudaStream_t s);
 void fill_red_out(fsb_ctx_s * c, const pending & red, red_out & r);
 bool program_is_registered(const program & p, bool dev);
 // run-time compiled program kernels (jit.cu)
@@ -242,6 +287,8 @@ void finalize_reduction(fsb_ctx_s * c, int n_partials, const pending & red);
 void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x);
 
 void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * host_rowptr);
+void build_window_format(fsb_ctx_s * c, csr_block & B, int64_t n_cols);
+void attach_offd_rows(fsb_ctx_s * c, csr_block & D, const csr_block & O);
 void extract_dinv(fsb_parcsr_s * A, double * d);
 void halo_p2p_setup(fsb_parcsr_s * A, const std::vector<int64_t> & dest_off);
 void halo_p2p_destroy(fsb_parcsr_s * A);

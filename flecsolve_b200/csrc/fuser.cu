@@ -372,8 +372,7 @@ void fill_red_out(fsb_ctx_s * c, const pending & red, red_out & r) {
 	r.d_value = c->d_results + slot;
 	r.token = red.token;
 	if (c->nranks == 1 || c->d_xrank) {
-		r.h_value = c->h_results_dev + slot;
-		r.h_flag = reinterpret_cast<long long *>(c->h_flags_dev + slot);
+		r.h_ll = c->h_ll_dev + slot;
 		r.d_extra = red.store >= 0 ? c->d_scalars + red.store : nullptr;
 		r.halt = c->d_halt;
 		r.halt_thr = red.halt_thr;
@@ -498,6 +497,7 @@ void flush(fsb_ctx_s * c) {
 			long long packets = layout_of(q[i])->box ? n : (n + 1) / 2; // box layout: one element per thread and trip
 			long long want = (packets + EW_BLOCK - 1) / EW_BLOCK;
 			const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, MAX_RED_BLOCKS)));
+			g.args.tl = timeline_slot(c, TL_KIND_EW + len); // kind = 16 + number of statements
 			int resident = 0;
 			const void * jk = (!g.launch && c->jit) ? jit_kernel(g.prog, g.dev, g.box, &resident) : nullptr;
 			if (g.launch)
@@ -522,7 +522,7 @@ void flush(fsb_ctx_s * c) {
 				FSB_CUDA(cudaMemcpyAsync(c->d_results + slot, &ident, sizeof(double), cudaMemcpyHostToDevice, c->stream));
 				FSB_CUDA(cudaStreamSynchronize(c->stream));
 				c->h_results[slot] = ident;
-				c->h_flags[slot] = q[k].token;
+				host_ll_store(c->h_ll + slot, ident, static_cast<uint32_t>(q[k].token));
 			}
 		}
 		for (int k = i; k < i + len; ++k) // ghost copies of overwritten vectors are stale from here on

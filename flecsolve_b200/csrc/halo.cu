@@ -13,109 +13,32 @@
 #include <cstring>
 
 #include "fsb_internal.h"
+#include "spmv_common.cuh"
 
 namespace fsb {
 
-constexpr int HALO_MAX_NBR = 8;
 constexpr int HALO_THREADS = 256;
 
-struct halo_dev {
-	int me, nranks, n_nbr;
-	int nbr_rank[HALO_MAX_NBR];
-	long long send_count[HALO_MAX_NBR]; // entries I send to nbr k
-	long long send_start[HALO_MAX_NBR]; // contiguous: first owned index; packed: offset into send_idx
-	int contiguous[HALO_MAX_NBR];
-	long long dest_off[HALO_MAX_NBR]; // where my entries land in nbr k's ghost interval
-	long long recv_count[HALO_MAX_NBR]; // entries nbr k sends me
-	const int32_t * send_idx; // packed send lists (general partitions)
-	long long n_ghost; // my ghost entries
-	long long gmax; // landing-area capacity (max ghost count over ranks)
-	unsigned char * base[8]; // every rank's block: [ready 2 x 8][ack 8][pad][landing 0][landing 1]
-	unsigned * counters; // local: [0] push CTAs done, [1] unpack CTAs done
-	int * error_flag;
-};
-
-__device__ __forceinline__ volatile long long * halo_ready(unsigned char * base, int buf, int src) {
-	return reinterpret_cast<volatile long long *>(base) + buf * 8 + src;
-}
-__device__ __forceinline__ volatile long long * halo_ack(unsigned char * base, int dst) {
-	return reinterpret_cast<volatile long long *>(base) + 16 + dst;
-}
-__device__ __forceinline__ double * halo_landing(unsigned char * base, int buf, long long gmax) {
-	return reinterpret_cast<double *>(base + 256) + static_cast<size_t>(buf) * gmax;
-}
-
-__device__ __forceinline__ bool spin_until(volatile long long * flag, long long at_least, bool exact) {
-	const long long t0 = clock64();
-	for (;;) {
-		const long long v = *flag;
-		if (exact ? v == at_least : v >= at_least)
-			return true;
-		if (clock64() - t0 > 20000000000LL)
-			return false;
-	}
-}
-
+// explicit exchange (fsb_parcsr_halo_exchange, NCCL-free fallback of the two-launch SpMV): the fused SpMV kernel runs the
+// same halo_push_part from its consumer warps instead
 __global__ void __launch_bounds__(HALO_THREADS) halo_push_kernel(const halo_dev * hp, const double * __restrict__ x,
                                                                  long long epoch) {
-	const halo_dev & h = *hp;
-	const int buf = static_cast<int>(epoch & 1);
-	// the landing buffer was last used by exchange epoch-2: its consumer must have acknowledged it
-	if (threadIdx.x < h.n_nbr && h.send_count[threadIdx.x] > 0) {
-		if (!spin_until(halo_ack(h.base[h.me], h.nbr_rank[threadIdx.x]), epoch - 2, false))
-			*reinterpret_cast<volatile int *>(h.error_flag) = 2;
-	}
-	__syncthreads();
-	const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-	for (int k = 0; k < h.n_nbr; ++k) {
-		double * dst = halo_landing(h.base[h.nbr_rank[k]], buf, h.gmax) + h.dest_off[k];
-		const long long n = h.send_count[k];
-		if (h.contiguous[k]) {
-			const double * src = x + h.send_start[k];
-			for (long long i = tid; i < n; i += stride)
-				dst[i] = src[i];
-		}
-		else {
-			const int32_t * idx = h.send_idx + h.send_start[k];
-			for (long long i = tid; i < n; i += stride)
-				dst[i] = x[idx[i]];
-		}
-	}
-	__threadfence_system();
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		if (atomicAdd(&h.counters[0], 1u) == gridDim.x - 1) { // every CTA's stores are fenced: publish
-			__threadfence_system();
-			for (int k = 0; k < h.n_nbr; ++k)
-				if (h.send_count[k] > 0)
-					*halo_ready(h.base[h.nbr_rank[k]], buf, h.me) = epoch;
-			h.counters[0] = 0u;
-		}
-	}
+	halo_push_part(*hp, x, epoch, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x, [] { __syncthreads(); });
 }
 
 __global__ void __launch_bounds__(HALO_THREADS) halo_unpack_kernel(const halo_dev * hp, double * __restrict__ ghosts,
                                                                    long long epoch) {
 	const halo_dev & h = *hp;
-	const int buf = static_cast<int>(epoch & 1);
-	if (threadIdx.x < h.n_nbr && h.recv_count[threadIdx.x] > 0) {
-		if (!spin_until(halo_ready(h.base[h.me], buf, h.nbr_rank[threadIdx.x]), epoch, true))
-			*reinterpret_cast<volatile int *>(h.error_flag) = 3;
-	}
-	__syncthreads();
-	__threadfence_system();
-	const double * src = halo_landing(h.base[h.me], buf, h.gmax);
+	const unsigned char * src = halo_landing(h.base[h.me], static_cast<int>(epoch & 1), h.gmax);
+	const unsigned flag = static_cast<unsigned>(epoch);
 	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
 	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < h.n_ghost; i += stride)
-		ghosts[i] = __ldcg(src + i);
+		ghosts[i] = halo_ghost(h, src, i, flag); // every entry validates itself
 	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		if (atomicAdd(&h.counters[1], 1u) == gridDim.x - 1) { // landing area fully consumed: acknowledge
-			for (int k = 0; k < h.n_nbr; ++k)
-				if (h.recv_count[k] > 0)
-					*halo_ack(h.base[h.nbr_rank[k]], h.me) = epoch;
+			halo_acknowledge(h, epoch);
 			h.counters[1] = 0u;
 		}
 	}
@@ -141,10 +64,10 @@ void halo_p2p_setup(fsb_parcsr_s * A, const std::vector<int64_t> & dest_off) {
 	FSB_CUDA(cudaStreamSynchronize(c->stream));
 	cudaFree(d_g);
 	const long long gmax = std::max<long long>(g, 1);
-	const size_t bytes = 256 + 2 * static_cast<size_t>(gmax) * sizeof(double);
+	const size_t bytes = 256 + 2 * static_cast<size_t>(gmax) * 16; // two landing buffers of flagged 16-byte words
 	unsigned char * block = nullptr;
 	FSB_CUDA(cudaMalloc(&block, bytes));
-	FSB_CUDA(cudaMemset(block, 0, 256));
+	FSB_CUDA(cudaMemset(block, 0, bytes)); // flags 0: no exchange number matches
 	struct packet {
 		cudaIpcMemHandle_t h;
 		long long ok;
@@ -270,7 +193,7 @@ void halo_p2p_unpack(fsb_parcsr_s * A, fsb_vec_s * x) {
 	FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
 	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
 	x->halo_valid = true;
-	x->halo_for = A;
+	x->halo_for = A->id;
 }
 
 } // namespace fsb

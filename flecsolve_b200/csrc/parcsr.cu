@@ -38,6 +38,9 @@ static void free_block(csr_block & B) {
 	cudaFree(B.blk_row);
 	cudaFree(B.blk_desc);
 	cudaFree(B.row_ids);
+	cudaFree(B.lcol);
+	cudaFree(B.rp16);
+	cudaFree(B.segs);
 	B = csr_block{};
 }
 
@@ -202,7 +205,7 @@ static void halo_exchange_async(fsb_parcsr_s * A, fsb_vec_s * x) {
 	FSB_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
 	c->stats[FSB_STAT_HALO_EXCHANGES]++;
 	x->halo_valid = true;
-	x->halo_for = A;
+	x->halo_for = A->id;
 }
 
 void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x) {
@@ -226,15 +229,37 @@ void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x) {
 void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot) {
 	fsb_parcsr_s * A = sp.A;
 	fsb_vec_s *x = sp.x, *y = sp.y;
+	spmv_call call;
+	call.x = x->d;
+	call.y = y->d;
+	call.x_padded = x->padded;
+	call.partials = c->d_partials;
+	if (dot) {
+		fsb_vec_s * other = dot->x == y ? dot->y : dot->x;
+		call.dot_u = other->d; // other == y gives sum y^2
+		call.x_padded = call.x_padded && other->padded; // the window kernel stages u with bulk copies as well
+	}
 	if (A->box) { // columns and row ids are storage offsets of the padded arrays: one launch, no ghost exchange
-		const double * u = dot ? (dot->x == y ? dot->y : dot->x)->d : nullptr;
-		launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream, dot);
+		call.fold = dot;
+		launch_spmv(c, A->diag, call, c->stream);
 		return;
 	}
 	const bool multi = c->nranks > 1 && !A->nbrs.empty();
-	bool waited = true, unpack = false;
 	static const bool debug_skip_halo = std::getenv("FSB_DEBUG_SKIP_HALO") != nullptr; // timing experiments only
-	if (multi && !(x->halo_valid && x->halo_for == A) && !debug_skip_halo) {
+	static const bool fused_allowed = !(std::getenv("FSB_FUSED_HALO") && std::atoi(std::getenv("FSB_FUSED_HALO")) == 0);
+	if (multi && A->halo_p2p && A->diag.has_offd_map && A->diag.n_blk > 0 && fused_allowed && !debug_skip_halo) {
+		// ONE launch: push of this rank's boundary entries, interior rows, boundary rows (wait for the neighbours'
+		// entries, add the off-process part from the landing area), dot fold + all-reduce, acknowledge
+		call.halo = A;
+		call.epoch = ++A->halo_epoch;
+		call.fold = dot;
+		launch_spmv(c, A->diag, call, c->stream);
+		c->stats[FSB_STAT_HALO_EXCHANGES]++;
+		y->halo_valid = false;
+		return;
+	}
+	bool waited = true, unpack = false;
+	if (multi && !(x->halo_valid && x->halo_for == A->id) && !debug_skip_halo) {
 		if (A->halo_p2p) {
 			halo_p2p_push(A, x); // peers' pushes land while the diag block below runs
 			unpack = true;
@@ -244,21 +269,20 @@ void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot) {
 			waited = false;
 		}
 	}
-	const double * u = nullptr;
-	if (dot) {
-		fsb_vec_s * other = dot->x == y ? dot->y : dot->x;
-		u = other->d; // other == y gives sum y^2
-	}
 	const bool has_offd = A->offd.n_blk > 0;
 	// the launch that runs last folds the dot partials (no separate fold kernel)
-	const int np_diag = launch_spmv(c, A->diag, x->d, y->d, false, u, c->d_partials, 0, c->stream, has_offd ? nullptr : dot);
+	call.fold = has_offd ? nullptr : dot;
+	const int np_diag = launch_spmv(c, A->diag, call, c->stream);
 	if (unpack)
 		halo_p2p_unpack(A, x);
 	if (has_offd) {
 		if (!waited)
 			FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
 		waited = true;
-		launch_spmv(c, A->offd, x->d, y->d, true, u, c->d_partials, np_diag, c->stream, dot);
+		call.accumulate = true;
+		call.partial_offset = np_diag;
+		call.fold = dot;
+		launch_spmv(c, A->offd, call, c->stream);
 	}
 	if (!waited) // ghosts were requested but no row uses them: still order the streams
 		FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
@@ -279,6 +303,7 @@ fsb_parcsr_s * fsb_parcsr_create_impl(fsb_ctx_s * c, int64_t n_global, const int
 	const int P = c->nranks, me = c->rank;
 	auto * A = new fsb_parcsr_s;
 	A->ctx = c;
+	A->id = c->next_mat_id++;
 	A->n_global = n_global;
 	A->row_part.assign(row_part, row_part + P + 1);
 	FSB_REQUIRE(A->row_part[0] == 0 && A->row_part[P] == n_global, "parcsr: row_part must span [0, n_global]");
@@ -331,8 +356,11 @@ fsb_parcsr_s * fsb_parcsr_create_impl(fsb_ctx_s * c, int64_t n_global, const int
 			orp.push_back(orp_full[r + 1]);
 		}
 	upload_block(c, A->diag, drp, dcol, dval, nullptr);
+	build_window_format(c, A->diag, A->n_local);
 	if (!orows.empty())
 		upload_block(c, A->offd, orp, ocol, oval, &orows);
+	if (P > 1)
+		attach_offd_rows(c, A->diag, A->offd);
 	A->d_colmap = dev_upload<int64_t>(c, A->colmap);
 	FSB_CUDA(cudaStreamSynchronize(c->stream));
 	build_halo_plan(A);
@@ -481,6 +509,7 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 	FSB_REQUIRE(P == 1 || nz % P == 0, "stencil: nz must be divisible by the number of ranks (plane-aligned slabs)");
 	auto * A = new fsb_parcsr_s;
 	A->ctx = c;
+	A->id = c->next_mat_id++;
 	A->n_global = plane * nz;
 	A->row_part.resize(P + 1);
 	for (int q = 0; q <= P; ++q)
@@ -545,6 +574,7 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 	FSB_CUDA(cudaGetLastError());
 	D.max_blk_nnz = width; // row width bound for the uniform block builder
 	build_blocks(c, D, nullptr);
+	build_window_format(c, D, n);
 
 	// ---- offd block over the rows that touch a neighbouring slab
 	if (A->n_ghost > 0) {
@@ -614,6 +644,7 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 		}
 	}
 	if (P > 1) { // collective: every rank takes part even if it had no ghosts
+		attach_offd_rows(c, A->diag, A->offd);
 		std::vector<int64_t> dest_off;
 		for (const neighbour & nb : A->nbrs)
 			dest_off.push_back(nb.rank < me ? (nb.rank > 0 ? plane : 0) : 0); // my plane lands after its lower ghosts
@@ -671,6 +702,7 @@ fsb_parcsr_s * fsb_parcsr_create_box_stencil_impl(fsb_ctx_s * c, int dim, const 
 	rp[n] = n * width;
 	auto * A = new fsb_parcsr_s;
 	A->ctx = c;
+	A->id = c->next_mat_id++;
 	A->box = true;
 	A->shape = b;
 	A->n_global = A->n_local = n;
@@ -727,60 +759,107 @@ void extract_dinv(fsb_parcsr_s * A, double * d) {
 	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
 }
 
-// x = omega * dinv * (b - (x - a_rr tmp)) + (1 - omega) * tmp, where on entry x = A tmp (full row sums).
-// Removing the diagonal term afterwards keeps one SpMV kernel for both uses; the reference sums the
-// off-diagonal terms directly (mg/jacobi.hh:73-89), the difference is rounding-level.
-__global__ void jacobi_finish_kernel(double * __restrict__ x, const double * __restrict__ b,
-                                     const double * __restrict__ tmp, const double * __restrict__ dinv, double omega,
-                                     long long n) {
+// second half of a Jacobi sweep whose off-process part came from its own launch (NCCL transport): on entry x holds
+// lpu = sum_{c != r} a_rc tmp[c], accumulated in the reference's order (mg/jacobi.hh:73-86)
+__global__ void jacobi_finalize_kernel(double * __restrict__ x, const double * __restrict__ b,
+                                       const double * __restrict__ tmp, const double * __restrict__ dinv, double omega,
+                                       long long n) {
 	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-	for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride) {
-		const double di = dinv[r], t = tmp[r];
-		const double lpu = x[r] - t / di; // (L+U) tmp
-		x[r] = omega * di * (b[r] - lpu) + (1.0 - omega) * t;
-	}
+	for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride)
+		x[r] = __dadd_rn(__dmul_rn(__dmul_rn(omega, dinv[r]), __dadd_rn(b[r], -x[r])), __dmul_rn(__dadd_rn(1.0, -omega), tmp[r]));
 }
 
 } // namespace fsb
 
+// mg::bound_jacobi::relax (solvers/mg/jacobi.hh:58-93): per sweep tmp = x (incl. ghosts), then
+// x[r] = omega / a_rr * (b[r] - sum_{c != r} a_rc tmp[c]) + (1 - omega) tmp[r].
+// One pass over the matrix per sweep: the SpMV kernel skips the diagonal entry while summing (in the reference's order,
+// so the result is bit-identical) and applies the update in its epilogue; ghosts of the previous iterate arrive through
+// the kernel's own halo exchange.  The copy x -> tmp is a pointer swap when both vectors own their storage.
 void fsb_parcsr_jacobi_relax_impl(fsb_parcsr_s * A, double omega, int64_t nrelax, fsb_vec_s * b, fsb_vec_s * x,
                                   fsb_vec_s * tmp) {
 	fsb_ctx_s * c = A->ctx;
 	flush(c);
 	FSB_REQUIRE(x != tmp && b != tmp && x != b, "jacobi_relax: b, x, tmp must be distinct");
+	FSB_REQUIRE(x->d != tmp->d && b->d != tmp->d && x->d != b->d, "jacobi_relax: b, x, tmp must not share storage");
 	FSB_REQUIRE(x->n_owned == A->n_local && b->n_owned == A->n_local && tmp->n_owned == A->n_local &&
 	                x->n_ghost >= A->n_ghost && tmp->n_ghost >= A->n_ghost,
 	            "jacobi_relax: vectors do not match the matrix");
-	if (!A->d_dinv) {
-		A->d_dinv = dev_alloc<double>(A->n_local);
-		extract_dinv(A, A->d_dinv);
-	}
+	FSB_REQUIRE(!A->diag.has_giant_rows, "jacobi_relax: rows longer than one pipeline stage (4080 entries) are not supported");
+	if (A->n_local == 0 && A->nbrs.empty())
+		return;
 	const bool multi = c->nranks > 1 && !A->nbrs.empty();
+	static const bool fused_allowed = !(std::getenv("FSB_FUSED_HALO") && std::atoi(std::getenv("FSB_FUSED_HALO")) == 0);
+	const bool fused = multi && A->halo_p2p && A->diag.has_offd_map && A->diag.n_blk > 0 && fused_allowed;
+	const bool can_swap = x->owns && tmp->owns && x->n_ghost == tmp->n_ghost && x->padded == tmp->padded;
 	for (int64_t s = 0; s < nrelax; ++s) {
-		// tmp = x over the whole span incl. ghosts (mg/jacobi.hh:63): refresh ghosts of x, then copy
-		if (multi && !(x->halo_valid && x->halo_for == A)) {
-			if (A->halo_p2p) {
-				halo_p2p_push(A, x);
-				halo_p2p_unpack(A, x);
+		if (!multi || fused) {
+			const double * in = x->d;
+			double * out = tmp->d;
+			if (!can_swap) { // the reference's std::copy, then an in-place sweep reading the copy
+				FSB_CUDA(cudaMemcpyAsync(tmp->d, x->d, (x->n_owned + A->n_ghost) * sizeof(double), cudaMemcpyDeviceToDevice,
+				                         c->stream));
+				in = tmp->d;
+				out = x->d;
 			}
-			else {
-				halo_exchange_async(A, x);
-				FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+			spmv_call call;
+			call.x = in;
+			call.y = out;
+			call.x_padded = x->padded && tmp->padded && b->padded;
+			call.jacobi = 1;
+			call.jacobi_b = b->d;
+			call.omega = omega;
+			if (fused) {
+				call.halo = A;
+				call.epoch = ++A->halo_epoch;
+				c->stats[FSB_STAT_HALO_EXCHANGES]++;
 			}
+			launch_spmv(c, A->diag, call, c->stream);
+			if (can_swap)
+				std::swap(x->d, tmp->d); // x: the new iterate; tmp: the previous one, as the reference leaves it
 		}
-		FSB_CUDA(cudaMemcpyAsync(tmp->d, x->d, (x->n_owned + A->n_ghost) * sizeof(double), cudaMemcpyDeviceToDevice,
-		                         c->stream));
-		tmp->halo_valid = true;
-		launch_spmv(c, A->diag, tmp->d, x->d, false, nullptr, nullptr, 0, c->stream);
-		if (A->offd.n_blk > 0)
-			launch_spmv(c, A->offd, tmp->d, x->d, true, nullptr, nullptr, 0, c->stream);
-		const long long n = A->n_local;
-		if (n > 0) {
-			const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, SM_COUNT * 8));
-			jacobi_finish_kernel<<<grid, 256, 0, c->stream>>>(x->d, b->d, tmp->d, A->d_dinv, omega, n);
-			FSB_CUDA(cudaGetLastError());
-			c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+		else {
+			// two launches: ghosts of x through NCCL (or the explicit peer-memory exchange), copy, owned-column part
+			// without the diagonal, off-process part continuing the same running sum, update
+			if (!A->d_dinv) {
+				A->d_dinv = dev_alloc<double>(A->n_local);
+				extract_dinv(A, A->d_dinv);
+			}
+			if (!(x->halo_valid && x->halo_for == A->id)) {
+				if (A->halo_p2p) {
+					halo_p2p_push(A, x);
+					halo_p2p_unpack(A, x);
+				}
+				else {
+					halo_exchange_async(A, x);
+					FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+				}
+			}
+			FSB_CUDA(cudaMemcpyAsync(tmp->d, x->d, (x->n_owned + A->n_ghost) * sizeof(double), cudaMemcpyDeviceToDevice,
+			                         c->stream));
+			spmv_call call;
+			call.x = tmp->d;
+			call.y = x->d;
+			call.x_padded = tmp->padded;
+			call.jacobi = 2;
+			launch_spmv(c, A->diag, call, c->stream);
+			if (A->offd.n_blk > 0) {
+				spmv_call oc;
+				oc.x = tmp->d;
+				oc.y = x->d;
+				oc.accumulate = true;
+				oc.acc_continue = true;
+				launch_spmv(c, A->offd, oc, c->stream);
+			}
+			const long long n = A->n_local;
+			if (n > 0) {
+				const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, SM_COUNT * 8));
+				jacobi_finalize_kernel<<<grid, 256, 0, c->stream>>>(x->d, b->d, tmp->d, A->d_dinv, omega, n);
+				FSB_CUDA(cudaGetLastError());
+				c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+			}
 		}
 		x->halo_valid = false;
+		tmp->halo_valid = false;
 	}
 }

@@ -62,6 +62,8 @@ enum fsb_option {
 	FSB_OPT_JIT = 6 /* 1: a statement group without an ahead-of-time kernel gets one compiled at run time
 	                   (NVRTC, cached per process) instead of the generic program kernel; 0 (default in this
 	                   version; FSB_JIT=1 in the environment turns it on) */
+	,
+	FSB_OPT_TIMELINE = 7 /* n > 0: keep a device-side timeline of the next n kernel launches (fsb_ctx_timeline_read); 0: off */
 };
 
 enum fsb_stat {
@@ -110,6 +112,16 @@ int fsb_ctx_event_elapsed_ms(fsb_ctx_t ctx, int slot_start, int slot_stop, doubl
 int fsb_ctx_profile_read(fsb_ctx_t ctx, double * spmv_ms, int64_t * spmv_launches);
 /* same, split by block: index 0 = diag (owned columns) launches, 1 = offd (ghost columns) launches */
 int fsb_ctx_profile_read_split(fsb_ctx_t ctx, double * ms2, int64_t * launches2);
+
+/* Device-side timeline (FSB_OPT_TIMELINE): every kernel of this library stamps %globaltimer (ns) into its slot:
+ * slot[0] earliest CTA start, [1] latest CTA end, [2] kind (1 SpMV, 2 its off-process launch, 3 fused SpMV + ghost
+ * exchange, +8 Jacobi sweep, 16 + k element-wise program of k statements, 32 / 33 explicit halo push / unpack),
+ * [3] ghost push published, [4] first CTA has its ghosts, [5] longest wait of a CTA for them (ns), [6] cross-rank all-reduce
+ * begins, [7] result published, [8..10] ghost push: acknowledgements seen / stores issued / fenced (latest CTA each);
+ * 0 or ~0 where a mark does not apply.  Reads up to max_slots slots of 16 words in
+ * launch order, then clears the timeline.  This is how the per-iteration gaps in profiles/ are measured on several
+ * ranks, where ncu cannot be used.                                                                              */
+int fsb_ctx_timeline_read(fsb_ctx_t ctx, uint64_t * out, int64_t max_slots, int64_t * n_slots);
 
 /* diagnostics: canonicalise the statement list raw[4 n] = {op, z, x, y} (ops as in csrc/program.h, vector ids
  * arbitrary small integers, -1 = unused) and compile its kernel for sm_100a with the run-time compiler.
@@ -276,6 +288,21 @@ int64_t fsb_parcsr_global_rows(fsb_parcsr_t A);
 int64_t fsb_parcsr_num_ghosts(fsb_parcsr_t A);
 int64_t fsb_parcsr_row_begin(fsb_parcsr_t A);
 int64_t fsb_parcsr_local_nnz(fsb_parcsr_t A, int which /* 0 diag, 1 offd */);
+/* how the device holds the matrix (diagnostics / tests / bench byte counts):
+ *   FSB_INFO_WINDOW_FORMAT  1 when the owned-column block also has the window format (10 B per nonzero: fp64 value +
+ *                           16-bit position inside the x segments its row block stages in shared memory)
+ *   FSB_INFO_ROW_BLOCKS     row blocks (units of work of the SpMV pipeline) of the owned-column block
+ *   FSB_INFO_WINDOW_X       x entries the largest row block stages (window format)
+ *   FSB_INFO_FUSED_HALO     1 when y = A x is ONE launch that also does the ghost exchange over peer memory
+ *   FSB_INFO_WIDE_OFFSETS   1 when row offsets are 64-bit (local nnz >= 2^31)                                 */
+enum fsb_parcsr_info_key {
+	FSB_INFO_WINDOW_FORMAT = 0,
+	FSB_INFO_ROW_BLOCKS = 1,
+	FSB_INFO_WINDOW_X = 2,
+	FSB_INFO_FUSED_HALO = 3,
+	FSB_INFO_WIDE_OFFSETS = 4
+};
+int64_t fsb_parcsr_info(fsb_parcsr_t A, int key);
 /* copy the split representation back to the host (tests: compare with the
  * oracle's color()/init_mats() restatement).  Any pointer may be NULL.      */
 int fsb_parcsr_download(fsb_parcsr_t A, int which, int64_t * rowptr, int32_t * col, double * val);

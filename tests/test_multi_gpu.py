@@ -17,17 +17,20 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("transport", ["peer_memory", "nccl"])
+@pytest.mark.parametrize("transport", ["peer_memory", "peer_memory_two_launch", "nccl"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_sharded_path(nranks, transport):
-    """transport: halo exchange + scalar all-reduce over cudaIpc-mapped peer memory (default) or
-    through NCCL send/recv + ncclAllReduce (FSB_P2P_REDUCE=0)."""
+    """transport: halo exchange + scalar all-reduce over cudaIpc-mapped peer memory -- inside the one SpMV launch
+    (default) or as separate push / unpack kernels (FSB_FUSED_HALO=0) -- or through NCCL send/recv + ncclAllReduce
+    (FSB_P2P_REDUCE=0)."""
     from flecsolve_b200 import _lib as F
     if F.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
     env = dict(os.environ)
     if transport == "nccl":
         env["FSB_P2P_REDUCE"] = "0"
+    if transport == "peer_memory_two_launch":  # explicit push / unpack kernels around separate diag and offd launches
+        env["FSB_FUSED_HALO"] = "0"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)

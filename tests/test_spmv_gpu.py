@@ -184,12 +184,110 @@ def test_dinv_and_jacobi_relax(ctx):
     b, x0 = rng.standard_normal(n), rng.standard_normal(n)
     w = float(np.float32(2 / 3))
     bv, xv, tv = A.vector(b), A.vector(x0), A.vector()
+    launches = ctx.stat("launches")
     A.jacobi_relax(w, 4, bv, xv, tv)
+    assert ctx.stat("launches") - launches == 4  # one pass over the matrix per sweep, nothing else
     ref = M.jacobi_relax(w, 4, b, x0)
-    assert np.abs(xv.download() - ref).max() <= 1e-13 * np.abs(ref).max()
+    # the kernel skips the diagonal while summing, in the reference's order (mg/jacobi.hh:73-89): same bits
+    assert np.array_equal(xv.download(), ref)
+    assert np.array_equal(tv.download(), M.jacobi_relax(w, 3, b, x0))  # tmp = the previous iterate, like std::copy leaves it
     for v in (d, bv, xv, tv):
         v.destroy()
     A.destroy()
+
+
+@pytest.mark.parametrize("kind,dims", [(7, (12, 11, 10)), (27, (9, 8, 7)), (5, (17, 13, 1)), (27, (33, 5, 3))])
+@pytest.mark.parametrize("nrelax", [1, 2, 5])
+def test_jacobi_relax_bit_exact(ctx, kind, dims, nrelax):
+    """weighted Jacobi (solvers/mg/jacobi.hh:44-93) in the gather and the window format, owned and wrapped vectors,
+    rows whose diagonal is huge (a cancellation-prone formulation would lose them) or stored twice"""
+    rp, col, val = O.stencil_csr(kind, *dims)
+    n = len(rp) - 1
+    rng = np.random.default_rng(kind + nrelax)
+    val = val * rng.uniform(0.5, 1.5, val.size)
+    diag = np.flatnonzero(col == np.repeat(np.arange(n), np.diff(rp)))
+    val[diag[::7]] = 1e30  # penalty rows
+    M = O.ParCSR(rp, col, val, colours=1)
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    w = float(np.float32(2 / 3))
+    bv, xv, tv = A.vector(b), A.vector(x0), A.vector()
+    A.jacobi_relax(w, nrelax, bv, xv, tv)
+    ref = M.jacobi_relax(w, nrelax, b, x0)
+    assert np.array_equal(xv.download(), ref)
+    for v in (bv, xv, tv):
+        v.destroy()
+    A.destroy()
+
+
+@pytest.mark.parametrize("dims", [(8, 8, 8), (9, 7, 5), (33, 17, 3), (64, 64, 4), (5, 5, 5), (130, 3, 3)])
+def test_window_format_27pt_bit_exact(ctx, dims):
+    """the 27-point operators take the window format (x segments staged in shared memory, 16-bit local columns):
+    same bits as the reference's row loop, also with the fused dot, for odd sizes and rows cut by the domain"""
+    rp, col, val = O.stencil_csr(27, *dims)
+    n = len(rp) - 1
+    rng = np.random.default_rng(n)
+    val = val * rng.uniform(0.5, 1.5, val.size)
+    for A in (F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val),):
+        assert A.info("window_format") == 1 and A.info("window_x") > 0
+        x = rng.standard_normal(n)
+        xv, yv, uv = A.vector(x), A.vector(), A.vector(rng.standard_normal(n))
+        A.spmv(xv, yv)
+        ref = O.csr_spmv(rp, col, val, x)
+        assert np.array_equal(yv.download(), ref)
+        A.spmv(xv, yv)
+        t = yv.dot_token(uv)
+        assert abs(ctx.get(t) - ref @ uv.download()) <= 1e-13 * (np.abs(ref) @ np.abs(uv.download()))
+        assert np.array_equal(yv.download(), ref)
+        A.spmv(xv, yv)
+        t = yv.sumsq_token()
+        assert abs(ctx.get(t) - ref @ ref) <= 1e-13 * (ref @ ref)
+        for v in (xv, yv, uv):
+            v.destroy()
+        A.destroy()
+    # the device generator builds the same thing
+    B = F.ParCSR.stencil(ctx, 27, *dims)
+    assert B.info("window_format") == 1
+    rp, col, val = O.stencil_csr(27, *dims)
+    xv, yv = B.vector(x), B.vector()
+    B.spmv(xv, yv)
+    assert np.array_equal(yv.download(), O.csr_spmv(rp, col, val, x))
+    xv.destroy(); yv.destroy(); B.destroy()
+
+
+def test_window_format_general_matrices(ctx):
+    """banded matrices with ragged rows: a few column clusters per row block -> window format; scattered columns ->
+    the builder declines and the gather kernel runs.  Both bit-exact."""
+    rng = np.random.default_rng(11)
+    n = 5000
+    rows, cols = [], []
+    for offs in (-700, -699, -3, -1, 0, 1, 2, 650, 651, 652):
+        r = np.arange(n)
+        keep = (r + offs >= 0) & (r + offs < n) & (rng.random(n) < 0.8)
+        rows.append(r[keep]); cols.append((r + offs)[keep])
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    import scipy.sparse as sp
+    S = sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(n, n))
+    S.sum_duplicates(); S.sort_indices()
+    rp, col, val = S.indptr.astype(np.int64), S.indices.astype(np.int64), S.data
+    import os
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    x = rng.standard_normal(n)
+    xv, yv = A.vector(x), A.vector()
+    A.spmv(xv, yv)
+    assert np.array_equal(yv.download(), O.csr_spmv(rp, col, val, x))
+    xv.destroy(); yv.destroy(); A.destroy()
+    # scattered: 12 random columns per row
+    cols = rng.integers(0, n, size=(n, 12))
+    S = sp.csr_matrix((rng.standard_normal(n * 12), (np.repeat(np.arange(n), 12), cols.ravel())), shape=(n, n))
+    S.sum_duplicates(); S.sort_indices()
+    rp, col, val = S.indptr.astype(np.int64), S.indices.astype(np.int64), S.data
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    assert A.info("window_format") == 0
+    xv, yv = A.vector(x), A.vector()
+    A.spmv(xv, yv)
+    assert np.array_equal(yv.download(), O.csr_spmv(rp, col, val, x))
+    xv.destroy(); yv.destroy(); A.destroy()
 
 
 def test_large_stencil_properties(ctx):
