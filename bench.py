@@ -6,6 +6,8 @@
   python bench.py --impl reference --gpus N ...            the reference's CPU path (oracle restatement)
 
 A "step" is one CG iteration.  Rank 0 prints ONE JSON line; see README/DESIGN.md for the fields.
+The headline (`value`, `e2e`, `roofline`) is always BASELINE.json configs[1] (7-point 256^3); `workloads` carries the
+same measurement for the other workloads (27-point 512^3 = configs[4], the strong-scaling target) at the same N.
 """
 from __future__ import annotations
 
@@ -26,6 +28,9 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
+# measured beside the headline at the same N (one short window each): configs[4], the strong-scaling target
+EXTRA_WORKLOADS = {"poisson7_256": ["poisson27_512"]}
+
 WORKLOADS = {
     # name: (stencil kind, nx, ny, nz, preconditioner)
     "poisson7_256": (7, 256, 256, 256, "dinv"),
@@ -34,6 +39,12 @@ WORKLOADS = {
     "poisson7_128": (7, 128, 128, 128, "dinv"),
     "poisson5_2d_256": (5, 256, 256, 1, None),
 }
+
+
+def describe(workload: str) -> str:
+    kind, nx, ny, nz, precond = WORKLOADS[workload]
+    return (f"{workload}: {kind}-point Poisson {nx}x{ny}x{nz}, {'Jacobi (1/diag) ' if precond else 'un'}preconditioned CG, "
+            f"fp64, b = A x_true, x0 = 0")
 
 
 def measured_peak_gbs():
@@ -109,17 +120,13 @@ def pinned(n: int) -> np.ndarray:
     return torch.empty(n, dtype=torch.float64).pin_memory().numpy()
 
 
-def run_ours(args):
+def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str, with_e2e: bool, history_cap: int = 0) -> dict:
+    """one workload on the ranks of `world`: device-resident timing of K iterations, SpMV roofline, optionally e2e"""
     from flecsolve_b200 import _lib as F
     from flecsolve_b200 import dist as D
     from flecsolve_b200 import host as H
 
-    world = D.init(D.world_from_env())
-    if world.size != args.gpus:
-        if world.size == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
-    kind, nx, ny, nz, precond = WORKLOADS[args.workload]
-    ctx = D.make_context(world)
+    kind, nx, ny, nz, precond = WORKLOADS[workload]
     t0 = time.time()
     A = F.ParCSR.stencil(ctx, kind, nx, ny, nz)
     ctx.sync()
@@ -133,134 +140,243 @@ def run_ours(args):
     ctx.sync()
     xt.destroy()
     setup_s = time.time() - t0
-
-    W, K = args.warmup, args.steps
     ctx.set_option("profile", 1)
-
     split = {}
+    hist_out = {}
 
     # ---- device-resident timing: iterations W+1 .. W+K of one solve, CUDA events on the library's stream
-    def timed_solve(solver=args.solver):
+    def timed_solve(which):
         S.x.zero()
         ctx.sync()
         ctx.profile_read()
         D.barrier(world)
         # cg_device looks at iteration j (and fires the event marks) after issuing iteration j + lag: issue
         # lag more iterations so that the marks still bracket exactly K of them
-        lag = 2 if solver == "cg_device" else 0
-        _, info, _ = S.solve(solver=solver, precond=precond, maxiter=W + K + lag, rtol=0.0, ev_start=W, ev_stop=W + K,
-                             lag=lag)
+        lag = 2 if which == "cg_device" else 0
+        _, info, hist = S.solve(solver=which, precond=precond, maxiter=W + K + lag, rtol=0.0, ev_start=W, ev_stop=W + K,
+                                lag=lag, history_cap=history_cap)
         ctx.sync()
         D.barrier(world)
         ms = ctx.event_elapsed_ms(0, 1)
         (ms_d, ms_o), (n_d, n_o) = ctx.profile_read_split()
-        split.update(diag_avg_ms=ms_d / max(n_d, 1), offd_avg_ms=ms_o / max(n_o, 1))
-        return ms, info, ms_d + ms_o, n_d + n_o
+        split.update(diag_avg_ms=ms_d / max(n_d, 1), offd_avg_ms=ms_o / max(n_o, 1), launches_per_spmv=1 if n_o == 0 else 2)
+        hist_out[which] = np.array(hist)
+        return ms, info, ms_d + ms_o, n_d
 
-    sampler = ClockSampler(world.local_rank).start() if world.is_root else None
-    timed_solve()  # cold pass: allocations, occupancy queries, NCCL channels
+    timed_solve(solver)  # cold pass: allocations, occupancy queries, NCCL channels
     # the timed region is short (K x ~0.5 ms): run it `repeats` times and report the MEDIAN run
-    runs = sorted((timed_solve() for _ in range(max(1, args.repeats))), key=lambda r: r[0])
+    runs = sorted((timed_solve(solver) for _ in range(max(1, repeats))), key=lambda r: r[0])
     ms, info, spmv_ms, spmv_n = runs[len(runs) // 2]
     # the other CG flavour beside it (cg: flecsolve's template, 3 host reads per iteration;
     # cg_device: scalars on the device, residual norm inspected late -- SURVEY 8(f) N1)
-    other = "cg_device" if args.solver == "cg" else "cg"
+    other = "cg_device" if solver == "cg" else "cg"
     timed_solve(other)
-    oruns = sorted((timed_solve(other) for _ in range(max(1, args.repeats))), key=lambda r: r[0])
+    oruns = sorted((timed_solve(other) for _ in range(max(1, repeats))), key=lambda r: r[0])
     oms, oinfo = oruns[len(oruns) // 2][:2]
     oms = D.max_over_ranks(world, oms)
-    clocks = sampler.stop() if sampler else {}
     ms = D.max_over_ranks(world, ms)
     ms_per_step = ms / K
-    value = 1000.0 / ms_per_step
-
-    # ---- end to end: full solve to rtol 1e-9 through the host-buffer call (H2D b, x0; D2H x)
     ctx.set_option("profile", 0)
-    b_host, x_host = pinned(n_local), pinned(n_local)
-    b_host[:] = S.b.download()
-    e2e_iters, e2e_s = 0, 0.0
-    for rep in range(2):  # first rep warms the pinned buffers / page tables
-        x_host[:] = 0.0
-        ctx.sync()
-        D.barrier(world)
-        t1 = time.perf_counter()
-        x_out, einfo, _ = S.solve(b_host, x_host, solver="cg", precond=precond, maxiter=5000, rtol=1e-9)
-        dt = time.perf_counter() - t1
-        e2e_s = D.max_over_ranks(world, dt)
-        e2e_iters = einfo.iters
-    err = float(np.abs(x_out - x_true(A.row_begin, n_local)).max())
-    err = D.max_over_ranks(world, err)
-    e2e_value = e2e_iters / e2e_s if e2e_s > 0 and e2e_iters > 0 else 0.0
 
     peak, peak_src = measured_peak_gbs()
     N, nnz = n_local, nnz_local
-    off = 8 if nnz >= 2 ** 31 - 16 else 4
+    wide = nnz >= 2 ** 31 - 16
+    off = 8 if wide else 4
+    # ALGORITHMIC bytes: fp64 values + int32 columns + row offsets + x + y (+ dot operand = x for CG: free)
     spmv_bytes = 12 * nnz + off * (N + 1) + 16 * N + 8 * A.num_ghosts
     iter_bytes = 12 * nnz + off * N + (108 - 4) * N + 8 * A.num_ghosts  # 12 nnz + 108 N (int32 offsets)
-    launches_per_spmv = 2 if A.nnz(1) > 0 else 1  # diag block, then the off-process block
-    spmv_avg_ms = spmv_ms / max(spmv_n // launches_per_spmv, 1)  # per SpMV (all its launches)
+    # bytes of the format the device really streams (window format: 8 + 2 per nonzero, 16-bit block-relative row offsets)
+    window = A.info("window_format") == 1
+    fmt_bytes = (10 * nnz + 2 * (2 * N + A.info("row_blocks")) if window else 12 * nnz + off * (N + 1)) + 16 * N + 16 * A.num_ghosts
+    spmv_avg_ms = spmv_ms / max(spmv_n, 1)  # per SpMV: all its launches (one, unless the two-launch transports are in use)
     spmv_gbs = spmv_bytes / spmv_avg_ms / 1e6 if spmv_avg_ms > 0 else 0.0
     iter_gbs = iter_bytes / ms_per_step / 1e6
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_spmv_ncu_summary.json")
-    if os.path.exists(tp) and args.workload == "poisson7_256" and world.size == 1:
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    out = {
+        "workload": describe(workload), "value": 1000.0 / ms_per_step, "ms_per_step": ms_per_step,
+        "rows": n_global, "nnz": nnz_global, "partition": f"{world.size} z-slab(s) of {n_local} rows",
+        "gpu_launches": int(info.window_launches), "setup_seconds": setup_s,
+        "device_format": ("window: fp64 value + 16-bit position in the row block's staged x segments per nonzero (10 B), "
+                          "16-bit block-relative row offsets" if window else
+                          f"csr: fp64 value + int32 column per nonzero (12 B), int{off * 8} row offsets"),
+        "spmv_launches_per_product": split.get("launches_per_spmv"),
+        "fused_halo": bool(A.info("fused_halo")),
+        "roofline": {
+            "bound": "hbm", "kernel": ("spmv_window_kernel" if window else "spmv_stream_kernel") + " (y = A p fused with p.Ap"
+                                      + (", ghost exchange and all-reduce inside" if A.info("fused_halo") else "") + ")",
+            "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
+            "launches_timed": spmv_n, "share_of_step": spmv_avg_ms / ms_per_step if ms_per_step > 0 else None,
+            "format_bytes_per_launch": fmt_bytes, "achieved_format_gbs": fmt_bytes / spmv_avg_ms / 1e6 if spmv_avg_ms > 0 else 0.0,
+            "note": "achieved = SURVEY 8(d) algorithmic bytes (12 B/nnz CSR) / time; the device streams format_bytes "
+                    "(window format: 10 B/nnz), so achieved may exceed the copy peak while achieved_format cannot",
+            "iteration": {"algorithmic_bytes": iter_bytes, "achieved": iter_gbs, "frac": iter_gbs / peak,
+                          "frac_of_nominal_8TBs": iter_gbs / 8000.0},
+        },
+        "solver": solver,
+        "other_solver": {"solver": other, "value": 1000.0 * K / oms, "ms_per_step": oms / K,
+                         "gpu_launches": int(oinfo.window_launches),
+                         "iteration_frac_of_peak": iter_bytes / (oms / K) / 1e6 / peak},
+    }
+    if history_cap:
+        out["_history"] = hist_out.get(solver)
+
+    if with_e2e:
+        # ---- end to end: full solve to rtol 1e-9 through the host-buffer call (H2D b, x0; D2H x), pinned buffers in place
+        b_host, x_host = pinned(n_local), pinned(n_local)
+        b_host[:] = S.b.download()
+        best = None
+        for rep in range(3):  # first rep warms the pinned buffers / page tables; the faster of the next two is reported
+            x_host[:] = 0.0
+            ctx.sync()
+            D.barrier(world)
+            t1 = time.perf_counter()
+            x_out, einfo, _ = S.solve(b_host, x_host, inplace=True, solver="cg", precond=precond, maxiter=5000, rtol=1e-9)
+            dt = D.max_over_ranks(world, time.perf_counter() - t1)
+            if rep > 0 and (best is None or dt < best[0]):
+                best = (dt, einfo.iters, einfo.h2d_ms, einfo.solve_ms, einfo.d2h_ms)
+        e2e_s, e2e_iters, h2d_ms, solve_ms, d2h_ms = best
+        err = D.max_over_ranks(world, float(np.abs(x_out - x_true(A.row_begin, n_local)).max()))
+        out["e2e"] = {
+            "value": e2e_iters / e2e_s if e2e_s > 0 and e2e_iters > 0 else 0.0, "unit": "iterations/s",
+            "h2d_bytes_per_step": 16 * n_local / max(e2e_iters, 1), "d2h_bytes_per_step": 8 * n_local / max(e2e_iters, 1),
+            "iterations": e2e_iters, "seconds": e2e_s,
+            "what": "fsbh_solve with pinned host b, x0 in and x out, rtol 1e-9f, wall clock around the call",
+            "max_abs_error_vs_x_true": err,
+            "breakdown_ms": {"h2d": h2d_ms, "solver_call": solve_ms, "of_which_iterations_at_device_rate": e2e_iters * ms_per_step,
+                             "d2h": d2h_ms, "binding_overhead": e2e_s * 1e3 - h2d_ms - solve_ms - d2h_ms,
+                             "note": "solver_call - iterations = prologue (|b|, residual, first preconditioner apply), "
+                                     "diagnostics and the final |x|; rank 0's numbers"},
+        }
+    S.close()
+    A.destroy()
+    return out
+
+
+def run_ours(args):
+    from flecsolve_b200 import dist as D
+
+    world = D.init(D.world_from_env())
+    if world.size != args.gpus:
+        if world.size == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    ctx = D.make_context(world)
+    W, K = args.warmup, args.steps
+    sampler = ClockSampler(world.local_rank).start() if world.is_root else None
+    cpu_iters = args.cpu_iters
+    head = measure(world, ctx, args.workload, W, K, args.repeats, args.solver, with_e2e=True, history_cap=W + K)
+    clocks = sampler.stop() if sampler else {}
+    gpu_hist = head.pop("_history")
+    extra = {}
+    if not args.no_extra_workloads:
+        for wl in EXTRA_WORKLOADS.get(args.workload, []):
+            r = measure(world, ctx, wl, 5, 30, 1, args.solver, with_e2e=False)
+            r.pop("_history", None)
+            extra[wl] = r
 
     line = {
         "metric": "cg_iterations_per_second",
-        "value": value,
+        "value": head["value"],
         "unit": "iterations/s",
         "n_gpus": world.size,
         "steps": K,
         "warmup": W,
-        "ms_per_step": ms_per_step,
+        "ms_per_step": head["ms_per_step"],
         "higher_is_better": True,
         "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": f"{args.workload}: {kind}-point Poisson {nx}x{ny}x{nz}, parallel CSR (fp64 values, int32 columns), "
-                        f"{'Jacobi (1/diag)' if precond else 'un'}preconditioned CG, b = A x_true, x0 = 0",
-            "rows": n_global, "nnz": nnz_global, "partition": f"{world.size} z-slab(s) of {n_local} rows",
-            "l2_policy": "inputs larger than L2 (per-iteration working set %.2f GB >> 126 MB)" % (iter_bytes / 1e9),
+            "workload": head["workload"],
+            "rows": head["rows"], "nnz": head["nnz"], "partition": head["partition"],
+            "device_format": head["device_format"],
+            "l2_policy": "inputs larger than L2 (per-iteration working set %.2f GB >> 126 MB)"
+                         % (head["roofline"]["iteration"]["algorithmic_bytes"] / 1e9),
             "timed": f"iterations {W + 1}..{W + K} of one solve (rtol 0), CUDA events on the library stream, max over ranks; "
                      f"median of {max(1, args.repeats)} such solves",
+            "host_templates": "this repo's flecsolve-shaped host layer (same call sequence as the reference's op::cg; the "
+                              "reference's own cg.hh over the same kernels is timed in `reference_templates` when "
+                              "tests/dropin/_build/libfsb_dropin.so is present)",
         },
-        "roofline": {
-            "bound": "hbm", "kernel": "spmv_stream_kernel (y = A p fused with p.Ap)",
-            "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak, "traffic": traffic,
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
-            "launches_timed": spmv_n, "diag_block_avg_ms": split.get("diag_avg_ms"),
-            "offd_block_avg_ms": split.get("offd_avg_ms"), "share_of_step": spmv_avg_ms / ms_per_step if ms_per_step > 0 else None,
-            "iteration": {"algorithmic_bytes": iter_bytes, "achieved": iter_gbs, "frac": iter_gbs / peak,
-                          "frac_of_nominal_8TBs": iter_gbs / 8000.0},
-        },
-        "e2e": {
-            "value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": 16 * n_local / max(e2e_iters, 1),
-            "d2h_bytes_per_step": 8 * n_local / max(e2e_iters, 1), "iterations": e2e_iters, "seconds": e2e_s,
-            "what": "fsbh_solve with pinned host b, x0 in and x out, rtol 1e-9f, wall clock around the call",
-            "max_abs_error_vs_x_true": err,
-        },
-        "gpu_launches": int(info.window_launches),
-        "solver": args.solver,
-        "other_solver": {"solver": other, "value": 1000.0 * K / oms, "ms_per_step": oms / K,
-                         "gpu_launches": int(oinfo.window_launches),
-                         "iteration_frac_of_peak": iter_bytes / (oms / K) / 1e6 / peak},
+        "roofline": head["roofline"],
+        "e2e": head["e2e"],
+        "gpu_launches": head["gpu_launches"],
+        "solver": head["solver"],
+        "other_solver": head["other_solver"],
+        "spmv_launches_per_product": head["spmv_launches_per_product"],
+        "fused_halo": head["fused_halo"],
         "clocks": clocks,
-        "setup_seconds": setup_s,
+        "setup_seconds": head["setup_seconds"],
+        "workloads": extra,
     }
+    tp = os.path.join(ROOT, "profiles", "r2_spmv_ncu_summary.json")
+    line["roofline"]["traffic"] = None
+    if os.path.exists(tp) and args.workload == "poisson7_256" and world.size == 1:
+        try:
+            t = json.load(open(tp))
+            line["roofline"]["traffic"] = t.get("dram_bytes_per_launch")
+            line["roofline"]["traffic_source"] = ("not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the "
+                                                  "same kernel on the same workload from the committed ncu --set full capture "
+                                                  "profiles/r2_spmv_ncu_summary.json")
+        except Exception:
+            pass
+    if world.is_root and world.size == 1:
+        ref = reference_templates(ctx, args.workload, W, K)
+        if ref:
+            line["reference_templates"] = ref
     if world.is_root and world.size == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.workload, sample_iters=args.cpu_iters)
-    S.close()
-    A.destroy()
+        base = cpu_baseline(args.workload, sample_iters=cpu_iters)
+        ref_hist = np.array(base.pop("history"))
+        m = min(len(ref_hist), len(gpu_hist))
+        if m:
+            rel = np.abs(gpu_hist[:m] - ref_hist[:m]) / ref_hist[:m]
+            line["parity"] = {"what": "residual norms of the first iterations: this run's device solve vs the CPU restatement "
+                                      "of the reference on the same full-size system",
+                              "iters_compared": int(m), "max_rel_diff": float(rel.max()), "tolerance": 1e-8,
+                              "ok": bool(rel.max() <= 1e-8)}
+        line["cpu_baseline"] = base
     ctx.close()
     if world.is_root:
         print(json.dumps(line), flush=True)
     D.finalize(world)
+
+
+def reference_templates(ctx, workload: str, W: int, K: int):
+    """the same window timed through the REFERENCE's own cg.hh (tests/dropin: unmodified /root/reference headers over the
+    policy classes of include/fsb_flecsolve/b200.hh, prebuilt where /root/reference exists); host buffers in and out"""
+    try:
+        from tests import dropin as DI
+        if not DI.available():
+            return None
+        from flecsolve_b200 import _lib as F
+        kind, nx, ny, nz, precond = WORKLOADS[workload]
+        A = F.ParCSR.stencil(ctx, kind, nx, ny, nz)
+        n = A.local_rows
+        xt, bv = A.vector(x_true(A.row_begin, n)), A.vector()
+        A.spmv(xt, bv)
+        b = bv.download()
+        xt.destroy(); bv.destroy()
+        d = DI.Dropin(DI.lib())
+        best = None
+        for _ in range(3):
+            _, info, _ = d.solve(ctx.h, A.h, b, np.zeros(n), solver="cg", precond=precond, rtol=0.0, maxiter=W + K,
+                                 ev_start=W, ev_stop=W + K)
+            ms = ctx.event_elapsed_ms(0, 1) / K
+            best = ms if best is None else min(best, ms)
+        A.destroy()
+        return {"value": 1000.0 / best, "ms_per_step": best, "gpu_launches": int(info.window_launches),
+                "what": "flecsolve's own solvers/cg.hh + vectors/core.hh + operators/*.hh (unmodified) over "
+                        "include/fsb_flecsolve/b200.hh, same kernels, same window of iterations"}
+    except Exception as e:  # never let the extra leg break the benchmark line
+        return {"unavailable": str(e)[:200]}
+
+
+def host_threads() -> int:
+    """all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def cpu_baseline(workload: str, sample_iters: int, warm: int = 2) -> dict:
@@ -268,7 +384,8 @@ def cpu_baseline(workload: str, sample_iters: int, warm: int = 2) -> dict:
     one pass per vector op, 3 blocking reductions per iteration) on the host cores of this box."""
     import oracle as O
     kind, nx, ny, nz, precond = WORKLOADS[workload]
-    threads = O.max_threads()
+    threads = host_threads()
+    O.set_threads(threads)
     rp, col, val = O.stencil_csr(kind, nx, ny, nz)
     M = O.ParCSR(rp, col, val, colours=threads)  # one colour per thread, like one MPI rank per core
     n = len(rp) - 1
@@ -276,11 +393,12 @@ def cpu_baseline(workload: str, sample_iters: int, warm: int = 2) -> dict:
     dinv = M.dinv() if precond else None
     M.cg(b, dinv=dinv, maxiter=warm, rtol=0.0)  # page in
     t0 = time.perf_counter()
-    _, info, _ = M.cg(b, dinv=dinv, maxiter=sample_iters, rtol=0.0)
+    _, info, hist = M.cg(b, dinv=dinv, maxiter=sample_iters, rtol=0.0, history_cap=sample_iters)
     dt = time.perf_counter() - t0
     out = {"value": sample_iters / dt, "unit": "iterations/s", "cores": threads, "kind": "port",
            "sample": f"first {sample_iters} CG iterations of the same system (x0 = 0), {threads} OpenMP threads = colours, "
-                     f"{dt:.1f} s", "seconds": dt, "host_cores": os.cpu_count()}
+                     f"{dt:.1f} s", "seconds": dt, "host_cores": os.cpu_count(), "omp_max_threads_in_use": O.max_threads(),
+           "history": [float(h) for h in hist]}
     if threads > 1:  # the serial figure beside it (one colour, one thread), on a shorter sample
         one_iters = max(3, sample_iters // 8)
         M1 = O.ParCSR(rp, col, val, colours=1)
@@ -298,22 +416,26 @@ def cpu_baseline(workload: str, sample_iters: int, warm: int = 2) -> dict:
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path is not buildable here
-    (needs FleCSI/MPI/Boost), so this times its line-faithful restatement under oracle/."""
+    (needs FleCSI/MPI/Boost), so this times its line-faithful restatement under oracle/ on ALL host cores."""
     from flecsolve_b200 import dist as D
     world = D.world_from_env()
     if world.rank != 0:
         return
     # at least 20 and at most --cpu-iters-cap iterations: a handful of iterations mostly times page faults
     iters = min(max(args.steps, 20), args.cpu_iters_cap)
-    base = cpu_baseline(args.workload, sample_iters=iters, warm=3)
-    kind, nx, ny, nz, precond = WORKLOADS[args.workload]
+    base = cpu_baseline(args.workload, sample_iters=iters, warm=max(args.warmup, 1) if args.warmup <= 5 else 3)
+    base.pop("history", None)
+    if base["cores"] * 2 < (os.cpu_count() or 1):
+        print(f"[bench] warning: reference arm runs on {base['cores']} of {os.cpu_count()} host cores", file=sys.stderr)
     line = {
         "impl": "reference",
         "metric": "cg_iterations_per_second", "value": base["value"], "unit": "iterations/s",
-        "n_gpus": args.gpus, "steps": iters, "warmup": 3, "ms_per_step": 1000.0 / base["value"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / base["value"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {kind}-point Poisson {nx}x{ny}x{nz}, reference CPU path restated "
-                               f"(oracle/oracle.cpp), {'Jacobi' if precond else 'un'}preconditioned CG"},
+        "config": {"workload": describe(args.workload),
+                   "implementation": "reference CPU path restated (oracle/oracle.cpp: size_t indices, diag/offd split + add "
+                                     "pass, one pass per vector op, blocking reductions), one colour per OpenMP thread",
+                   "sampled_steps": iters},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -330,6 +452,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=40, help="CG iterations of the CPU baseline sample")
     ap.add_argument("--cpu-iters-cap", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true", help="skip the 27-point 512^3 block")
     ap.add_argument("--repeats", type=int, default=3, help="timed solves of W+K iterations; the median one is reported")
     ap.add_argument("--solver", default="cg", choices=["cg", "cg_device"],
                     help="cg: flecsolve's CG template unchanged (headline); cg_device: scalars kept on the device")

@@ -41,7 +41,7 @@ constexpr int SPMV_MAX_STAGES = 4;
 constexpr int ROWS_MAX = 512; // rows per block (shared scratch of the boundary phases is sized for it)
 constexpr int WIN_MAXSEG = 16; // x segments per row block (window format)
 constexpr int WIN_GAP = 8; // columns closer than this are covered by one segment
-constexpr unsigned WIN_DIAG_BIT = 0x8000u; // local column index: bit 15 marks the diagonal entry, bits 0-14 the position
+constexpr unsigned WIN_NO_DIAG = 0xffffu; // row meta: the row stores no diagonal entry
 
 struct spmv_args {
 	const void * rowptr;
@@ -77,11 +77,13 @@ struct spmv_args {
 	double omega;
 	// window format
 	const uint16_t * lcol;
-	const uint16_t * rp16;
+	const uint16_t * rp16; // per row block: nrows + 1 row offsets relative to its first nonzero, then nrows diagonal positions
 	const x_segment * segs; // [n_blk][WIN_MAXSEG] in row order
 	int xcap; // doubles of x staged per block (capacity)
-	const double * aux; // row-aligned operand staged with the block: the dot operand u, or b of a Jacobi sweep (or nullptr)
-	int acap; // its capacity per stage (0 when aux == nullptr)
+	const double * aux; // row-aligned operand of the epilogue (window kernel): the dot operand u, or b of a Jacobi sweep
+	int acap; // its capacity per stage when it is staged with the block (aux_mode 1)
+	int aux_mode; // 0 none; 1 staged with the block by a bulk copy; 2 u is x itself: read it from the x window at the
+	              // diagonal's position (CG's <Ap, p>: no extra bytes at all); 3 plain global load
 	unsigned long long * tl; // timeline slot of this launch or nullptr
 };
 
@@ -572,9 +574,9 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_window_kernel(const 
 			const long long za = d.z0 & ~7LL; // 16-byte aligned start of the 16-bit stream
 			const long long cnt = ((d.z0 + d.nnz + 7) & ~7LL) - za;
 			const long long ra = d.rp0 & ~7LL;
-			const long long rcnt = ((static_cast<long long>(d.rp0) + d.nrows + 1 + 7) & ~7LL) - ra;
+			const long long rcnt = ((static_cast<long long>(d.rp0) + 2 * d.nrows + 1 + 7) & ~7LL) - ra;
 			const long long aa = d.r0 & ~1LL; // row-aligned operand: rows [r0, r0 + nrows), 16-byte granular
-			const long long acnt = a.aux ? ((static_cast<long long>(d.r0) + d.nrows + 1) & ~1LL) - aa : 0;
+			const long long acnt = a.aux_mode == 1 ? ((static_cast<long long>(d.r0) + d.nrows + 1) & ~1LL) - aa : 0;
 			if (lane == 0) {
 				if (it >= NSTAGE)
 					mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
@@ -626,51 +628,40 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_window_kernel(const 
 			const double * sv = reinterpret_cast<const double *>(base) + (d.z0 - za);
 			const double * xs = reinterpret_cast<const double *>(base + off_x);
 			const double * sa = reinterpret_cast<const double *>(base + off_a) + (d.r0 & 1);
-			const bool staged_aux = a.aux != nullptr;
+			const int aux_mode = a.aux_mode;
 			const uint16_t * sl = reinterpret_cast<const uint16_t *>(base + off_c) + (d.z0 - za);
 			const uint16_t * srp = reinterpret_cast<const uint16_t *>(base + off_r) + (d.rp0 & 7);
 			const int r0 = d.r0, nrows = d.nrows;
 			const bool boundary = HALO && d.ocnt > 0;
+			const uint16_t * sdk = srp + nrows + 1; // position of the diagonal entry inside each row (or WIN_NO_DIAG)
 			for (int i = ctid; i < nrows; i += nconsumers) {
 				const int p0 = srp[i], p1 = srp[i + 1];
+				const unsigned dk = sdk[i];
+				const int pd = dk != WIN_NO_DIAG ? p0 + static_cast<int>(dk) : -1; // the row's diagonal entry
+				const bool have_diag = pd >= 0;
 				double sum = 0.0, dg = 0.0, xold = 0.0;
-				bool have_diag = false;
 				for (int p = p0; p < p1; p += UNROLL) {
 					double prod[UNROLL];
-					if constexpr (JAC == 0) {
 #pragma unroll
-						for (int k = 0; k < UNROLL; ++k)
-							if (p + k < p1)
-								prod[k] = __dmul_rn(sv[p + k], xs[sl[p + k] & (WIN_DIAG_BIT - 1)]);
+					for (int k = 0; k < UNROLL; ++k)
+						if (p + k < p1 && (JAC == 0 || p + k != pd)) // a Jacobi sweep leaves the diagonal out of the sum
+							prod[k] = __dmul_rn(sv[p + k], xs[sl[p + k]]);
 #pragma unroll
-						for (int k = 0; k < UNROLL; ++k)
-							if (p + k < p1)
-								sum = __dadd_rn(sum, prod[k]);
-					}
-					else {
-						bool keep[UNROLL];
-#pragma unroll
-						for (int k = 0; k < UNROLL; ++k) {
-							keep[k] = p + k < p1;
-							if (keep[k]) {
-								const unsigned c = sl[p + k];
-								if (c & WIN_DIAG_BIT) {
-									dg = sv[p + k];
-									xold = xs[c & (WIN_DIAG_BIT - 1)]; // x[row] sits in the window at the diagonal's position
-									have_diag = true;
-									keep[k] = false;
-								}
-								else
-									prod[k] = __dmul_rn(sv[p + k], xs[c]);
-							}
-						}
-#pragma unroll
-						for (int k = 0; k < UNROLL; ++k)
-							if (keep[k])
-								sum = __dadd_rn(sum, prod[k]);
-					}
+					for (int k = 0; k < UNROLL; ++k)
+						if (p + k < p1 && (JAC == 0 || p + k != pd))
+							sum = __dadd_rn(sum, prod[k]);
 				}
-				const double auxv = staged_aux ? sa[i] : 0.0;
+				if ((JAC != 0 || aux_mode == 2) && have_diag) { // x[row] sits in the window where the diagonal entry points
+					xold = xs[sl[pd]];
+					dg = sv[pd];
+				}
+				double auxv = 0.0;
+				if (aux_mode == 1)
+					auxv = sa[i];
+				else if (aux_mode == 2)
+					auxv = have_diag ? xold : a.x[r0 + i];
+				else if (aux_mode == 3)
+					auxv = a.aux[r0 + i];
 				if constexpr (JAC == 1) {
 					if (!have_diag)
 						xold = a.x[r0 + i];
@@ -720,7 +711,7 @@ __global__ void build_desc_kernel(const void * rowptr, bool wide, const int32_t 
 	d.r0 = r0;
 	d.nrows = r1 - r0;
 	d.nnz = static_cast<int>(z1 - z0);
-	d.rp0 = r0 + b; // window format: the block's 16-bit row offsets (nrows + 1 of them)
+	d.rp0 = 2 * r0 + b; // window format: the block's 16-bit row meta (nrows + 1 offsets, then nrows diagonal positions)
 	d.seg_slot = b * WIN_MAXSEG; // window format: the block's segment slots (unused ones have len 0)
 	out[b] = d;
 }
@@ -769,8 +760,9 @@ __global__ void __launch_bounds__(WIN_THREADS) build_window_kernel(const OffT * 
 	const int r0 = blk_row[b], r1 = blk_row[b + 1];
 	const long long z0 = static_cast<long long>(rowptr[r0]);
 	const int nnz = static_cast<int>(static_cast<long long>(rowptr[r1]) - z0);
+	uint16_t * meta = rp16 + 2 * static_cast<size_t>(r0) + b; // [nrows + 1 offsets | nrows diagonal positions]
 	for (int i = tid; i <= r1 - r0; i += WIN_THREADS)
-		rp16[r0 + b + i] = static_cast<uint16_t>(static_cast<long long>(rowptr[r0 + i]) - z0);
+		meta[i] = static_cast<uint16_t>(static_cast<long long>(rowptr[r0 + i]) - z0);
 	if (tid < WIN_MAXSEG)
 		segs[static_cast<size_t>(b) * WIN_MAXSEG + tid] = x_segment{0, 0};
 	if (nnz > WIN_THREADS * WIN_ITEMS) {
@@ -835,23 +827,25 @@ __global__ void __launch_bounds__(WIN_THREADS) build_window_kernel(const OffT * 
 		}
 		seg_off[nseg] = off;
 		atomicMax(&status[1], off);
-		if (off > xcap_limit || off >= static_cast<int>(WIN_DIAG_BIT))
+		if (off > xcap_limit || off > 0xffff)
 			atomicOr(&status[0], 1);
 	}
 	__syncthreads();
-	// local column of every nonzero: thread per row so the diagonal can be marked
+	// local column of every nonzero; thread per row, which also notes where the row keeps its diagonal entry (the last
+	// one if it is stored more than once, as the reference's loop would use it)
 	for (int i = tid; i < r1 - r0; i += WIN_THREADS) {
 		const long long q0 = static_cast<long long>(rowptr[r0 + i]), q1 = static_cast<long long>(rowptr[r0 + i + 1]);
+		unsigned dk = WIN_NO_DIAG;
 		for (long long q = q0; q < q1; ++q) {
 			const int c = col[q];
 			int s = 0;
 			while (s + 1 < nseg && seg_start[s + 1] <= c)
 				++s;
-			unsigned v = static_cast<unsigned>(seg_off[s] + (c - seg_start[s]));
+			lcol[q] = static_cast<uint16_t>(seg_off[s] + (c - seg_start[s]));
 			if (c == r0 + i)
-				v |= WIN_DIAG_BIT;
-			lcol[q] = static_cast<uint16_t>(v);
+				dk = static_cast<unsigned>(q - q0);
 		}
+		meta[(r1 - r0) + 1 + i] = static_cast<uint16_t>(dk);
 	}
 }
 
@@ -889,9 +883,9 @@ static spmv_config configure(const fsb_ctx_s * c, const csr_block & B, bool wind
 	k.cap = ((B.max_blk_nnz + 16 + 7) / 8) * 8; // + alignment slack on both ends
 	if (k.cap < 64)
 		k.cap = 64;
-	k.rcap = ((B.max_blk_rows + 1 + 16 + 7) / 8) * 8;
+	k.rcap = (((window ? 2 : 1) * B.max_blk_rows + 1 + 16 + 7) / 8) * 8;
 	k.xcap = window ? ((B.win_xcap + 7) / 8) * 8 : 0;
-	k.acap = (window && staged_operand) ? k.rcap : 0;
+	k.acap = (window && staged_operand) ? ((B.max_blk_rows + 2 + 7) / 8) * 8 : 0;
 	const size_t stage_bytes = window ? static_cast<size_t>(k.cap) * 10 + static_cast<size_t>(k.xcap + k.acap) * 8 + static_cast<size_t>(k.rcap) * 2
 	                                  : static_cast<size_t>(k.cap) * 12 + static_cast<size_t>(k.rcap) * (B.wide ? 8 : 4);
 	// consumer threads: one per row of a block, at most 512
@@ -903,7 +897,7 @@ static spmv_config configure(const fsb_ctx_s * c, const csr_block & B, bool wind
 	// Measured on B200 (profiles/r1_spmv_sweep.txt): throughput follows the number of resident
 	// consumer threads (>= 1024 per SM saturates HBM); a second stage only pays when it does not
 	// cost resident CTAs.
-	const size_t budget = 208 * 1024; // of the 227 KB an SM offers: static scratch and per-CTA reservations come on top
+	const size_t budget = 206 * 1024; // of the 227 KB an SM offers: static scratch (<= 8.5 KB) and 1 KB reserved per CTA come on top
 	const size_t ctas_for_1024 = (1024 + consumers - 1) / consumers;
 	k.nstage = (2 * stage_bytes * ctas_for_1024 <= budget) ? 2 : 1;
 	if (window) // consumers read shared memory only: two stages per CTA, as many CTAs as fit (r2 sweep)
@@ -1049,9 +1043,21 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const spmv_call & call, cuda
 	const bool rowlist = B.row_ids != nullptr;
 	// the window format serves plain passes over the owned-column block with x vectors that may be over-read by one entry
 	const bool window = B.lcol != nullptr && !rowlist && !call.accumulate && call.x_padded;
-	// row-aligned operand of the epilogue that the window kernel stages with the block
+	// row-aligned operand of the window kernel's epilogue: u == x comes out of the x window for free; otherwise it is staged
+	// with the block unless that costs a resident CTA (then: plain loads)
 	const double * aux = !window ? nullptr : (call.jacobi == 1 ? call.jacobi_b : (call.dot_u && call.dot_u != call.y ? call.dot_u : nullptr));
-	const spmv_config k = configure(c, B, window, aux != nullptr);
+	int aux_mode = aux ? 1 : 0;
+	if (aux && call.jacobi == 0 && aux == call.x)
+		aux_mode = 2;
+	spmv_config k = configure(c, B, window, aux_mode == 1);
+	if (aux_mode == 1) {
+		const spmv_config lean = configure(c, B, window, false);
+		const size_t per_sm = 227 * 1024;
+		if (per_sm / (lean.smem + 1536) > per_sm / (k.smem + 1536) || lean.nstage > k.nstage) {
+			k = lean;
+			aux_mode = 3;
+		}
+	}
 	FSB_REQUIRE(k.smem <= 225 * 1024, "spmv: row block does not fit shared memory");
 	spmv_args a{};
 	a.rowptr = B.rowptr;
@@ -1076,6 +1082,7 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const spmv_call & call, cuda
 	a.xcap = k.xcap;
 	a.aux = aux;
 	a.acap = k.acap;
+	a.aux_mode = aux_mode;
 	a.acc_continue = call.acc_continue ? 1 : 0;
 	a.jb = call.jacobi_b;
 	a.omega = call.omega;
@@ -1179,8 +1186,12 @@ void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * hos
 		rows = pow2;
 		// wide rows are headed for the window format, which runs best with ~17 KB stages, two per CTA and five CTAs per
 		// SM (27-point: 64 rows; measured in profiles/r2_spmv_window_sweep.txt); short rows keep 512-row blocks
-		if (width >= 16 && env_int("FSB_SPMV_WINDOW", 1) != 0 && !B.row_ids)
-			rows = std::min(rows, 64);
+		if (env_int("FSB_SPMV_WINDOW", 1) != 0 && !B.row_ids) {
+			if (width >= 16)
+				rows = std::min(rows, 64);
+			else if (rows == ROWS_MAX)
+				rows = 448; // two stages of a 7-point block + its x segments, two CTAs per SM, in every kernel variant
+		}
 		// small matrices (the off-process block of a slab): one row block per resident CTA, so the
 		// whole block is a single latency-bound pass instead of several sequential ones
 		int fit = 32;
@@ -1230,7 +1241,7 @@ void build_window_format(fsb_ctx_s * c, csr_block & B, int64_t n_cols) {
 	x_segment * segs = nullptr;
 	int * status = nullptr;
 	FSB_CUDA(cudaMalloc(&lcol, (static_cast<size_t>(B.nnz) + 32) * sizeof(uint16_t)));
-	FSB_CUDA(cudaMalloc(&rp16, (static_cast<size_t>(B.n_rows) + B.n_blk + 32) * sizeof(uint16_t)));
+	FSB_CUDA(cudaMalloc(&rp16, (2 * static_cast<size_t>(B.n_rows) + B.n_blk + 32) * sizeof(uint16_t)));
 	FSB_CUDA(cudaMalloc(&segs, static_cast<size_t>(B.n_blk) * WIN_MAXSEG * sizeof(x_segment)));
 	FSB_CUDA(cudaMalloc(&status, 2 * sizeof(int)));
 	FSB_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int), c->stream));

@@ -23,7 +23,8 @@ class Info(C.Structure):
     _fields_ = [("status", C.c_int), ("iters", C.c_int), ("restarts", C.c_int),
                 ("res_norm_initial", C.c_float), ("res_norm_final", C.c_float),
                 ("sol_norm_initial", C.c_float), ("sol_norm_final", C.c_float), ("rhs_norm", C.c_float),
-                ("callbacks", C.c_int), ("window_launches", C.c_int), ("solve_ms", C.c_double)]
+                ("callbacks", C.c_int), ("window_launches", C.c_int), ("solve_ms", C.c_double),
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
 
     @property
     def reason(self) -> str:
@@ -150,9 +151,10 @@ class Session:
             _check(lib().fsbh_session_destroy(self.h))
             self.h = None
 
-    def solve(self, b=None, x0=None, history_cap=0, **kw):
+    def solve(self, b=None, x0=None, history_cap=0, inplace=False, **kw):
         """Host-buffer call when b is given (uploads b and x0, downloads x); device-resident
-        otherwise (uses self.b / self.x as they are)."""
+        otherwise (uses self.b / self.x as they are).  inplace: x0 (a contiguous float64 array, e.g. pinned memory)
+        is the in/out buffer itself instead of being copied."""
         opts = make_options(**kw)
         info = Info()
         hist = np.zeros(max(history_cap, 1))
@@ -161,7 +163,11 @@ class Session:
             x = None
         else:
             b = np.ascontiguousarray(b, dtype=np.float64)
-            x = np.array(x0 if x0 is not None else np.zeros_like(b), dtype=np.float64)
+            if inplace:
+                assert x0 is not None and x0.dtype == np.float64 and x0.flags.c_contiguous
+                x = x0
+            else:
+                x = np.array(x0 if x0 is not None else np.zeros_like(b), dtype=np.float64)
             _check(lib().fsbh_solve(self.h, C.byref(opts), _d(b), _d(x), C.byref(info), _d(hist), history_cap))
         return x, info, hist[:min(info.callbacks, history_cap)]
 

@@ -109,7 +109,8 @@ struct fsbh_info {
 	float res_norm_initial, res_norm_final, sol_norm_initial, sol_norm_final, rhs_norm;
 	int callbacks; // times the diagnostic ran
 	int window_launches; // kernels launched between the two event marks
-	double solve_ms; // wall clock around the solver call alone, device idle on both sides (multi-vector driver)
+	double solve_ms; // wall clock around the solver call alone, device idle on both sides
+	double h2d_ms, d2h_ms; // fsbh_solve with host buffers: upload of b and x0 / download of x (wall clock, synchronous copies)
 };
 
 struct fsbh_options {
@@ -184,6 +185,7 @@ void fill(fsbh_info * out, const solve_info & i, int callbacks, std::int64_t win
 	out->rhs_norm = i.rhs_norm;
 	out->callbacks = callbacks;
 	out->solve_ms = 0;
+	out->h2d_ms = out->d2h_ms = 0;
 }
 
 template<class S, class P>
@@ -244,10 +246,15 @@ int fsbh_solve(void * sv, const fsbh_options * o, const double * b_host, double 
 	return guarded([&] {
 		session & S = *static_cast<session *>(sv);
 		const std::int64_t n = fsb_vec_local_size(S.b.data.handle());
+		using clk = std::chrono::steady_clock;
+		auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+		const auto t_h2d = clk::now();
 		if (b_host)
 			device::check(fsb_vec_upload(S.b.data.handle(), b_host, n, 0));
 		if (x_host && !o->use_zero_guess)
 			device::check(fsb_vec_upload(S.x.data.handle(), x_host, n, 0));
+		const double h2d_ms = ms_since(t_h2d);
+		const auto t_solve = clk::now();
 		recorder rec{S.ctx.handle(), history, history_cap, o->ev_start, o->ev_stop};
 		solve_info si;
 		if (o->precond == 1) {
@@ -268,11 +275,15 @@ int fsbh_solve(void * sv, const fsbh_options * o, const double * b_host, double 
 		else {
 			si = run_solver<int>(S, *o, op::I, rec);
 		}
+		S.ctx.sync();
+		const double solve_ms = ms_since(t_solve);
+		const auto t_d2h = clk::now();
 		if (x_host)
 			device::check(fsb_vec_download(S.x.data.handle(), x_host, n, 0));
-		else
-			S.ctx.sync();
 		fill(info, si, rec.count, rec.launches_stop - rec.launches_start);
+		info->solve_ms = solve_ms;
+		info->h2d_ms = h2d_ms;
+		info->d2h_ms = x_host ? ms_since(t_d2h) : 0.0;
 	});
 }
 

@@ -90,6 +90,7 @@ struct fsbd_info {
 	int callbacks;
 	int window_launches;
 	double solve_ms;
+	double h2d_ms, d2h_ms;
 };
 struct fsbd_options {
 	int solver; // 0 cg, 1 gmres, 2 bicgstab, 3 fcg
@@ -132,6 +133,7 @@ void fill(fsbd_info * out, const solve_info & i, const recorder & rec) {
 	out->callbacks = rec.count;
 	out->window_launches = static_cast<int>(rec.launches_stop - rec.launches_start);
 	out->solve_ms = 0;
+	out->h2d_ms = out->d2h_ms = 0;
 }
 
 // bind the reference's solver templates exactly as solvers/test/cg.cc:62-91 and examples/poisson do
