@@ -152,7 +152,7 @@ def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str
         D.barrier(world)
         # cg_device looks at iteration j (and fires the event marks) after issuing iteration j + lag: issue
         # lag more iterations so that the marks still bracket exactly K of them
-        lag = 2 if which == "cg_device" else 0
+        lag = 2 if which in ("cg_device", "cg_sr") else 0
         _, info, hist = S.solve(solver=which, precond=precond, maxiter=W + K + lag, rtol=0.0, ev_start=W, ev_stop=W + K,
                                 lag=lag, history_cap=history_cap)
         ctx.sync()
@@ -174,6 +174,11 @@ def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str
     oruns = sorted((timed_solve(other) for _ in range(max(1, repeats))), key=lambda r: r[0])
     oms, oinfo = oruns[len(oruns) // 2][:2]
     oms = D.max_over_ranks(world, oms)
+    # single-reduction CG (solvers/cg_sr.hh): two launches and one synchronisation point per iteration
+    timed_solve("cg_sr")
+    sruns = sorted((timed_solve("cg_sr") for _ in range(max(1, repeats))), key=lambda r: r[0])
+    sms, sinfo = sruns[len(sruns) // 2][:2]
+    sms = D.max_over_ranks(world, sms)
     ms = D.max_over_ranks(world, ms)
     ms_per_step = ms / K
     ctx.set_option("profile", 0)
@@ -216,6 +221,9 @@ def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str
         "other_solver": {"solver": other, "value": 1000.0 * K / oms, "ms_per_step": oms / K,
                          "gpu_launches": int(oinfo.window_launches),
                          "iteration_frac_of_peak": iter_bytes / (oms / K) / 1e6 / peak},
+        "single_reduction_solver": {"solver": "cg_sr", "value": 1000.0 * K / sms, "ms_per_step": sms / K,
+                                    "gpu_launches": int(sinfo.window_launches),
+                                    "what": "Chronopoulos-Gear CG, scalars on the device: 2 launches / iteration, 12 nnz + 116 N bytes"},
     }
     if history_cap:
         out["_history"] = hist_out.get(solver)
@@ -303,6 +311,7 @@ def run_ours(args):
         "gpu_launches": head["gpu_launches"],
         "solver": head["solver"],
         "other_solver": head["other_solver"],
+        "single_reduction_solver": head["single_reduction_solver"],
         "spmv_launches_per_product": head["spmv_launches_per_product"],
         "fused_halo": head["fused_halo"],
         "clocks": clocks,

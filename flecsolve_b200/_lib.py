@@ -71,8 +71,16 @@ class Coef(C.Structure):
     _fields_ = [("scale", C.c_double), ("num", C.c_int32), ("den", C.c_int32)]
 
 
+class ScalarOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("dst", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
+
+
 class RedOpts(C.Structure):
-    _fields_ = [("store", C.c_int32), ("halt_mode", C.c_int), ("halt_threshold", C.c_double)]
+    _fields_ = [("store", C.c_int32), ("halt_mode", C.c_int), ("halt_threshold", C.c_double), ("n_post", C.c_int32),
+                ("post", ScalarOp * 8)]
+
+
+SOP = {"add": 0, "sub": 1, "mul": 2, "div": 3, "copy": 4}
 
 
 HALT_NEVER, HALT_IF_SQRT_LT, HALT_IF_LT = 0, 1, 2
@@ -258,6 +266,12 @@ class Context:
             v.upload(data)
         return v
 
+    def wrap(self, device_ptr: int, n_owned: int, n_ghost: int = 0) -> "Vector":
+        """a vector over caller-owned device memory (fsb_vec_wrap)"""
+        h = _p()
+        check(lib().fsb_vec_wrap(self.h, C.c_void_p(device_ptr), n_owned, n_ghost, C.byref(h)))
+        return Vector(self, n_owned, n_ghost, handle=h)
+
     def get(self, token: int) -> float:
         out = _dbl()
         check(lib().fsb_red_get(self.h, token, C.byref(out)))
@@ -372,8 +386,12 @@ class Vector:
 
     def dot_token(self, x): return self._tok(lib().fsb_vec_dot, self.h, x.h)
 
-    def dot_opts_token(self, x, store=0, halt_mode=HALT_NEVER, halt_threshold=0.0):
+    def dot_opts_token(self, x, store=0, halt_mode=HALT_NEVER, halt_threshold=0.0, post=()):
+        """post: [(op, dst, a, b), ...] scalar statements evaluated on the device once the value is stored"""
         o = RedOpts(store, halt_mode, halt_threshold)
+        o.n_post = len(post)
+        for k, (op, dst, a, b) in enumerate(post):
+            o.post[k] = ScalarOp(SOP[op], dst, a, b)
         t = _i64()
         check(lib().fsb_vec_dot_opts(self.h, x.h, C.byref(o), C.byref(t)))
         return t.value

@@ -134,7 +134,7 @@ static void setup_peer_reductions(fsb_ctx_s * c) {
 extern "C" {
 
 const char * fsb_last_error(void) { return g_last_error.c_str(); }
-int fsb_version(void) { return 100; }
+int fsb_version(void) { return 200; }
 
 int fsb_device_count(void) {
 	int n = 0;
@@ -791,6 +791,16 @@ static void push_red(int op, fsb_vec_t x, fsb_vec_t y, double a, fsb_token_t * t
 			p.store = o->store;
 		p.halt_mode = o->halt_mode;
 		p.halt_thr = o->halt_threshold;
+		FSB_REQUIRE(o->n_post >= 0 && o->n_post <= FSB_MAX_POST_OPS, "too many scalar statements on one reduction");
+		p.n_post = o->n_post;
+		for (int k = 0; k < o->n_post; ++k) {
+			const fsb_scalar_op & s = o->post[k];
+			FSB_REQUIRE(s.op >= FSB_SOP_ADD && s.op <= FSB_SOP_COPY, "unknown scalar operation");
+			for (fsb_scalar_t id : {s.dst, s.a, s.b})
+				FSB_REQUIRE(id >= 0 && id < fsb::MAX_SCALARS && c->scalar_used[id], "scalar statement names an unknown device scalar");
+			FSB_REQUIRE(s.dst > 0, "slot 0 is the constant 1.0");
+			p.post[k] = s;
+		}
 	}
 	p.token = new_token(c, fold_of(op));
 	*tok = p.token;

@@ -26,7 +26,20 @@ struct red_out {
 	int * halt; // flag to raise, used when halt_mode != 0
 	double halt_thr;
 	int halt_mode; // 0 none, 1: sqrt(value) < thr, 2: value < thr
+	// scalar statements evaluated by the publishing thread once the value is stored: slots[dst] = slots[a] op slots[b]
+	double * slots;
+	int n_post;
+	unsigned char post[8][4]; // {op, dst, a, b}
 };
+
+// 0 add, 1 sub, 2 mul, 3 div, 4 copy (fsb.h: FSB_SOP_*), one IEEE rounding each
+__device__ __forceinline__ void run_post_ops(const red_out & r) {
+	for (int k = 0; k < r.n_post; ++k) {
+		const double a = r.slots[r.post[k][2]], b = r.slots[r.post[k][3]];
+		const int op = r.post[k][0];
+		r.slots[r.post[k][1]] = op == 0 ? __dadd_rn(a, b) : op == 1 ? __dadd_rn(a, -b) : op == 2 ? __dmul_rn(a, b) : op == 3 ? __ddiv_rn(a, b) : a;
+	}
+}
 
 // Flagged 16-byte words ("LL" protocol, as NCCL's low-latency path): a double travels as two 8-byte halves
 // {32 data bits, 32 flag bits}.  8-byte stores are single-copy atomic over NVLink and PCIe, so a reader that finds the
@@ -200,6 +213,7 @@ __device__ __forceinline__ void publish(const red_out & r, double t) {
 		*r.d_extra = t;
 	if (r.halt_mode != 0 && (r.halt_mode == 1 ? sqrt(t) : t) < r.halt_thr)
 		*reinterpret_cast<volatile int *>(r.halt) = 1;
+	run_post_ops(r);
 	if (r.h_ll) // value and token in one flagged word: the host polls it, no fence needed
 		ll_store(r.h_ll, t, static_cast<unsigned>(r.token));
 }

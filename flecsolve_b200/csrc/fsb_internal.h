@@ -71,6 +71,8 @@ struct pending {
 	int store = -1;
 	int halt_mode = 0; // 0 none, 1 sqrt(value) < halt_thr, 2 value < halt_thr
 	double halt_thr = 0;
+	int n_post = 0; // RED: scalar statements evaluated once the value is stored (fsb_red_opts::post)
+	fsb_scalar_op post[FSB_MAX_POST_OPS] = {};
 };
 
 // interior sub-box of a padded array (structured-grid vectors); colexicographic dof order, x fastest

@@ -202,6 +202,13 @@ FSB_PROGRAM(p_bdf_error_norm, S_SCALE(1, 0), S_SCALE(2, 0), S_ADDS(2, 2), S_LIN2
 FSB_PROGRAM(p_cgdev_update_jacobi, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), R_DOT(3, 3), S_MUL(5, 4, 3), R_DOT(3, 5))
 FSB_PROGRAM(p_cgdev_update_copy, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), R_DOT(3, 3), S_SCALE(4, 3), R_DOT(3, 4))
 
+// Single-reduction CG (solvers/cg_sr.hh): the whole vector side of an iteration is ONE pass
+//   p = u + b p ; s = w + b s ; x += a p ; r -= a s ; |r|^2 ; u = dinv * r ; r.u        (96 B/row)
+FSB_PROGRAM(p_cgsr_update_jacobi, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), S_LIN2(4, 1, 4), S_LIN2(5, 3, 5), R_DOT(5, 5), S_MUL(0, 6, 5),
+            R_DOT(5, 0))
+FSB_PROGRAM(p_cgsr_update_copy, S_LIN2(1, 0, 1), S_LIN2(3, 2, 3), S_LIN2(4, 1, 4), S_LIN2(5, 3, 5), R_DOT(5, 5), S_SCALE(0, 5),
+            R_DOT(5, 0))
+
 static registry_t & registry() {
 	static registry_t r = [] {
 		registry_t g;
@@ -227,6 +234,7 @@ static registry_t & registry() {
 		g.add<p_axpy2_same_sumsq>(); g.add<p_bdf_error_norm>();
 		g.add_dev<p_cgdev_update_jacobi>(); g.add_dev<p_cgdev_update_copy>(); g.add_dev<p_lin2_zy>();
 		g.add_dev<p_cg_update>(); g.add_dev<p_axpy2>();
+		g.add_dev<p_cgsr_update_jacobi>(); g.add_dev<p_cgsr_update_copy>();
 		return g;
 	}();
 	return r;
@@ -296,9 +304,11 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 	raw_stmt rs[MAXS];
 	fsb_vec_s * vecs[3 * MAXS];
 	int nvec = 0;
+	// slots are keyed on the device storage, not on the handle: two handles over the same memory (fsb_vec_wrap) are one
+	// slot, so a statement reading through one sees what an earlier statement of the group wrote through the other
 	auto id_of = [&](fsb_vec_s * v) {
 		for (int k = 0; k < nvec; ++k)
-			if (vecs[k] == v)
+			if (vecs[k]->d == v->d)
 				return k;
 		vecs[nvec] = v;
 		return nvec++;
@@ -363,6 +373,20 @@ static bool bind_group(fsb_ctx_s * c, const pending * q, int len, bound_group & 
 	return true;
 }
 
+// the scalar statements a reduction carries (fsb_red_opts::post), in the compact form the kernels read
+static void fill_post(fsb_ctx_s * c, const pending & red, red_out & r) {
+	r.slots = c->d_scalars;
+	r.n_post = std::min(red.n_post, FSB_MAX_POST_OPS);
+	for (int k = 0; k < FSB_MAX_POST_OPS; ++k) {
+		if (k >= r.n_post)
+			break;
+		r.post[k][0] = static_cast<unsigned char>(red.post[k].op);
+		r.post[k][1] = static_cast<unsigned char>(red.post[k].dst);
+		r.post[k][2] = static_cast<unsigned char>(red.post[k].a);
+		r.post[k][3] = static_cast<unsigned char>(red.post[k].b);
+	}
+}
+
 // where a finished reduction goes.  One rank / peer-memory all-reduce: the producing kernel has the
 // all-rank value, so it also serves the scalar slot and the convergence test; NCCL transport: the
 // kernel only leaves the rank-local value in d_results and finish_reduction_nccl() does the rest.
@@ -377,15 +401,17 @@ void fill_red_out(fsb_ctx_s * c, const pending & red, red_out & r) {
 		r.halt = c->d_halt;
 		r.halt_thr = red.halt_thr;
 		r.halt_mode = red.halt_mode;
+		fill_post(c, red, r);
 	}
 }
 
-__global__ void after_allreduce_kernel(const double * value, double * extra, int * halt, int mode, double thr) {
+__global__ void after_allreduce_kernel(const double * value, double * extra, int * halt, int mode, double thr, red_out post) {
 	const double t = *value;
 	if (extra)
 		*extra = t;
 	if (mode != 0 && (mode == 1 ? sqrt(t) : t) < thr)
 		*halt = 1;
+	run_post_ops(post);
 }
 
 void finish_reduction_nccl(fsb_ctx_s * c, const pending & red) {
@@ -394,9 +420,11 @@ void finish_reduction_nccl(fsb_ctx_s * c, const pending & red) {
 	const ncclRedOp_t op = f == 0 ? ncclSum : (f == 1 ? ncclMax : ncclMin);
 	FSB_NCCL(ncclAllReduce(c->d_results + slot, c->d_results + slot, 1, ncclDouble, op, c->nccl, c->stream));
 	c->stats[FSB_STAT_ALLREDUCES]++;
-	if (red.store >= 0 || red.halt_mode != 0) {
+	if (red.store >= 0 || red.halt_mode != 0 || red.n_post > 0) {
+		red_out post{};
+		fill_post(c, red, post);
 		after_allreduce_kernel<<<1, 1, 0, c->stream>>>(c->d_results + slot, red.store >= 0 ? c->d_scalars + red.store : nullptr,
-		                                               c->d_halt, red.halt_mode, red.halt_thr);
+		                                               c->d_halt, red.halt_mode, red.halt_thr, post);
 		FSB_CUDA(cudaGetLastError());
 		c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
 	}
@@ -472,13 +500,41 @@ void flush(fsb_ctx_s * c) {
 		// a statement whose coefficient is produced by a reduction of this very run needs the finished
 		// (grid-wide, all-rank) value: it starts the next launch
 		auto needs_result_of_run = [&](int k) {
-			for (int m = i; m < k; ++m)
-				if (q[m].kind == pending::RED && q[m].store >= 0 &&
-				    (q[m].store == q[k].a_num || q[m].store == q[k].a_den || q[m].store == q[k].b_num || q[m].store == q[k].b_den))
+			auto used = [&](int slot) {
+				return slot > 0 && (slot == q[k].a_num || slot == q[k].a_den || slot == q[k].b_num || slot == q[k].b_den);
+			};
+			for (int m = i; m < k; ++m) {
+				if (q[m].kind != pending::RED)
+					continue;
+				if (q[m].store >= 0 && used(q[m].store))
 					return true;
+				for (int t = 0; t < q[m].n_post; ++t)
+					if (used(q[m].post[t].dst))
+						return true;
+			}
 			return false;
 		};
-		while (j < total && j - i < cap && q[j].kind != pending::SPMV && same_layout(q[i], q[j]) && !needs_result_of_run(j))
+		// operands that overlap in memory without being the same vector (wrapped sub-ranges) cannot share a launch:
+		// element i of one is element i + k of the other
+		auto overlaps_partially = [&](int k) {
+			fsb_vec_s * mine[3] = {q[k].z, q[k].x, q[k].y};
+			for (int m = i; m <= k; ++m) {
+				fsb_vec_s * theirs[3] = {q[m].z, q[m].x, q[m].y};
+				for (fsb_vec_s * u : mine)
+					for (fsb_vec_s * v : theirs) {
+						if (!u || !v || u->d == v->d || (u->owns && v->owns))
+							continue;
+						const double *ub = u->d, *ue = u->d + u->n_owned + u->n_ghost, *vb = v->d, *ve = v->d + v->n_owned + v->n_ghost;
+						if (ub < ve && vb < ue)
+							return true;
+					}
+			}
+			return false;
+		};
+		if (overlaps_partially(i))
+			throw error(FSB_ERR_ARG, "operands of one statement overlap in memory without being the same vector");
+		while (j < total && j - i < cap && q[j].kind != pending::SPMV && same_layout(q[i], q[j]) && !needs_result_of_run(j) &&
+		       !overlaps_partially(j))
 			++j;
 		// the whole run as one launch: a registered instantiation if there is one, else the generic
 		// program kernel; a run that exceeds the slot limits is cut at the longest prefix that fits

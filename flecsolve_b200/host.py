@@ -15,7 +15,7 @@ _lib = None
 
 STOP_REASONS = ["converged_atol", "converged_rtol", "converged_user", "diverged_dtol", "diverged_iters",
                 "diverged_breakdown", "unknown"]
-SOLVERS = {"cg": 0, "gmres": 1, "bicgstab": 2, "fcg": 3, "cg_device": 4}
+SOLVERS = {"cg": 0, "gmres": 1, "bicgstab": 2, "fcg": 3, "cg_device": 4, "cg_sr": 5}
 PRECONDS = {None: 0, "none": 0, "identity": 0, "dinv": 1, "jacobi": 1, "relax": 2}
 
 

@@ -24,6 +24,7 @@
 #include "flecsolve/solvers/bicgstab.hh"
 #include "flecsolve/solvers/cg.hh"
 #include "flecsolve/solvers/cg_device.hh"
+#include "flecsolve/solvers/cg_sr.hh"
 #include "flecsolve/solvers/factory.hh"
 #include "flecsolve/matrices/io/matrix_market.hh"
 #include "flecsolve/topo/narray.hh"
@@ -114,7 +115,7 @@ struct fsbh_info {
 };
 
 struct fsbh_options {
-	int solver; // 0 cg, 1 gmres, 2 bicgstab, 3 fcg, 4 cg with device-resident scalars (cg_device.hh)
+	int solver; // 0 cg, 1 gmres, 2 bicgstab, 3 fcg, 4 cg with device-resident scalars (cg_device.hh), 5 single-reduction cg (cg_sr.hh)
 	int precond; // 0 identity (op::I), 1 diagonal inverse, 2 weighted Jacobi relaxation
 	float omega; // precond 2
 	int nrelax; // precond 2
@@ -202,6 +203,11 @@ solve_info run_solver(session & S_, const fsbh_options & o, P precond_handle, re
 	if (o.solver == 4) {
 		cg_device::settings st{{o.maxiter, o.rtol, o.atol, o.use_zero_guess != 0}, o.lag};
 		auto slv = cg_device::solver(st, cg_device::make_work(x))(op::ref(A), precond_handle, std::ref(rec));
+		return slv(b, x);
+	}
+	if (o.solver == 5) {
+		cg_sr::settings st{{o.maxiter, o.rtol, o.atol, o.use_zero_guess != 0}, o.lag};
+		auto slv = cg_sr::solver(st, cg_sr::make_work(x))(op::ref(A), precond_handle, std::ref(rec));
 		return slv(b, x);
 	}
 	if (o.solver == 3) {
@@ -773,7 +779,7 @@ int fsbh_config_dump(const char * fname, int kind, const char * prefix, char * o
 		}
 		if (kind == 1 || kind == 3) {
 			auto s = kind == 1 ? read_config(fname, krylov_factory::options(prefix)) : *ks;
-			static const char * names[] = {"cg", "gmres", "bicgstab", "cg-device"};
+			static const char * names[] = {"cg", "gmres", "bicgstab", "cg-device", "cg-sr"};
 			os << "\"type\": \"" << names[static_cast<int>(s.target_id.value())] << "\", ";
 			std::visit(
 				[&](const auto & t) {
@@ -782,7 +788,7 @@ int fsbh_config_dump(const char * fname, int kind, const char * prefix, char * o
 					if constexpr (std::is_same_v<T, gmres::settings>)
 						os << ", \"max_krylov_dim\": " << t.max_krylov_dim << ", \"pre_side\": \"" << t.pre_side
 						   << "\", \"restart\": " << (t.restart ? "true" : "false");
-					if constexpr (std::is_same_v<T, cg_device::settings>)
+					if constexpr (std::is_same_v<T, cg_device::settings> || std::is_same_v<T, cg_sr::settings>)
 						os << ", \"lag\": " << t.lag;
 				},
 				s.target_settings);

@@ -39,10 +39,35 @@ void linear_sum(Z & z, fsb_coef a, const X & x, fsb_coef b, const Y & y) {
 	check(fsb_vec_linear_sum_c(z.data.handle(), a, x.data.handle(), b, y.data.handle()));
 }
 
-// <x, y>, optionally kept in `store` and tested against the halt threshold
+// scalar statements a reduction carries: evaluated on the device, in order, once its all-rank value is stored
+struct scalar_program {
+	fsb_scalar_op ops[FSB_MAX_POST_OPS];
+	int n = 0;
+	scalar_program & then(int op, const scalar & dst, const scalar & a, const scalar & b) {
+		if (n == FSB_MAX_POST_OPS)
+			throw error(FSB_ERR_ARG, "too many scalar statements on one reduction");
+		ops[n++] = fsb_scalar_op{op, dst.id(), a.id(), b.id()};
+		return *this;
+	}
+	scalar_program & div(const scalar & dst, const scalar & a, const scalar & b) { return then(FSB_SOP_DIV, dst, a, b); }
+	scalar_program & mul(const scalar & dst, const scalar & a, const scalar & b) { return then(FSB_SOP_MUL, dst, a, b); }
+	scalar_program & sub(const scalar & dst, const scalar & a, const scalar & b) { return then(FSB_SOP_SUB, dst, a, b); }
+	scalar_program & copy(const scalar & dst, const scalar & a) { return then(FSB_SOP_COPY, dst, a, a); }
+};
+
+// <x, y>, optionally kept in `store`, tested against the halt threshold, and followed by scalar statements
 template<class X, class Y>
-device_future dot(const X & x, const Y & y, const scalar * store, int halt_mode = FSB_HALT_NEVER, double threshold = 0) {
-	fsb_red_opts o{store ? store->id() : 0, halt_mode, threshold};
+device_future dot(const X & x, const Y & y, const scalar * store, int halt_mode = FSB_HALT_NEVER, double threshold = 0,
+                  const scalar_program * post = nullptr) {
+	fsb_red_opts o{};
+	o.store = store ? store->id() : 0;
+	o.halt_mode = halt_mode;
+	o.halt_threshold = threshold;
+	if (post) {
+		o.n_post = post->n;
+		for (int k = 0; k < post->n; ++k)
+			o.post[k] = post->ops[k];
+	}
 	device_future f{x.data.ctx(), 0};
 	check(fsb_vec_dot_opts(x.data.handle(), y.data.handle(), &o, &f.token));
 	return f;

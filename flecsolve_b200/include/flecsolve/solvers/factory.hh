@@ -1,5 +1,5 @@
 // krylov_factory: the Krylov solver a configuration file names,
-//     [linear-solver]            type = cg | gmres | bicgstab | cg-device
+//     [linear-solver]            type = cg | gmres | bicgstab | cg-device | cg-sr
 //     [linear-solver.options]    maxiter = ...   (the chosen solver's own option table)
 // built over the caller's operator / preconditioner / diagnostic handles:
 //     auto s   = read_config(file, krylov_factory::options("linear-solver"));
@@ -7,7 +7,7 @@
 //
 // Same surface as the reference (flecsolve/solvers/factory.hh:28-89: krylov_target, krylov_registry<T>,
 // krylov_factory_policy, krylov_factory = op::factory<policy>).  `cg-device` is the extra target of
-// SURVEY 8(f) N1 (solvers/cg_device.hh).  The reference's fourth target, nka, is a nonlinear accelerator
+// SURVEY 8(f) N1 (solvers/cg_device.hh), `cg-sr` its single-reduction sibling (solvers/cg_sr.hh).  The reference's fourth target, nka, is a nonlinear accelerator
 // outside the scoped solve loop: its name is rejected as an invalid value rather than mapped to something else.
 #ifndef FLECSOLVE_B200_SOLVERS_FACTORY_HH
 #define FLECSOLVE_B200_SOLVERS_FACTORY_HH
@@ -23,15 +23,16 @@
 #include "flecsolve/solvers/bicgstab.hh"
 #include "flecsolve/solvers/cg.hh"
 #include "flecsolve/solvers/cg_device.hh"
+#include "flecsolve/solvers/cg_sr.hh"
 #include "flecsolve/solvers/gmres.hh"
 
 namespace flecsolve {
 
-enum class krylov_target { cg, gmres, bicgstab, cg_device };
+enum class krylov_target { cg, gmres, bicgstab, cg_device, cg_sr };
 
 namespace detail {
 // spelling of each target in configuration files, indexed by the enum value
-inline constexpr std::array<std::string_view, 4> krylov_target_names{"cg", "gmres", "bicgstab", "cg-device"};
+inline constexpr std::array<std::string_view, 5> krylov_target_names{"cg", "gmres", "bicgstab", "cg-device", "cg-sr"};
 
 // what the operator factory needs to know about one solver family: its settings and option types and
 // how to bind it; WorkFactory is the family's `make_work` object type
@@ -61,6 +62,7 @@ FLECSOLVE_KRYLOV_FAMILY(cg, cg);
 FLECSOLVE_KRYLOV_FAMILY(gmres, gmres);
 FLECSOLVE_KRYLOV_FAMILY(bicgstab, bicgstab);
 FLECSOLVE_KRYLOV_FAMILY(cg_device, cg_device);
+FLECSOLVE_KRYLOV_FAMILY(cg_sr, cg_sr);
 #undef FLECSOLVE_KRYLOV_FAMILY
 
 inline std::ostream & operator<<(std::ostream & os, krylov_target t) {
@@ -81,7 +83,7 @@ inline std::istream & operator>>(std::istream & is, krylov_target & t) {
 
 struct krylov_factory_policy {
 	using target = krylov_target;
-	using targets = includes<target::cg, target::gmres, target::bicgstab, target::cg_device>;
+	using targets = includes<target::cg, target::gmres, target::bicgstab, target::cg_device, target::cg_sr>;
 	template<target T>
 	using registry = krylov_registry<T>;
 };

@@ -79,7 +79,7 @@ enum fsb_stat {
 };
 
 const char * fsb_last_error(void);
-int fsb_version(void);
+int fsb_version(void); /* 200: this layout of fsb_red_opts */
 /* number of visible CUDA devices (0 when none / no driver) */
 int fsb_device_count(void);
 
@@ -139,7 +139,9 @@ int fsb_debug_jit_compile(const int32_t * raw, int n, int device_coefficients, i
  * space: n_owned entries followed by n_ghost ghost entries
  * (topo/csr.hh:420-431, 524-526; vectors/data/topo_view.hh:24-71).          */
 int fsb_vec_create(fsb_ctx_t ctx, int64_t n_owned, int64_t n_ghost, fsb_vec_t * out);
-/* wrap caller-owned device memory of (n_owned + n_ghost) doubles, 16-byte aligned */
+/* wrap caller-owned device memory of (n_owned + n_ghost) doubles, 16-byte aligned.  Handles that wrap the SAME memory
+ * are the same vector to every call (fused statements see each other's writes); handles whose ranges overlap only
+ * partly never share a fused launch, and using two of them in ONE call is rejected (FSB_ERR_ARG). */
 int fsb_vec_wrap(fsb_ctx_t ctx, double * device_ptr, int64_t n_owned, int64_t n_ghost, fsb_vec_t * out);
 int fsb_vec_destroy(fsb_vec_t v);
 int64_t fsb_vec_local_size(fsb_vec_t v); /* vec::ops::topo_view::local_size, operations/topo_view.hh:276-280 */
@@ -217,10 +219,21 @@ typedef struct fsb_coef {
 	fsb_scalar_t num, den;
 } fsb_coef;
 enum { FSB_HALT_NEVER = 0, FSB_HALT_IF_SQRT_LT = 1, FSB_HALT_IF_LT = 2 };
+/* scalar arithmetic carried by a reduction: once its all-rank value is stored, the thread that publishes it evaluates
+ * up to FSB_MAX_POST_OPS statements  slot[dst] = slot[a] op slot[b]  in order (IEEE double, one rounding each) -- how
+ * single-reduction CG keeps  beta = g'/g,  alpha = g' / (d - beta g'/alpha)  on the device without a launch of its own */
+enum { FSB_SOP_ADD = 0, FSB_SOP_SUB = 1, FSB_SOP_MUL = 2, FSB_SOP_DIV = 3, FSB_SOP_COPY = 4 /* slot[dst] = slot[a] */ };
+#define FSB_MAX_POST_OPS 8
+typedef struct fsb_scalar_op {
+	int32_t op; /* FSB_SOP_* */
+	fsb_scalar_t dst, a, b;
+} fsb_scalar_op;
 typedef struct fsb_red_opts {
 	fsb_scalar_t store; /* slot that receives the value (0: none) */
 	int halt_mode; /* FSB_HALT_*: raise the halt flag when [sqrt](value) < halt_threshold */
 	double halt_threshold;
+	int32_t n_post; /* scalar statements evaluated after the value is stored (0: none) */
+	fsb_scalar_op post[FSB_MAX_POST_OPS];
 } fsb_red_opts;
 int fsb_scalar_create(fsb_ctx_t ctx, fsb_scalar_t * out);
 int fsb_scalar_destroy(fsb_ctx_t ctx, fsb_scalar_t s);

@@ -117,6 +117,11 @@ int finish(fsb_ctx_s * c, double v, fsb_token_t * tok, const fsb_red_opts * o = 
 			c->halted = true;
 		if (o->halt_mode == FSB_HALT_IF_LT && v < o->halt_threshold)
 			c->halted = true;
+		for (int k = 0; k < o->n_post; ++k) {
+			const fsb_scalar_op & s = o->post[k];
+			const double a = c->scalars[s.a], b = c->scalars[s.b];
+			c->scalars[s.dst] = s.op == FSB_SOP_ADD ? a + b : s.op == FSB_SOP_SUB ? a - b : s.op == FSB_SOP_MUL ? a * b : s.op == FSB_SOP_DIV ? a / b : a;
+		}
 	}
 	return FSB_OK;
 }

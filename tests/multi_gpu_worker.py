@@ -105,6 +105,11 @@ def main():
     m = min(len(hist), len(dhist), 30)
     assert np.allclose(dhist[:m], hist[:m], rtol=1e-8)
     assert np.abs(xd - xo[lo:hi]).max() <= 1e-6
+    # single-reduction CG: the scalar recurrences ride on the all-reduced <w,u>, identically on every rank
+    xr, rinfo, rhist = S.solve(b[lo:hi], np.zeros(hi - lo), solver="cg_sr", precond="dinv", rtol=1e-9, maxiter=1000,
+                               history_cap=1000, lag=2)
+    assert rinfo.reason == "converged_rtol" and abs(rinfo.iters - info.iters) <= 2, (rinfo.iters, info.iters)
+    assert np.abs(xr - xo[lo:hi]).max() <= 1e-6
     if P > 1 and os.environ.get("FSB_P2P_REDUCE") == "0":
         assert ctx.stat("allreduces") > 0  # the NCCL path really ran
     elif P > 1:

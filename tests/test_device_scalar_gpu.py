@@ -121,6 +121,52 @@ def test_cg_device_walks_the_same_iterates_as_cg(ctx, kind, dims, precond, lag):
     S.close(); A.destroy()
 
 
+@pytest.mark.parametrize("lag", [0, 2])
+@pytest.mark.parametrize("precond", [None, "dinv"])
+@pytest.mark.parametrize("kind,dims", [(5, (48, 48, 1)), (7, (20, 18, 16)), (27, (12, 12, 12))])
+def test_single_reduction_cg(ctx, kind, dims, precond, lag):
+    """solvers/cg_sr.hh: two launches per iteration (one fused vector pass, one SpMV that also carries <w,u> and the
+    scalar recurrences), CG's iterates to rounding, same stop reason, iteration count +- 2"""
+    n, rp, col, val = _system(kind, dims, precond == "dinv")
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    S = H.Session(ctx, A)
+    As = sp.csr_matrix((val, col, rp))
+    b = As @ np.linspace(1, 2, n)
+    x0 = np.random.default_rng(7).random(n)
+    x, info, hist = S.solve(b, x0, solver="cg", precond=precond, rtol=1e-9, maxiter=2000, history_cap=2000)
+    ctx.reset_stats()
+    xs, sinfo, shist = S.solve(b, x0, solver="cg_sr", precond=precond, rtol=1e-9, maxiter=2000, history_cap=2000, lag=lag)
+    launches, unmatched = ctx.stat("launches"), ctx.stat("unmatched_groups")
+    assert sinfo.reason == info.reason == "converged_rtol"
+    assert abs(sinfo.iters - info.iters) <= 2, (sinfo.iters, info.iters)
+    m = min(len(hist), len(shist)) * 2 // 3
+    assert np.allclose(shist[:m], hist[:m], rtol=1e-6)
+    res = np.linalg.norm(b - As @ xs)
+    assert res <= 2 * np.float32(1e-9) * np.linalg.norm(b)
+    assert launches <= 2 * (sinfo.iters + lag) + 14, launches
+    assert unmatched <= 2  # the iteration's groups run through ahead-of-time kernels
+    S.close(); A.destroy()
+
+
+def test_scalar_statements_ride_on_a_reduction(ctx):
+    """fsb_red_opts::post: slot arithmetic evaluated on the device once the reduction's value is stored"""
+    n = 1000
+    x = ctx.vector(n)
+    x.set_scalar(2.0)
+    a, b, c = ctx.scalar(3.0), ctx.scalar(0.0), ctx.scalar(0.0)
+    launches = ctx.stat("launches")
+    # b = <x,x> = 4000 ; then c = b / a ; a = a * a ; b = c - a ; c = copy of a
+    t = x.dot_opts_token(x, store=b, post=[("div", c, b, a), ("mul", a, a, a), ("sub", b, c, a), ("copy", c, a, a)])
+    assert ctx.get(t) == 4.0 * n
+    assert ctx.stat("launches") - launches == 1
+    assert ctx.scalar_get(a) == 9.0 and ctx.scalar_get(b) == 4000.0 / 3.0 - 9.0 and ctx.scalar_get(c) == 9.0
+    with pytest.raises(F.FsbError):
+        x.dot_opts_token(x, post=[("add", 0, a, a)])  # slot 0 is the constant 1
+    for s in (a, b, c):
+        ctx.scalar_destroy(s)
+    x.destroy()
+
+
 def test_cg_device_maxiter_user_stop_and_early_exit(ctx):
     n, rp, col, val = _system(7, (10, 10, 10), False)
     A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)

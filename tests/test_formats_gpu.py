@@ -44,6 +44,7 @@ rtol = 1e-8
     ("gmres", "max-krylov-dim = 20\nrestart = true", dict(solver="gmres", max_krylov_dim=20, restart=True)),
     ("bicgstab", "", dict(solver="bicgstab")),
     ("cg-device", "lag = 1", dict(solver="cg_device", lag=1)),
+    ("cg-sr", "lag = 1", dict(solver="cg_sr", lag=1)),
 ])
 def test_solver_named_by_config_file(ctx, tmp_path, kind, extra, direct, precond):
     path = os.path.join(HERE, "golden", "mtx", "lap30_sym.mtx")

@@ -104,6 +104,26 @@ def test_cg_device_is_the_same_iteration_as_cg(hc, entry, lag):
     S.close()
 
 
+@pytest.mark.parametrize("lag", [0, 2])
+@pytest.mark.parametrize("entry", [e for e in SOLVER_CASES if e["case"][2] == "cg"],
+                         ids=lambda e: "-".join(map(str, e["case"][:4])).replace(" ", ""))
+def test_single_reduction_cg_follows_cg(hc, entry, lag):
+    """Chronopoulos-Gear CG (solvers/cg_sr.hh): CG's iterates in exact arithmetic; in floating point the residual
+    history agrees to ~1e-6 while the residual is above rounding, and the iteration count to +- 2"""
+    (rp, col, val), M, b, x0, solver, precond, kw = G.problem(entry["case"])
+    A = hc.from_csr(len(rp) - 1, rp, col, val)
+    S = H.Session(hc.ctx, A)
+    x, info, hist = S.solve(b, x0, solver="cg_sr", precond="dinv" if precond else None, history_cap=2000, lag=lag, **kw)
+    ref = entry["info"]
+    assert info.status == ref["status"] and abs(info.iters - ref["iters"]) <= 2
+    rh = G.history(entry)
+    m = min(len(hist), len(rh)) * 2 // 3
+    assert np.allclose(hist[:m], rh[:m], rtol=1e-6)
+    As = sp.csr_matrix((val, col, rp))
+    assert np.linalg.norm(b - As @ x) <= 2 * np.float32(kw["rtol"]) * np.linalg.norm(b)
+    S.close()
+
+
 def test_fcg_and_maxiter_and_early_exit(hc):
     rp, col, val = O.stencil_csr(7, 9, 8, 7)
     n = len(rp) - 1
@@ -213,7 +233,8 @@ def test_config_chosen_solver_and_narray_example(hc, tmp_path):
     x0 = np.random.default_rng(7).random(n)
     for kind, extra, direct in (("cg", "", dict(solver="cg")), ("bicgstab", "", dict(solver="bicgstab")),
                                 ("gmres", "max-krylov-dim = 20\nrestart = true", dict(solver="gmres", max_krylov_dim=20, restart=True)),
-                                ("cg-device", "lag = 1", dict(solver="cg_device", lag=1))):
+                                ("cg-device", "lag = 1", dict(solver="cg_device", lag=1)),
+                                ("cg-sr", "lag = 1", dict(solver="cg_sr", lag=1))):
         cfg = tmp_path / f"{kind}.cfg"
         cfg.write_text(f"[ls]\ntype = {kind}\n[ls.options]\nmaxiter = 300\nuse-zero-guess = false\nrtol = 1e-8\n{extra}\n")
         x, info, hist = S.solve_config(str(cfg), "ls", b, x0, precond="dinv", history_cap=300)

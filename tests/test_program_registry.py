@@ -40,6 +40,11 @@ KRYLOV_GROUPS = {
     "cg_device update (jacobi)": ([(LIN2, x, p, x), (LIN2, r, w, r), (DOT, -1, r, r), (MUL, z, dinv, r), (DOT, -1, r, z)], True),
     "cg_device update (identity)": ([(LIN2, x, p, x), (LIN2, r, w, r), (DOT, -1, r, r), (SCALE, z, r, -1), (DOT, -1, r, z)], True),
     "cg_device direction": ([(LIN2, p, z, p)], True),
+    # cg_sr.hh: the whole vector side of a single-reduction CG iteration in one pass (z plays u, t plays s = A p)
+    "cg_sr update (jacobi)": ([(LIN2, p, z, p), (LIN2, t, w, t), (LIN2, x, p, x), (LIN2, r, t, r), (DOT, -1, r, r),
+                               (MUL, z, dinv, r), (DOT, -1, r, z)], True),
+    "cg_sr update (identity)": ([(LIN2, p, z, p), (LIN2, t, w, t), (LIN2, x, p, x), (LIN2, r, t, r), (DOT, -1, r, r),
+                                 (SCALE, z, r, -1), (DOT, -1, r, z)], True),
     # gmres.hh: modified Gram-Schmidt step, normalise + store (+ precondition)
     "gmres mgs step": ([(LIN2, v, p, v), (DOT, -1, v, w)], False),
     "gmres normalise + copy": ([(SCALE, v, v, -1), (SCALE, w, v, -1)], False),

@@ -251,3 +251,37 @@ def test_multivector_closed_forms_of_the_reference_test(ctx):
         assert out[11] == -7
         assert np.all(out[12:18] == 1.0), out[12:18]
         S.close(); A.destroy()
+
+
+def test_handles_over_the_same_memory_are_one_vector(ctx):
+    """fsb_vec_wrap: two handles over the same storage behave as one vector inside a fused group (a statement reading
+    through one sees what an earlier statement wrote through the other); partially overlapping ranges never share a
+    launch, and are rejected inside one call"""
+    n = 4096
+    rng = np.random.default_rng(5)
+    base, y = ctx.vector(n + 2), ctx.vector(n)
+    yh = rng.standard_normal(n)
+    y.upload(yh)
+    ptr = base.device_ptr
+    a, b = ctx.wrap(ptr, n), ctx.wrap(ptr, n)
+    launches = ctx.stat("launches")
+    a.set_scalar(2.0)          # writes through a
+    y.axpy(3.0, b, y)          # reads through b: must see 2.0 although both statements share a launch
+    t = b.sumsq_token()
+    got = y.download()
+    assert ctx.stat("launches") - launches == 1
+    assert np.array_equal(got, 3.0 * 2.0 + yh) and ctx.get(t) == 4.0 * n
+    # shifted by two entries: element i of c is element i + 2 of a
+    c = ctx.wrap(ptr + 16, n)
+    launches = ctx.stat("launches")
+    a.set_scalar(1.0)
+    c.scale(5.0, c)            # its own launch, after the first one completed
+    ctx.sync()
+    assert ctx.stat("launches") - launches == 2
+    full = np.zeros(n + 2); base_h = base.download(); full[:] = base_h
+    assert np.array_equal(full[:2], [1.0, 1.0]) and np.all(full[2:n] == 5.0)
+    with pytest.raises(F.FsbError):
+        a.add(a, c)
+        ctx.sync()
+    for v in (a, b, c, base, y):
+        v.destroy()
