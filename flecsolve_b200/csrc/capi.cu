@@ -24,6 +24,11 @@ namespace fsb {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string & m) { g_last_error = m; }
 
+bool pdl_enabled() {
+	static const bool on = !(std::getenv("FSB_PDL") && std::atoi(std::getenv("FSB_PDL")) == 0);
+	return on;
+}
+
 // the host only hands out slots (and stamps the kind); the kernels write the times
 unsigned long long * timeline_slot(fsb_ctx_s * c, int kind) {
 	if (!c->d_timeline || c->timeline_used >= c->timeline_cap)

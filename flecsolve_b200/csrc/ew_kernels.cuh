@@ -112,6 +112,14 @@ __device__ __forceinline__ void tl_mark_max(unsigned long long * tl, int word) {
 		atomicMax(tl + word, tl_now());
 }
 
+// Programmatic dependent launch: kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// scheduled while the previous kernel of the stream is still draining (its launch latency and prologue hide behind
+// that tail); this is the point where they wait for the previous kernel's memory to be complete and visible.  Without
+// the attribute it returns at once.
+__device__ __forceinline__ void grid_dependency_wait() {
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct ew_args {
 	double * v[MAXV];
 	double s[MAXSC];
@@ -338,6 +346,7 @@ __device__ __forceinline__ void run_elements_box(const ew_args & a, const SC & s
 template<class PT, bool DEV, bool BOX>
 __device__ __forceinline__ void ew_program_body(const ew_args & a) {
 	constexpr program P = PT::value;
+	grid_dependency_wait();
 	tl_begin(a.tl);
 	auto run = [&](const auto & sc, double (&acc)[MAXR]) {
 		if constexpr (BOX)
@@ -379,6 +388,8 @@ __device__ __forceinline__ void ew_program_body(const ew_args & a) {
 		__syncthreads();
 		if (is_last) {
 			__threadfence();
+			// fold every reduction's partials (thread 0 ends up with the rank-local values) ...
+			__shared__ double local[MAXR], gathered[MAXR][XRANK_MAX];
 			[&]<int... R>(iseq<R...>) {
 				(([&] {
 					 constexpr int F = red_fold<PT, R>();
@@ -387,18 +398,46 @@ __device__ __forceinline__ void ew_program_body(const ew_args & a) {
 						 t = fold<F>(t, __ldcg(&a.partials[R * a.partial_stride + b]));
 					 t = block_fold<F>(t, scratch);
 					 if (threadIdx.x == 0)
-						 tl_mark_min(a.tl, 6);
-					 if (a.xr)
-						 t = xrank_allreduce<F>(a.xr, t, a.r[R].token, scratch);
-					 if (threadIdx.x == 0) {
-						 publish(a.r[R], t);
-						 tl_mark_max(a.tl, 7);
-					 }
+						 local[R] = t;
 				 }()),
 				 ...);
 			}(make_iseq<P.nr>{});
+			__syncthreads();
 			if (threadIdx.x == 0)
+				tl_mark_min(a.tl, 6);
+			if (a.xr) {
+				// ... exchange ALL of them with the other ranks at once: thread (R, q) stores reduction R's value into
+				// rank q's mailbox and picks up q's value from this rank's, so k reductions cost one round trip
+				const int np = a.xr->nranks, me = a.xr->me;
+				if (static_cast<int>(threadIdx.x) < np * P.nr) {
+					const int R = threadIdx.x / np, q = threadIdx.x % np;
+					const long long token = a.r[R].token;
+					const size_t slot = static_cast<size_t>(token % XRANK_RING);
+					ll_store(a.xr->mailbox[q] + (slot * np + me) * 2, local[R], static_cast<unsigned>(token));
+					double v;
+					if (!ll_load(a.xr->mailbox[me] + (slot * np + q) * 2, static_cast<unsigned>(token), v))
+						*reinterpret_cast<volatile int *>(a.xr->error_flag) = 1;
+					gathered[R][q] = v;
+				}
+				__syncthreads();
+			}
+			if (threadIdx.x == 0) {
+				[&]<int... R>(iseq<R...>) {
+					(([&] {
+						 constexpr int F = red_fold<PT, R>();
+						 double t = local[R];
+						 if (a.xr) { // rank order: the same bits on every rank
+							 t = fold_identity<F>();
+							 for (int q = 0; q < a.xr->nranks; ++q)
+								 t = fold<F>(t, gathered[R][q]);
+						 }
+						 publish(a.r[R], t);
+					 }()),
+					 ...);
+				}(make_iseq<P.nr>{});
+				tl_mark_max(a.tl, 7);
 				*a.counter = 0u;
+			}
 		}
 	}
 	tl_end(a.tl);
@@ -451,6 +490,7 @@ template<int UNUSED = 0> // template only so the header may be included by sever
 __global__ void __launch_bounds__(EW_BLOCK) ew_interp_kernel(const __grid_constant__ interp_args ia) {
 	const ew_args & a = ia.a;
 	const program & P = ia.p;
+	grid_dependency_wait();
 	tl_begin(a.tl);
 	__shared__ int rfold[MAXR];
 	if (threadIdx.x == 0)

@@ -253,6 +253,24 @@ namespace fsb {
 enum { TL_KIND_SPMV = 1, TL_KIND_SPMV_OFFD = 2, TL_KIND_SPMV_FUSED = 3, TL_KIND_EW = 16, TL_KIND_HALO_PUSH = 32, TL_KIND_HALO_UNPACK = 33 };
 unsigned long long * timeline_slot(fsb_ctx_s * c, int kind);
 
+// Launch with programmatic stream serialisation: the kernel may be scheduled while its predecessor in the stream
+// drains; it calls grid_dependency_wait() before it touches anything the predecessor wrote (FSB_PDL=0 turns it off).
+bool pdl_enabled();
+template<class Kernel, class Args>
+void launch_dependent(Kernel kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const Args & args) {
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = pdl_enabled() ? 1 : 0;
+	FSB_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+}
+
 // queue / fuser (fuser.cu)
 void enqueue(fsb_ctx_s * c, const pending & p);
 void flush(fsb_ctx_s * c);

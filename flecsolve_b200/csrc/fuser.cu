@@ -32,7 +32,7 @@ static void launch_program(const ew_args & a, int want, cudaStream_t s) {
 		resident = nb * SM_COUNT;
 	}
 	const int grid = want < resident ? want : resident;
-	ew_program_kernel<PT><<<grid, EW_BLOCK, 0, s>>>(a);
+	launch_dependent(ew_program_kernel<PT>, dim3(grid), dim3(EW_BLOCK), 0, s, a);
 }
 
 template<class PT>
@@ -45,7 +45,7 @@ static void launch_program_dev(const ew_args & a, int want, cudaStream_t s) {
 		resident = nb * SM_COUNT;
 	}
 	const int grid = want < resident ? want : resident;
-	ew_program_kernel<PT, true><<<grid, EW_BLOCK, 0, s>>>(a);
+	launch_dependent(ew_program_kernel<PT, true>, dim3(grid), dim3(EW_BLOCK), 0, s, a);
 }
 
 static std::string key_of(const program & p) {
@@ -296,7 +296,7 @@ static void launch_interp(const bound_group & g, int want, cudaStream_t s) {
 	interp_args ia;
 	ia.a = g.args;
 	ia.p = g.prog;
-	ew_interp_kernel<0><<<want < resident ? want : resident, EW_BLOCK, 0, s>>>(ia);
+	launch_dependent(ew_interp_kernel<0>, dim3(want < resident ? want : resident), dim3(EW_BLOCK), 0, s, ia);
 }
 
 // bind queue[i, i+len) to a registered kernel; with allow_generic, to the generic kernel if there is none

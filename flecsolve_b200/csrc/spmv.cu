@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const 
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();
+	grid_dependency_wait(); // everything above is independent of the previous kernel (programmatic dependent launch)
 	tl_begin(a.tl);
 
 	double dot_acc = 0.0;
@@ -523,6 +524,7 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_window_kernel(const 
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();
+	grid_dependency_wait(); // everything above is independent of the previous kernel (programmatic dependent launch)
 	tl_begin(a.tl);
 
 	double dot_acc = 0.0;
@@ -957,8 +959,7 @@ static int launch_kernel(Kernel kern, const spmv_args & a, const spmv_config & k
 		b.chunk = std::min(env_chunk, 4);
 	if (b.halo) // every CTA pushes its share of the boundary entries while its first stage is in flight: a few stores and
 		b.push_parts = grid; // one system fence each, so no CTA starts its row blocks later than the others
-	kern<<<grid, k.threads, k.smem, s>>>(b);
-	FSB_CUDA(cudaGetLastError());
+	launch_dependent(kern, dim3(grid), dim3(k.threads), k.smem, s, b);
 	return grid;
 }
 

@@ -39,7 +39,7 @@ def main():
     xt = A.vector(x_true(A.row_begin, A.local_rows))
     A.spmv(xt, S.b)
     ctx.sync()
-    lag = 2 if solver == "cg_device" else 0
+    lag = 2 if solver in ("cg_device", "cg_sr") else 0
     warm = 10
 
     def run():
