@@ -147,7 +147,7 @@ struct fsb_ctx_s {
 	bool fusion = true;
 	bool trace = false;
 	bool reproducible = true; // SpMV row blocks statically assigned to CTAs (set from nranks at creation)
-	bool jit = false; // statement groups without a compiled instantiation: compile one at run time (jit.cu)
+	bool jit = true; // statement groups without a compiled instantiation: compile one at run time (jit.cu); FSB_JIT=0 turns it off
 	int spmv_rows_per_cta = 0; // 0 = auto
 	int spmv_threads = 0;
 

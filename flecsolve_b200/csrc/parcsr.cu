@@ -375,14 +375,25 @@ struct grid_desc {
 	long long nx, ny, nz;
 	long long row_begin, row_end; // owned global rows
 	long long lower, upper; // ghost counts below / above
+	long long reach; // how far (in row numbers) a stencil reaches: ghost candidates are [row_begin - reach, row_begin) and
+	                 // [row_end, row_end + reach), clipped to the grid
+	long long lo_base; // first candidate below
+	const int * rank_lo; // exclusive scan of the "referenced" flags over the candidates below / above =
+	const int * rank_hi; // position of each ghost in the sorted ghost list
 	double diag, off;
 	int kind; // 5, 7, 27
+	int neumann; // 7-point only: Neumann closure (kind 107 of the C ABI)
 };
 
 // visit the stencil of global row g in ascending column order
 template<class F>
 __device__ __forceinline__ void visit_stencil(const grid_desc & G, long long g, F && f) {
 	const long long i = g % G.nx, j = (g / G.nx) % G.ny, k = g / (G.nx * G.ny);
+	double diag = G.diag;
+	if (G.neumann) { // diagonal = (neighbours inside the box + shift) * scale = G.diag - missing * scale, as the oracle
+		const int missing = (i == 0) + (i == G.nx - 1) + (j == 0) + (j == G.ny - 1) + (k == 0) + (k == G.nz - 1);
+		diag = G.diag + missing * G.off;
+	}
 	if (G.kind == 27) {
 		for (int dk = -1; dk <= 1; ++dk)
 			for (int dj = -1; dj <= 1; ++dj)
@@ -400,7 +411,7 @@ __device__ __forceinline__ void visit_stencil(const grid_desc & G, long long g, 
 			f(g - G.nx, G.off);
 		if (i > 0)
 			f(g - 1, G.off);
-		f(g, G.diag);
+		f(g, diag);
 		if (i < G.nx - 1)
 			f(g + 1, G.off);
 		if (j < G.ny - 1)
@@ -451,15 +462,36 @@ __global__ void stencil_fill_offd_kernel(grid_desc G, const int32_t * __restrict
 	long long p = rowptr[cr];
 	visit_stencil(G, G.row_begin + row_ids[cr], [&](long long c, double v) {
 		if (c < G.row_begin) {
-			col[p] = static_cast<int32_t>(n_owned + (c - (G.row_begin - G.lower)));
+			col[p] = static_cast<int32_t>(n_owned + G.rank_lo[c - G.lo_base]);
 			val[p] = v;
 			++p;
 		}
 		else if (c >= G.row_end) {
-			col[p] = static_cast<int32_t>(n_owned + G.lower + (c - G.row_end));
+			col[p] = static_cast<int32_t>(n_owned + G.lower + G.rank_hi[c - G.row_end]);
 			val[p] = v;
 			++p;
 		}
+	});
+}
+
+// which candidates are referenced by an owned row (only rows within `reach` of either end of the block can)
+__global__ void stencil_mark_kernel(grid_desc G, int * __restrict__ flag_lo, int * __restrict__ flag_hi) {
+	const long long n = G.row_end - G.row_begin;
+	long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (r >= 2 * G.reach)
+		return;
+	if (r >= G.reach) { // second half of the threads: the rows at the upper end
+		r = n - 2 * G.reach + r;
+		if (r < G.reach) // short block: already covered by the first half
+			return;
+	}
+	if (r < 0 || r >= n)
+		return;
+	visit_stencil(G, G.row_begin + r, [&](long long c, double) {
+		if (c < G.row_begin)
+			flag_lo[c - G.lo_base] = 1;
+		else if (c >= G.row_end)
+			flag_hi[c - G.row_end] = 1;
 	});
 }
 
@@ -469,12 +501,18 @@ __global__ void iota_kernel(int32_t * p, long long n) {
 		p[i] = static_cast<int32_t>(i);
 }
 
-__global__ void colmap_kernel(grid_desc G, long long * colmap) {
+__global__ void colmap_kernel(grid_desc G, const int * __restrict__ flag_lo, const int * __restrict__ flag_hi,
+                              long long * __restrict__ colmap) {
 	const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (i < G.lower)
-		colmap[i] = G.row_begin - G.lower + i;
-	else if (i < G.lower + G.upper)
-		colmap[i] = G.row_end + (i - G.lower);
+	if (i < G.reach) {
+		if (flag_lo[i])
+			colmap[G.rank_lo[i]] = G.lo_base + i;
+	}
+	else if (i < 2 * G.reach) {
+		const long long k = i - G.reach;
+		if (flag_hi[k])
+			colmap[G.lower + G.rank_hi[k]] = G.row_end + k;
+	}
 }
 
 struct nonzero_flag {
@@ -501,23 +539,33 @@ static void exclusive_scan(fsb_ctx_s * c, In in, Out out, long long n) {
 fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t nx, int64_t ny, int64_t nz,
                                               double diag_shift, double scale) {
 	flush(c);
-	FSB_REQUIRE(kind == 5 || kind == 7 || kind == 27, "stencil: kind must be 5, 7 or 27");
+	const bool neumann = kind == 107;
+	if (neumann)
+		kind = 7;
+	FSB_REQUIRE(kind == 5 || kind == 7 || kind == 27, "stencil: kind must be 5, 7, 27 or 107");
 	FSB_REQUIRE(nx > 0 && ny > 0 && nz > 0, "stencil: empty grid");
 	FSB_REQUIRE(kind != 5 || nz == 1, "stencil: the 5-point operator is 2-D (nz == 1)");
 	const int P = c->nranks, me = c->rank;
 	const int64_t plane = nx * ny;
-	FSB_REQUIRE(P == 1 || nz % P == 0, "stencil: nz must be divisible by the number of ranks (plane-aligned slabs)");
 	auto * A = new fsb_parcsr_s;
 	A->ctx = c;
 	A->id = c->next_mat_id++;
 	A->n_global = plane * nz;
+	// equal contiguous row blocks, the first N % P one row longer: flecsi::util::equal_map as the reference partitions
+	// rows and columns (matrices/parcsr.hh:170-172); z-slabs of whole planes whenever nz % P == 0
 	A->row_part.resize(P + 1);
-	for (int q = 0; q <= P; ++q)
-		A->row_part[q] = plane * (nz / P) * q;
+	{
+		const int64_t base = A->n_global / P, rem = A->n_global % P;
+		for (int q = 0; q <= P; ++q)
+			A->row_part[q] = base * q + std::min<int64_t>(q, rem);
+	}
+	const int64_t reach = kind == 27 ? plane + nx + 1 : (kind == 7 ? plane : nx);
+	FSB_REQUIRE(P == 1 || A->n_global / P >= reach,
+	            "stencil: row blocks thinner than the stencil's reach (ghosts beyond the adjacent ranks): assemble on the host and use fsb_parcsr_create");
 	A->row_begin = A->row_part[me];
 	const int64_t row_end = A->row_part[me + 1];
 	A->n_local = row_end - A->row_begin;
-	FSB_REQUIRE(A->n_local + 2 * plane < (1LL << 31), "stencil: local column space exceeds int32");
+	FSB_REQUIRE(A->n_local + 2 * reach < (1LL << 31), "stencil: local column space exceeds int32");
 
 	grid_desc G{};
 	G.nx = nx;
@@ -525,17 +573,39 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 	G.nz = nz;
 	G.row_begin = A->row_begin;
 	G.row_end = row_end;
-	G.lower = (P > 1 && me > 0) ? plane : 0;
-	G.upper = (P > 1 && me < P - 1) ? plane : 0;
+	G.reach = reach;
+	G.lo_base = std::max<int64_t>(0, A->row_begin - reach);
 	G.kind = kind;
+	G.neumann = neumann ? 1 : 0;
 	const double center = kind == 27 ? 26.0 : (kind == 7 ? 6.0 : 4.0);
 	G.diag = (center + diag_shift) * scale;
 	G.off = -1.0 * scale;
-	A->n_ghost = G.lower + G.upper;
 
 	const long long n = A->n_local;
 	const int T = 256;
 	const int grid = static_cast<int>((n + T - 1) / T);
+	// ghost discovery (topo/csr.hh:506-526): the referenced columns outside the block, sorted = flagged candidates
+	int *flag_lo = nullptr, *flag_hi = nullptr, *rank_lo = nullptr, *rank_hi = nullptr;
+	if (P > 1) {
+		flag_lo = dev_alloc<int>(reach + 1);
+		flag_hi = dev_alloc<int>(reach + 1);
+		rank_lo = dev_alloc<int>(reach + 1);
+		rank_hi = dev_alloc<int>(reach + 1);
+		FSB_CUDA(cudaMemsetAsync(flag_lo, 0, (reach + 1) * sizeof(int), c->stream));
+		FSB_CUDA(cudaMemsetAsync(flag_hi, 0, (reach + 1) * sizeof(int), c->stream));
+		stencil_mark_kernel<<<static_cast<int>((2 * reach + T - 1) / T), T, 0, c->stream>>>(G, flag_lo, flag_hi);
+		FSB_CUDA(cudaGetLastError());
+		exclusive_scan(c, flag_lo, rank_lo, reach + 1);
+		exclusive_scan(c, flag_hi, rank_hi, reach + 1);
+		int counts[2] = {0, 0};
+		FSB_CUDA(cudaMemcpy(&counts[0], rank_lo + reach, sizeof(int), cudaMemcpyDeviceToHost));
+		FSB_CUDA(cudaMemcpy(&counts[1], rank_hi + reach, sizeof(int), cudaMemcpyDeviceToHost));
+		G.lower = counts[0];
+		G.upper = counts[1];
+		G.rank_lo = rank_lo;
+		G.rank_hi = rank_hi;
+	}
+	A->n_ghost = G.lower + G.upper;
 	int * cnt_d = dev_alloc<int>(n + 1);
 	int * cnt_o = dev_alloc<int>(n + 1);
 	FSB_CUDA(cudaMemsetAsync(cnt_d + n, 0, sizeof(int), c->stream));
@@ -615,45 +685,32 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 		if (n_rows > 0) {
 			stencil_fill_offd_kernel<<<(n_rows + T - 1) / T, T, 0, c->stream>>>(G, rows, n_rows, rp, O.col, O.val);
 			FSB_CUDA(cudaGetLastError());
+			// a row reaches at most 9 (27-point) / 1 (7- and 5-point) columns on either side; both sides only when the
+			// block is thinner than twice the reach
 			const int per_side = kind == 27 ? 9 : 1;
-			O.max_blk_nnz = (A->n_local == plane && G.lower && G.upper) ? 2 * per_side : per_side;
+			O.max_blk_nnz = (A->n_local < 2 * reach && G.lower && G.upper) ? 2 * per_side : per_side;
 			build_blocks(c, O, nullptr);
 		}
-		// colmap + analytic halo plan: whole boundary planes, contiguous on both sides
+		// colmap[ghost] = global id, ascending (topo/csr.hh:524-526)
 		A->d_colmap = dev_alloc<int64_t>(A->n_ghost);
-		colmap_kernel<<<static_cast<int>((A->n_ghost + T - 1) / T), T, 0, c->stream>>>(
-			G, reinterpret_cast<long long *>(A->d_colmap));
+		colmap_kernel<<<static_cast<int>((2 * reach + T - 1) / T), T, 0, c->stream>>>(G, flag_lo, flag_hi,
+		                                                                             reinterpret_cast<long long *>(A->d_colmap));
+		FSB_CUDA(cudaGetLastError());
 		A->colmap.resize(A->n_ghost);
 		FSB_CUDA(cudaMemcpyAsync(A->colmap.data(), A->d_colmap, A->n_ghost * sizeof(int64_t), cudaMemcpyDeviceToHost,
 		                         c->stream));
-		if (G.lower) {
-			neighbour nb{};
-			nb.rank = me - 1;
-			nb.send_count = nb.recv_count = plane;
-			nb.recv_offset = 0;
-			nb.contiguous_start = 0;
-			A->nbrs.push_back(nb);
-		}
-		if (G.upper) {
-			neighbour nb{};
-			nb.rank = me + 1;
-			nb.send_count = nb.recv_count = plane;
-			nb.recv_offset = G.lower;
-			nb.contiguous_start = A->n_local - plane;
-			A->nbrs.push_back(nb);
-		}
-	}
-	if (P > 1) { // collective: every rank takes part even if it had no ghosts
-		attach_offd_rows(c, A->diag, A->offd);
-		std::vector<int64_t> dest_off;
-		for (const neighbour & nb : A->nbrs)
-			dest_off.push_back(nb.rank < me ? (nb.rank > 0 ? plane : 0) : 0); // my plane lands after its lower ghosts
-		FSB_CUDA(cudaStreamSynchronize(c->stream));
-		halo_p2p_setup(A, dest_off);
 	}
 	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(flag_lo);
+	cudaFree(flag_hi);
+	cudaFree(rank_lo);
+	cudaFree(rank_hi);
 	cudaFree(cnt_d);
 	cudaFree(cnt_o);
+	if (P > 1) { // collective: every rank takes part even if it had no ghosts
+		attach_offd_rows(c, A->diag, A->offd);
+		build_halo_plan(A); // the copy plan (topo/csr.hh:116-187): who sends which of its entries where; whole planes for z-slabs
+	}
 	return A;
 }
 

@@ -59,9 +59,9 @@ enum fsb_option {
 	                            communication kernels (default when halo and reductions go through NCCL;
 	                            results then vary in the last bits) */
 	,
-	FSB_OPT_JIT = 6 /* 1: a statement group without an ahead-of-time kernel gets one compiled at run time
-	                   (NVRTC, cached per process) instead of the generic program kernel; 0 (default in this
-	                   version; FSB_JIT=1 in the environment turns it on) */
+	FSB_OPT_JIT = 6 /* 1 (default): a statement group without an ahead-of-time kernel gets one compiled at run time
+	                   (NVRTC, ~0.3 s once per group and process) instead of the generic program kernel, which remains
+	                   the fallback when libnvrtc is not available; 0 (or FSB_JIT=0 in the environment): never compile */
 	,
 	FSB_OPT_TIMELINE = 7 /* n > 0: keep a device-side timeline of the next n kernel launches (fsb_ctx_timeline_read); 0: off */
 };
@@ -289,9 +289,11 @@ int fsb_parcsr_create(fsb_ctx_t ctx,
                       const double * val,
                       fsb_parcsr_t * out);
 /* synthetic stencil operators generated on the device:
- * kind 7: diag 6 / off -1;  kind 27: diag 26 / off -1;  kind 5: 2-D (nz==1) diag 4 / off -1.
- * Dirichlet truncation, columns ascending, rows g = i + nx*(j + ny*k) split into
- * equal contiguous blocks (z-slabs; requires nz % nranks == 0 when nranks > 1).
+ * kind 7: diag 6 / off -1;  kind 27: diag 26 / off -1;  kind 5: 2-D (nz==1) diag 4 / off -1;
+ * kind 107: 7-point with Neumann closure (diagonal = number of neighbours inside the box; config 4's second component).
+ * Dirichlet truncation, columns ascending, rows g = i + nx*(j + ny*k) split into equal contiguous blocks like the
+ * reference's equal_map (the first n % nranks blocks one row longer; z-slabs of whole planes when nz % nranks == 0).
+ * A block must be at least as long as the stencil reaches (one plane; plane + nx + 1 for kind 27).
  * diag_shift is added to the diagonal, scale multiplies every entry.        */
 int fsb_parcsr_create_stencil(fsb_ctx_t ctx, int kind, int64_t nx, int64_t ny, int64_t nz,
                               double diag_shift, double scale, fsb_parcsr_t * out);

@@ -604,10 +604,17 @@ void jacobi_relax(ParCsr & M, double omega, idx nrelax, const double * b, double
 }
 
 // synthetic operators of SURVEY.md section 8d: rows g = i + nx*(j + ny*k), Dirichlet truncation,
-// columns ascending.  kind 5 / 7 / 27.
+// columns ascending.  kind 5 / 7 / 27; kind 107 = 7-point with Neumann closure (SURVEY 8d, config 4's second
+// component): the diagonal of a row is (number of neighbours inside the box + diag_shift) * scale, passed here as
+// dv = (6 + diag_shift) * scale and corrected by the missing neighbours.
 template<class F>
 void visit_stencil(int kind, int64_t nx, int64_t ny, int64_t nz, int64_t g, double dv, double ov, F && f) {
 	const int64_t i = g % nx, j = (g / nx) % ny, k = g / (nx * ny);
+	if (kind == 107) {
+		const int missing = (i == 0) + (i == nx - 1) + (j == 0) + (j == ny - 1) + (k == 0) + (k == nz - 1);
+		dv = dv + missing * ov; // ov = -scale: (6 + shift) scale - missing scale
+		kind = 7;
+	}
 	if (kind == 27) {
 		for (int dk = -1; dk <= 1; ++dk)
 			for (int dj = -1; dj <= 1; ++dj)
@@ -676,7 +683,7 @@ void orc_set_threads(int n) {
 int64_t orc_stencil_nnz(int kind, int64_t nx, int64_t ny, int64_t nz) {
 	if (kind == 27)
 		return (3 * nx - 2) * (3 * ny - 2) * (3 * nz - 2);
-	if (kind == 7)
+	if (kind == 7 || kind == 107)
 		return 7 * nx * ny * nz - 2 * (nx * ny + ny * nz + nx * nz);
 	return 5 * nx * ny - 2 * (nx + ny);
 }
@@ -684,7 +691,7 @@ int64_t orc_stencil_nnz(int kind, int64_t nx, int64_t ny, int64_t nz) {
 void orc_stencil_fill(int kind, int64_t nx, int64_t ny, int64_t nz, double diag_shift, double scale, int64_t * rowptr,
                       int64_t * col, double * val) {
 	const int64_t n = nx * ny * nz;
-	const double center = kind == 27 ? 26.0 : (kind == 7 ? 6.0 : 4.0);
+	const double center = kind == 27 ? 26.0 : ((kind == 7 || kind == 107) ? 6.0 : 4.0);
 	const double dv = (center + diag_shift) * scale, ov = -1.0 * scale;
 	rowptr[0] = 0;
 	for (int64_t g = 0; g < n; ++g) {

@@ -72,6 +72,26 @@ def main():
     S.close()
     A.destroy()
 
+    # ---- device generator: row blocks that are not whole planes (equal_map gives the first N % P ranks one more row),
+    # 27-point ghosts that are not a contiguous range, Neumann closure
+    for gkind, gdims in ((7, (12, 11, 5 * P + 1)), (27, (9, 8, 4 * P + 1)), (107, (7, 9, 3 * P + 2)), (5, (13, 7 * P + 3, 1))):
+        grp, gcol, gval = O.stencil_csr(gkind, *gdims)
+        gn = len(grp) - 1
+        GM = O.ParCSR(grp, gcol, gval, colours=P)
+        GA = F.ParCSR.stencil(ctx, gkind, *gdims)
+        glo, ghi = GA.row_begin, GA.row_begin + GA.local_rows
+        assert [glo, ghi] == list(GM.partition()[me:me + 2]), (gkind, glo, ghi)
+        for which in (0, 1):
+            orp, ocol, oval, ocm = GM.block(me, which)
+            drp, dcol, dval = GA.download(which)
+            assert np.array_equal(drp, orp) and np.array_equal(dcol, ocol) and np.array_equal(dval, oval), ("gen", gkind, which)
+        assert np.array_equal(GA.colmap(), GM.block(me, 1)[3]), ("colmap", gkind)
+        gx = rng.standard_normal(gn)
+        gxv, gyv = GA.vector(gx[glo:ghi]), GA.vector()
+        GA.spmv(gxv, gyv)
+        assert np.array_equal(gyv.download(), GM.spmv(gx)[glo:ghi]), ("gen spmv", gkind)
+        gxv.destroy(); gyv.destroy(); GA.destroy()
+
     # ---- device generator path: plane-aligned z-slabs
     nn = 16
     rp, col, val = O.stencil_csr(7, nn, nn, nn * P if P > 1 else nn)
