@@ -97,6 +97,7 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_device_count", C.c_int)
     f("fsb_nccl_unique_id", C.c_int, _p)
     f("fsb_ctx_create", C.c_int, C.c_int, C.c_int, C.c_int, _p, C.POINTER(_p))
+    f("fsb_ctx_create_group", C.c_int, C.c_int, C.c_int, C.POINTER(_p))
     f("fsb_ctx_destroy", C.c_int, _p)
     f("fsb_ctx_flush", C.c_int, _p)
     f("fsb_ctx_sync", C.c_int, _p)
@@ -195,6 +196,19 @@ class Context:
         check(lib().fsb_ctx_create(device, rank, nranks, buf, C.byref(h)))
         self.h = h
         self.rank, self.nranks = rank, nranks
+
+    @classmethod
+    def group(cls, device: int, nranks: int) -> list["Context"]:
+        """nranks contexts = the ranks of one group as threads of this process on one device (fsb_ctx_create_group);
+        each must then be driven by its own host thread"""
+        handles = (_p * nranks)()
+        check(lib().fsb_ctx_create_group(device, nranks, handles))
+        out = []
+        for r in range(nranks):
+            c = cls.__new__(cls)
+            c.h, c.rank, c.nranks = _p(handles[r]), r, nranks
+            out.append(c)
+        return out
 
     @staticmethod
     def unique_id() -> bytes:

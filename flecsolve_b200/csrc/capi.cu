@@ -1,14 +1,17 @@
 // extern "C" surface of libfsb.so: contexts, vectors, reductions, matrix wrappers.
 #include <immintrin.h>
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
 #include <random>
+#include <thread>
 
 #include "ew_kernels.cuh"
 #include "fsb_internal.h"
+#include "setup_exchange.h"
 
 using namespace fsb;
 
@@ -24,9 +27,13 @@ namespace fsb {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string & m) { g_last_error = m; }
 
+// Off for the whole process once an in-process rank group exists: there the peers' kernels share the device, and a
+// dependent kernel scheduled early sits on SM resources while the kernel it depends on waits for a peer that may need them
+// (observed as a time-out of the cross-rank reduction on B200; separate processes on separate GPUs are not affected).
+static std::atomic<bool> g_pdl_off{false};
 bool pdl_enabled() {
 	static const bool on = !(std::getenv("FSB_PDL") && std::atoi(std::getenv("FSB_PDL")) == 0);
-	return on;
+	return on && !g_pdl_off.load(std::memory_order_relaxed);
 }
 
 // the host only hands out slots (and stamps the kind); the kernels write the times
@@ -70,8 +77,9 @@ static int guarded(F && body) noexcept {
 	}
 }
 
-// Map every rank's reduction mailbox into this process (cudaIpc) so the kernels can all-reduce
-// scalars with plain stores/loads over NVLink.  Any failure leaves d_xrank null => NCCL path.
+// Make every rank's reduction mailbox addressable by this rank's kernels (cudaIpc across processes, plain pointers among
+// the threads of a rank group) so the kernels can all-reduce scalars with plain stores/loads over NVLink.  Any failure
+// leaves d_xrank null => NCCL path.
 static void setup_peer_reductions(fsb_ctx_s * c) {
 	static_assert(XRANK_RING == FSB_RED_RING, "mailbox ring must match the token ring");
 	const int P = c->nranks;
@@ -80,60 +88,92 @@ static void setup_peer_reductions(fsb_ctx_s * c) {
 	const size_t bytes = sizeof(double) * 2 * XRANK_RING * P;
 	FSB_CUDA(cudaMalloc(&c->d_mailbox, bytes));
 	FSB_CUDA(cudaMemset(c->d_mailbox, 0, bytes));
-	cudaIpcMemHandle_t mine;
-	bool ok = cudaIpcGetMemHandle(&mine, c->d_mailbox) == cudaSuccess;
-	// all-gather the handles (and whether every rank got one) with NCCL
-	struct packet {
-		cudaIpcMemHandle_t h;
-		long long ok;
-	};
-	std::vector<packet> all(P);
-	packet * d_all = nullptr;
-	FSB_CUDA(cudaMalloc(&d_all, sizeof(packet) * P));
-	packet me{mine, ok ? 1 : 0};
-	FSB_CUDA(cudaMemcpy(d_all + c->rank, &me, sizeof(packet), cudaMemcpyHostToDevice));
-	FSB_NCCL(ncclAllGather(d_all + c->rank, d_all, sizeof(packet), ncclChar, c->nccl, c->stream));
-	FSB_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(packet) * P, cudaMemcpyDeviceToHost, c->stream));
-	FSB_CUDA(cudaStreamSynchronize(c->stream));
-	cudaFree(d_all);
-	for (int q = 0; q < P; ++q)
-		ok = ok && all[q].ok;
-	xrank_info info{};
-	info.me = c->rank;
-	info.nranks = P;
-	for (int q = 0; q < P && ok; ++q) {
-		if (q == c->rank) {
-			info.mailbox[q] = c->d_mailbox;
-			continue;
-		}
-		void * p = nullptr;
-		if (cudaIpcOpenMemHandle(&p, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-			cudaGetLastError();
-			ok = false;
-			break;
-		}
-		c->peer_mailbox[q] = p;
-		info.mailbox[q] = static_cast<double *>(p);
-	}
-	// every rank must agree, otherwise some would wait on mailboxes nobody writes
-	long long * d_ok = nullptr;
-	FSB_CUDA(cudaMalloc(&d_ok, sizeof(long long)));
-	long long v = ok ? 1 : 0;
-	FSB_CUDA(cudaMemcpy(d_ok, &v, sizeof(v), cudaMemcpyHostToDevice));
-	FSB_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt64, ncclMin, c->nccl, c->stream));
-	FSB_CUDA(cudaMemcpyAsync(&v, d_ok, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
-	FSB_CUDA(cudaStreamSynchronize(c->stream));
-	cudaFree(d_ok);
-	if (!v) {
+	void * peers[XRANK_MAX] = {};
+	if (!c->boot->share(c->d_mailbox, peers)) {
 		if (c->rank == 0)
 			fprintf(stderr, "[fsb] peer-memory reductions unavailable (cudaIpc failed); using ncclAllReduce\n");
 		return;
+	}
+	xrank_info info{};
+	info.me = c->rank;
+	info.nranks = P;
+	for (int q = 0; q < P; ++q) {
+		info.mailbox[q] = static_cast<double *>(peers[q]);
+		if (q != c->rank)
+			c->peer_mailbox[q] = peers[q];
 	}
 	FSB_CUDA(cudaHostAlloc(&c->h_xrank_error, sizeof(int), cudaHostAllocMapped));
 	*c->h_xrank_error = 0;
 	FSB_CUDA(cudaHostGetDevicePointer(&info.error_flag, c->h_xrank_error, 0));
 	FSB_CUDA(cudaMalloc(&c->d_xrank, sizeof(xrank_info)));
 	FSB_CUDA(cudaMemcpy(c->d_xrank, &info, sizeof(info), cudaMemcpyHostToDevice));
+}
+
+// everything of a context that does not depend on how its ranks talk to each other
+static fsb_ctx_s * new_context(int device, int rank, int nranks) {
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		throw fsb::error(FSB_ERR_NOGPU, "no CUDA device available: this library has no CPU fallback");
+	}
+	FSB_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+	FSB_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop{};
+	FSB_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10)
+		throw fsb::error(FSB_ERR_NOGPU, std::string("device is sm_") + std::to_string(prop.major) +
+		                                    std::to_string(prop.minor) + "; kernels are built for sm_100a only");
+	auto * c = new fsb_ctx_s;
+	c->device = device;
+	c->rank = rank;
+	c->nranks = nranks;
+	FSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	FSB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+	FSB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+	FSB_CUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+	FSB_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * MAXR * MAX_RED_BLOCKS));
+	FSB_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned)));
+	FSB_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned)));
+	FSB_CUDA(cudaMalloc(&c->d_sched, 2 * sizeof(unsigned)));
+	FSB_CUDA(cudaMemset(c->d_sched, 0, 2 * sizeof(unsigned)));
+	FSB_CUDA(cudaMalloc(&c->d_results, sizeof(double) * FSB_RED_RING));
+	FSB_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * fsb::MAX_SCALARS));
+	{
+		std::vector<double> init(fsb::MAX_SCALARS, 0.0);
+		init[0] = 1.0;
+		FSB_CUDA(cudaMemcpy(c->d_scalars, init.data(), sizeof(double) * fsb::MAX_SCALARS, cudaMemcpyHostToDevice));
+		c->scalar_used[0] = true;
+	}
+	FSB_CUDA(cudaMalloc(&c->d_halt, sizeof(int)));
+	FSB_CUDA(cudaMemset(c->d_halt, 0, sizeof(int)));
+	FSB_CUDA(cudaHostAlloc(&c->h_results, sizeof(double) * FSB_RED_RING, cudaHostAllocDefault));
+	FSB_CUDA(cudaHostAlloc(&c->h_ll, sizeof(fsb::ll_word) * FSB_RED_RING, cudaHostAllocMapped));
+	std::memset(c->h_results, 0, sizeof(double) * FSB_RED_RING);
+	std::memset(c->h_ll, 0, sizeof(fsb::ll_word) * FSB_RED_RING);
+	FSB_CUDA(cudaHostGetDevicePointer(&c->h_ll_dev, c->h_ll, 0));
+	c->token_op.assign(FSB_RED_RING, 0);
+	c->token_event.resize(FSB_RED_RING, nullptr);
+	return c;
+}
+
+// the part that follows once the ranks can talk (c->boot is set when nranks > 1)
+static void finish_context(fsb_ctx_s * c) {
+	const int nranks = c->nranks;
+	if (nranks > 1 && (c->boot->in_process() || !(std::getenv("FSB_P2P_REDUCE") && std::atoi(std::getenv("FSB_P2P_REDUCE")) == 0)))
+		setup_peer_reductions(c);
+	FSB_REQUIRE(nranks == 1 || c->nccl || c->d_xrank, "a rank group in one process needs peer-memory reductions");
+	// Static row-block schedule (bitwise reproducible, and measured faster: profiles/r1_scaling_final.txt)
+	// unless NCCL kernels share the SMs with the SpMV: a CTA that starts late behind a communication
+	// kernel would otherwise stretch the one-wave grid into two.
+	c->reproducible = nranks == 1 || c->d_xrank != nullptr;
+	if (const char * e = std::getenv("FSB_REPRODUCIBLE")) // measurement override
+		c->reproducible = std::atoi(e) != 0;
+	if (const char * t = std::getenv("FSB_JIT"))
+		c->jit = std::atoi(t) != 0;
+	if (const char * t = std::getenv("FSB_TRACE"))
+		c->trace = std::atoi(t) != 0;
+	if (const char * t = std::getenv("FSB_FUSION"))
+		c->fusion = std::atoi(t) != 0;
 }
 
 extern "C" {
@@ -165,48 +205,7 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 		FSB_REQUIRE(out, "null output");
 		FSB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
 		FSB_REQUIRE(nranks == 1 || uid, "nccl_unique_id required when nranks > 1");
-		int ndev = 0;
-		if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-			cudaGetLastError();
-			throw fsb::error(FSB_ERR_NOGPU, "no CUDA device available: this library has no CPU fallback");
-		}
-		FSB_REQUIRE(device >= 0 && device < ndev, "device index out of range");
-		FSB_CUDA(cudaSetDevice(device));
-		cudaDeviceProp prop{};
-		FSB_CUDA(cudaGetDeviceProperties(&prop, device));
-		if (prop.major != 10)
-			throw fsb::error(FSB_ERR_NOGPU, std::string("device is sm_") + std::to_string(prop.major) +
-			                                    std::to_string(prop.minor) + "; kernels are built for sm_100a only");
-		auto * c = new fsb_ctx_s;
-		c->device = device;
-		c->rank = rank;
-		c->nranks = nranks;
-		FSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-		FSB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
-		FSB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
-		FSB_CUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
-		FSB_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * MAXR * MAX_RED_BLOCKS));
-		FSB_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned)));
-		FSB_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned)));
-		FSB_CUDA(cudaMalloc(&c->d_sched, 2 * sizeof(unsigned)));
-		FSB_CUDA(cudaMemset(c->d_sched, 0, 2 * sizeof(unsigned)));
-		FSB_CUDA(cudaMalloc(&c->d_results, sizeof(double) * FSB_RED_RING));
-		FSB_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * fsb::MAX_SCALARS));
-		{
-			std::vector<double> init(fsb::MAX_SCALARS, 0.0);
-			init[0] = 1.0;
-			FSB_CUDA(cudaMemcpy(c->d_scalars, init.data(), sizeof(double) * fsb::MAX_SCALARS, cudaMemcpyHostToDevice));
-			c->scalar_used[0] = true;
-		}
-		FSB_CUDA(cudaMalloc(&c->d_halt, sizeof(int)));
-		FSB_CUDA(cudaMemset(c->d_halt, 0, sizeof(int)));
-		FSB_CUDA(cudaHostAlloc(&c->h_results, sizeof(double) * FSB_RED_RING, cudaHostAllocDefault));
-		FSB_CUDA(cudaHostAlloc(&c->h_ll, sizeof(fsb::ll_word) * FSB_RED_RING, cudaHostAllocMapped));
-		std::memset(c->h_results, 0, sizeof(double) * FSB_RED_RING);
-		std::memset(c->h_ll, 0, sizeof(fsb::ll_word) * FSB_RED_RING);
-		FSB_CUDA(cudaHostGetDevicePointer(&c->h_ll_dev, c->h_ll, 0));
-		c->token_op.assign(FSB_RED_RING, 0);
-		c->token_event.resize(FSB_RED_RING, nullptr);
+		fsb_ctx_s * c = new_context(device, rank, nranks);
 		if (nranks > 1) {
 			ncclUniqueId id;
 			std::memcpy(&id, uid, sizeof(id));
@@ -214,22 +213,46 @@ int fsb_ctx_create(int device, int rank, int nranks, const void * uid, fsb_ctx_t
 			FSB_NCCL(ncclCommSplit(c->nccl, 0, rank, &c->nccl_halo_comm, nullptr));
 			for (auto & e : c->token_event)
 				FSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			c->boot = std::make_shared<fsb::nccl_exchange>(c);
 		}
-		if (nranks > 1 && !(std::getenv("FSB_P2P_REDUCE") && std::atoi(std::getenv("FSB_P2P_REDUCE")) == 0))
-			setup_peer_reductions(c);
-		// Static row-block schedule (bitwise reproducible, and measured faster: profiles/r1_scaling_final.txt)
-		// unless NCCL kernels share the SMs with the SpMV: a CTA that starts late behind a communication
-		// kernel would otherwise stretch the one-wave grid into two.
-		c->reproducible = nranks == 1 || c->d_xrank != nullptr;
-		if (const char * e = std::getenv("FSB_REPRODUCIBLE")) // measurement override
-			c->reproducible = std::atoi(e) != 0;
-		if (const char * t = std::getenv("FSB_JIT"))
-			c->jit = std::atoi(t) != 0;
-		if (const char * t = std::getenv("FSB_TRACE"))
-			c->trace = std::atoi(t) != 0;
-		if (const char * t = std::getenv("FSB_FUSION"))
-			c->fusion = std::atoi(t) != 0;
+		finish_context(c);
 		*out = c;
+	});
+}
+
+int fsb_ctx_create_group(int device, int nranks, fsb_ctx_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(out && nranks >= 1 && nranks <= XRANK_MAX, "bad arguments");
+		auto group = std::make_shared<fsb::local_group>(nranks);
+		if (nranks > 1)
+			fsb::g_pdl_off.store(true);
+		std::vector<fsb_ctx_s *> made;
+		for (int r = 0; r < nranks; ++r) {
+			fsb_ctx_s * c = new_context(device, r, nranks);
+			if (nranks > 1)
+				c->boot = std::make_shared<fsb::local_exchange>(group, r);
+			made.push_back(c);
+		}
+		// the collective part of the setup, one thread per rank as every later collective call needs it
+		std::vector<std::thread> threads;
+		std::vector<std::string> errors(static_cast<size_t>(nranks));
+		for (int r = 0; r < nranks; ++r)
+			threads.emplace_back([&, r] {
+				try {
+					cudaSetDevice(device);
+					finish_context(made[static_cast<size_t>(r)]);
+				}
+				catch (const std::exception & e) {
+					errors[static_cast<size_t>(r)] = e.what();
+				}
+			});
+		for (auto & t : threads)
+			t.join();
+		for (const std::string & e : errors)
+			if (!e.empty())
+				throw fsb::error(FSB_ERR_STATE, e);
+		for (int r = 0; r < nranks; ++r)
+			out[r] = made[static_cast<size_t>(r)];
 	});
 }
 
@@ -241,8 +264,8 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 		cudaStreamSynchronize(c->stream);
 		cudaStreamSynchronize(c->comm_stream);
 		for (void * p : c->peer_mailbox)
-			if (p)
-				cudaIpcCloseMemHandle(p);
+			if (p && c->boot)
+				c->boot->unshare(p);
 		cudaFree(c->d_mailbox);
 		cudaFree(c->d_xrank);
 		if (c->h_xrank_error)
@@ -267,6 +290,8 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 		cudaFree(c->d_halt);
 		cudaFree(c->d_flush);
 		cudaFree(c->d_timeline);
+		for (void * p : c->deferred_free)
+			cudaFree(p);
 		cudaFreeHost(c->h_results);
 		cudaFreeHost(c->h_ll);
 		cudaEventDestroy(c->ev_main);
@@ -519,7 +544,12 @@ int fsb_vec_destroy(fsb_vec_t v) {
 		if (v->owns) {
 			FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
 			FSB_CUDA(cudaStreamSynchronize(v->ctx->comm_stream));
-			cudaFree(v->d);
+			// cudaFree waits for the whole device: among the ranks of an in-process group that would wait for a peer's
+			// kernel which may itself be waiting for this rank's next launch -- the memory goes with the context instead
+			if (v->ctx->boot && v->ctx->boot->in_process())
+				v->ctx->deferred_free.push_back(v->d);
+			else
+				cudaFree(v->d);
 		}
 		delete v;
 	});
@@ -905,14 +935,9 @@ int fsb_vec_global_size(fsb_vec_t x, int64_t * out) {
 			return;
 		}
 		flush(c);
-		long long * d = nullptr;
-		FSB_CUDA(cudaMalloc(&d, sizeof(long long)));
-		long long v = x->n_owned;
-		FSB_CUDA(cudaMemcpyAsync(d, &v, sizeof(v), cudaMemcpyHostToDevice, c->stream));
-		FSB_NCCL(ncclAllReduce(d, d, 1, ncclInt64, ncclSum, c->nccl, c->stream));
-		FSB_CUDA(cudaMemcpyAsync(&v, d, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
-		FSB_CUDA(cudaStreamSynchronize(c->stream));
-		cudaFree(d);
+		long long v = 0;
+		for (long long n : c->boot->gather<long long>(x->n_owned, c->nranks))
+			v += n;
 		*out = v;
 	});
 }
@@ -944,8 +969,17 @@ static void wait_token(fsb_ctx_t c, fsb_token_t tok) {
 			}
 		}
 		c->h_results[slot] = v;
-		if (c->h_xrank_error && *(volatile int *)c->h_xrank_error)
-			throw fsb::error(FSB_ERR_STATE, "cross-rank reduction timed out waiting for a peer");
+		if (c->h_xrank_error && *(volatile int *)c->h_xrank_error) {
+			static const char * what[] = {"", "a reduction's all-reduce", "the acknowledgement of a ghost landing buffer",
+			                              "ghost entries"};
+			const int word = *(volatile int *)c->h_xrank_error, code = word & 15;
+			std::string detail;
+			if (code == 1) // which reduction, whose value (ew_kernels.cuh: xrank_allreduce)
+				detail = " (reduction " + std::to_string(word >> 8) + ", rank " + std::to_string((word >> 4) & 15) + "'s value; this rank has issued " +
+				         std::to_string(c->next_token - 1) + ")";
+			throw fsb::error(FSB_ERR_STATE, std::string("rank ") + std::to_string(c->rank) + ": a kernel timed out waiting for " +
+			                                    what[code >= 1 && code <= 3 ? code : 0] + " from a peer" + detail);
+		}
 	}
 	c->stats[FSB_STAT_HOST_SYNCS]++;
 	c->stats[FSB_STAT_WAIT_NS] +=

@@ -203,7 +203,7 @@ __device__ __forceinline__ double xrank_allreduce(const xrank_info * xr, double 
 		ll_store(xr->mailbox[q] + (slot * P + me) * 2, local, flag);
 		double v;
 		if (!ll_load(xr->mailbox[me] + (slot * P + q) * 2, flag, v))
-			*reinterpret_cast<volatile int *>(xr->error_flag) = 1;
+			*reinterpret_cast<volatile int *>(xr->error_flag) = 1 + 16 * q + 256 * static_cast<int>(token & 0x3fffff);
 		scratch[q] = v;
 	}
 	__syncthreads();
@@ -416,7 +416,7 @@ __device__ __forceinline__ void ew_program_body(const ew_args & a) {
 					ll_store(a.xr->mailbox[q] + (slot * np + me) * 2, local[R], static_cast<unsigned>(token));
 					double v;
 					if (!ll_load(a.xr->mailbox[me] + (slot * np + q) * 2, static_cast<unsigned>(token), v))
-						*reinterpret_cast<volatile int *>(a.xr->error_flag) = 1;
+						*reinterpret_cast<volatile int *>(a.xr->error_flag) = 1 + 16 * q + 256 * static_cast<int>(token & 0x3fffff);
 					gathered[R][q] = v;
 				}
 				__syncthreads();

@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -16,6 +17,7 @@
 namespace fsb {
 struct xrank_info;
 struct red_out;
+struct setup_exchange;
 constexpr int MAX_SCALARS = 64; // device scalars per context; slot 0 is the constant 1.0
 }
 
@@ -116,7 +118,8 @@ struct fsb_ctx_s {
 	cudaStream_t stream = nullptr;
 	cudaStream_t comm_stream = nullptr;
 	cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
-	ncclComm_t nccl = nullptr; // reductions + setup, used on `stream`
+	std::shared_ptr<fsb::setup_exchange> boot; // host-side exchange among the ranks during setup (setup_exchange.h)
+	ncclComm_t nccl = nullptr; // reductions + setup, used on `stream`; null when the ranks are threads of one process
 	ncclComm_t nccl_halo_comm = nullptr; // ghost exchange, used on `comm_stream`
 	ncclComm_t nccl_halo() const { return nccl_halo_comm; }
 
@@ -169,6 +172,7 @@ struct fsb_ctx_s {
 	int64_t stats[16] = {};
 	uint64_t next_vec_id = 1;
 	uint64_t next_mat_id = 1;
+	std::vector<void *> deferred_free; // in-process rank groups: vector storage released with the context
 };
 
 struct fsb_vec_s {
@@ -269,6 +273,14 @@ void launch_dependent(Kernel kern, dim3 grid, dim3 block, size_t smem, cudaStrea
 	cfg.attrs = attr;
 	cfg.numAttrs = pdl_enabled() ? 1 : 0;
 	FSB_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+}
+
+// CUDA loads a kernel at its first use, and the load waits for everything running in the context.  The ranks of an
+// in-process group call this before they meet for a launch whose kernels wait for each other (setup_exchange::rendezvous).
+template<class Kernel>
+void preload_kernel(Kernel kern) {
+	cudaFuncAttributes fa;
+	FSB_CUDA(cudaFuncGetAttributes(&fa, kern));
 }
 
 // queue / fuser (fuser.cu)

@@ -8,12 +8,14 @@
 // value; only reductions see a different (fixed, reproducible) summation order.
 #include <chrono>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <string>
 #include <unordered_map>
 
 #include "ew_kernels.cuh"
 #include "fsb_internal.h"
+#include "setup_exchange.h"
 
 namespace fsb {
 
@@ -21,31 +23,34 @@ namespace fsb {
 
 using launcher_t = void (*)(const ew_args &, int want_ctas, cudaStream_t);
 
-// grid: enough CTAs for the data, at most one resident wave (occupancy API, cached per program)
+// grid: enough CTAs for the data, at most one resident wave (occupancy API, cached per program).
+// want_ctas < 0: no launch, only make sure the kernel is loaded (CUDA loads a kernel at its first use, and that load
+// waits for everything running in the context: the ranks of an in-process group do it BEFORE they meet for a launch
+// whose kernels wait for each other, see setup_exchange::rendezvous)
+template<class Kernel>
+static void launch_one_wave(Kernel kern, std::atomic<int> & resident, const ew_args & a, int want, cudaStream_t s) {
+	if (resident.load(std::memory_order_acquire) == 0) {
+		int nb = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, EW_BLOCK, 0) != cudaSuccess || nb < 1)
+			nb = 4;
+		resident.store(nb * SM_COUNT, std::memory_order_release);
+	}
+	if (want < 0)
+		return;
+	const int most = resident.load(std::memory_order_relaxed);
+	launch_dependent(kern, dim3(want < most ? want : most), dim3(EW_BLOCK), 0, s, a);
+}
+
 template<class PT>
 static void launch_program(const ew_args & a, int want, cudaStream_t s) {
-	static int resident = 0;
-	if (resident == 0) {
-		int nb = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ew_program_kernel<PT>, EW_BLOCK, 0) != cudaSuccess || nb < 1)
-			nb = 4;
-		resident = nb * SM_COUNT;
-	}
-	const int grid = want < resident ? want : resident;
-	launch_dependent(ew_program_kernel<PT>, dim3(grid), dim3(EW_BLOCK), 0, s, a);
+	static std::atomic<int> resident{0};
+	launch_one_wave(ew_program_kernel<PT>, resident, a, want, s);
 }
 
 template<class PT>
 static void launch_program_dev(const ew_args & a, int want, cudaStream_t s) {
-	static int resident = 0;
-	if (resident == 0) {
-		int nb = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ew_program_kernel<PT, true>, EW_BLOCK, 0) != cudaSuccess || nb < 1)
-			nb = 4;
-		resident = nb * SM_COUNT;
-	}
-	const int grid = want < resident ? want : resident;
-	launch_dependent(ew_program_kernel<PT, true>, dim3(grid), dim3(EW_BLOCK), 0, s, a);
+	static std::atomic<int> resident{0};
+	launch_one_wave(ew_program_kernel<PT, true>, resident, a, want, s);
 }
 
 static std::string key_of(const program & p) {
@@ -272,6 +277,8 @@ static std::string describe(const pending * q, int n) {
 		s += is_reduction(q[i].op) ? rnames[q[i].op - RD_FIRST] : names[q[i].op];
 		auto id = [](fsb_vec_s * v) { return v ? std::to_string(v->id) : std::string("-"); };
 		s += "(z" + id(q[i].z) + ",x" + id(q[i].x) + ",y" + id(q[i].y) + ")";
+		if (q[i].kind == pending::RED)
+			s += "#" + std::to_string(q[i].token);
 	}
 	return s;
 }
@@ -285,18 +292,21 @@ struct bound_group {
 	bool box = false; // structured-grid layout
 };
 
-static void launch_interp(const bound_group & g, int want, cudaStream_t s) {
-	static int resident = 0;
-	if (resident == 0) {
+static void launch_interp(const bound_group & g, int want, cudaStream_t s) { // want < 0: load only, as launch_one_wave
+	static std::atomic<int> resident{0};
+	if (resident.load(std::memory_order_acquire) == 0) {
 		int nb = 0;
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ew_interp_kernel<0>, EW_BLOCK, 0) != cudaSuccess || nb < 1)
 			nb = 4;
-		resident = nb * SM_COUNT;
+		resident.store(nb * SM_COUNT, std::memory_order_release);
 	}
+	if (want < 0)
+		return;
 	interp_args ia;
 	ia.a = g.args;
 	ia.p = g.prog;
-	launch_dependent(ew_interp_kernel<0>, dim3(want < resident ? want : resident), dim3(EW_BLOCK), 0, s, ia);
+	const int most = resident.load(std::memory_order_relaxed);
+	launch_dependent(ew_interp_kernel<0>, dim3(want < most ? want : most), dim3(EW_BLOCK), 0, s, ia);
 }
 
 // bind queue[i, i+len) to a registered kernel; with allow_generic, to the generic kernel if there is none
@@ -485,7 +495,7 @@ void flush(fsb_ctx_s * c) {
 				}
 			}
 			if (c->trace)
-				fprintf(stderr, "[fsb] launch: spmv%s\n", dot ? " + dot" : "");
+				fprintf(stderr, "[fsb %d] launch: spmv%s%s\n", c->rank, dot ? " + dot #" : "", dot ? std::to_string(dot->token).c_str() : "");
 			spmv_group(c, q[i], dot);
 			if (dot) {
 				publish_multi_rank(c, dot, 1);
@@ -548,7 +558,7 @@ void flush(fsb_ctx_s * c) {
 		if (!g.launch)
 			c->stats[FSB_STAT_UNMATCHED_GROUPS]++;
 		if (c->trace)
-			fprintf(stderr, "[fsb] launch%s: %s\n", g.launch ? "" : " (generic)", describe(&q[i], len).c_str());
+			fprintf(stderr, "[fsb %d] launch%s: %s\n", c->rank, g.launch ? "" : " (generic)", describe(&q[i], len).c_str());
 		if (n > 0 || (g.nr > 0 && c->nranks > 1)) {
 			long long packets = layout_of(q[i])->box ? n : (n + 1) / 2; // box layout: one element per thread and trip
 			long long want = (packets + EW_BLOCK - 1) / EW_BLOCK;
@@ -556,6 +566,14 @@ void flush(fsb_ctx_s * c) {
 			g.args.tl = timeline_slot(c, TL_KIND_EW + len); // kind = 16 + number of statements
 			int resident = 0;
 			const void * jk = (!g.launch && c->jit) ? jit_kernel(g.prog, g.dev, g.box, &resident) : nullptr;
+			if (g.nr > 0 && c->d_xrank && c->boot && c->boot->in_process()) {
+				// the kernel's last CTA waits for the peers' values: meet them first, with the kernel compiled and loaded
+				if (g.launch)
+					g.launch(g.args, -1, c->stream);
+				else if (!jk)
+					launch_interp(g, -1, c->stream);
+				c->boot->rendezvous();
+			}
 			if (g.launch)
 				g.launch(g.args, grid, c->stream);
 			else if (jk) {
@@ -566,6 +584,8 @@ void flush(fsb_ctx_s * c) {
 				launch_interp(g, grid, c->stream);
 			FSB_CUDA(cudaGetLastError());
 			c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+			if (g.nr > 0 && c->d_xrank && c->boot && c->boot->in_process())
+				c->boot->rendezvous(); // every rank's kernel of this step is launched before any rank goes on (setup_exchange.h)
 		}
 		else if (g.nr > 0) {
 			// empty local part: publish fold identities without a kernel

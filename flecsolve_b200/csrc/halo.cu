@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "fsb_internal.h"
+#include "setup_exchange.h"
 #include "spmv_common.cuh"
 
 namespace fsb {
@@ -55,74 +56,27 @@ void halo_p2p_setup(fsb_parcsr_s * A, const std::vector<int64_t> & dest_off) {
 		if (std::atoi(e) == 0)
 			return;
 	// capacity = max ghost count over ranks
-	long long * d_g = nullptr;
-	FSB_CUDA(cudaMalloc(&d_g, sizeof(long long)));
-	long long g = A->n_ghost;
-	FSB_CUDA(cudaMemcpyAsync(d_g, &g, sizeof(g), cudaMemcpyHostToDevice, c->stream));
-	FSB_NCCL(ncclAllReduce(d_g, d_g, 1, ncclInt64, ncclMax, c->nccl, c->stream));
-	FSB_CUDA(cudaMemcpyAsync(&g, d_g, sizeof(g), cudaMemcpyDeviceToHost, c->stream));
-	FSB_CUDA(cudaStreamSynchronize(c->stream));
-	cudaFree(d_g);
+	long long g = 0;
+	for (long long n : c->boot->gather<long long>(A->n_ghost, P))
+		g = std::max(g, n);
 	const long long gmax = std::max<long long>(g, 1);
 	const size_t bytes = 256 + 2 * static_cast<size_t>(gmax) * 16; // two landing buffers of flagged 16-byte words
 	unsigned char * block = nullptr;
 	FSB_CUDA(cudaMalloc(&block, bytes));
 	FSB_CUDA(cudaMemset(block, 0, bytes)); // flags 0: no exchange number matches
-	struct packet {
-		cudaIpcMemHandle_t h;
-		long long ok;
-	};
-	packet mine{};
-	mine.ok = cudaIpcGetMemHandle(&mine.h, block) == cudaSuccess ? 1 : 0;
-	packet * d_all = nullptr;
-	FSB_CUDA(cudaMalloc(&d_all, sizeof(packet) * P));
-	FSB_CUDA(cudaMemcpy(d_all + c->rank, &mine, sizeof(packet), cudaMemcpyHostToDevice));
-	FSB_NCCL(ncclAllGather(d_all + c->rank, d_all, sizeof(packet), ncclChar, c->nccl, c->stream));
-	std::vector<packet> all(P);
-	FSB_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(packet) * P, cudaMemcpyDeviceToHost, c->stream));
-	FSB_CUDA(cudaStreamSynchronize(c->stream));
-	cudaFree(d_all);
-	bool ok = true;
-	for (int q = 0; q < P; ++q)
-		ok = ok && all[q].ok;
+	void * peers[8] = {};
+	if (!c->boot->share(block, peers)) {
+		cudaFree(block);
+		return;
+	}
 	halo_dev h{};
 	h.me = c->rank;
 	h.nranks = P;
 	std::vector<void *> opened(P, nullptr);
-	for (int q = 0; q < P && ok; ++q) {
-		if (q == c->rank) {
-			h.base[q] = block;
-			continue;
-		}
-		// only neighbours need to be mapped
-		bool is_nbr = false;
-		for (const neighbour & nb : A->nbrs)
-			is_nbr = is_nbr || nb.rank == q;
-		if (!is_nbr)
-			continue;
-		void * p = nullptr;
-		if (cudaIpcOpenMemHandle(&p, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-			cudaGetLastError();
-			ok = false;
-			break;
-		}
-		opened[q] = p;
-		h.base[q] = static_cast<unsigned char *>(p);
-	}
-	long long * d_ok = nullptr;
-	FSB_CUDA(cudaMalloc(&d_ok, sizeof(long long)));
-	long long v = ok ? 1 : 0;
-	FSB_CUDA(cudaMemcpy(d_ok, &v, sizeof(v), cudaMemcpyHostToDevice));
-	FSB_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt64, ncclMin, c->nccl, c->stream));
-	FSB_CUDA(cudaMemcpyAsync(&v, d_ok, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
-	FSB_CUDA(cudaStreamSynchronize(c->stream));
-	cudaFree(d_ok);
-	if (!v) {
-		for (void * p : opened)
-			if (p)
-				cudaIpcCloseMemHandle(p);
-		cudaFree(block);
-		return;
+	for (int q = 0; q < P; ++q) {
+		h.base[q] = static_cast<unsigned char *>(peers[q]);
+		if (q != c->rank)
+			opened[q] = peers[q];
 	}
 	h.n_nbr = static_cast<int>(A->nbrs.size());
 	for (int k = 0; k < h.n_nbr; ++k) {
@@ -159,8 +113,8 @@ void halo_p2p_destroy(fsb_parcsr_s * A) {
 	if (!A->halo_p2p)
 		return;
 	for (void * p : A->halo_opened)
-		if (p)
-			cudaIpcCloseMemHandle(p);
+		if (p && A->ctx->boot)
+			A->ctx->boot->unshare(p);
 	cudaFree(A->halo_counters);
 	cudaFree(A->halo_block);
 	cudaFree(A->halo_p2p);
@@ -185,9 +139,15 @@ void halo_p2p_push(fsb_parcsr_s * A, fsb_vec_s * x) {
 // finish it: ghosts of x become valid (compute stream)
 void halo_p2p_unpack(fsb_parcsr_s * A, fsb_vec_s * x) {
 	fsb_ctx_s * c = A->ctx;
+	if (c->boot && c->boot->in_process()) { // the kernel waits for the neighbours' push kernels
+		preload_kernel(halo_unpack_kernel);
+		c->boot->rendezvous();
+	}
 	halo_unpack_kernel<<<A->halo_unpack_ctas, HALO_THREADS, 0, c->stream>>>(static_cast<const halo_dev *>(A->halo_p2p),
 	                                                                         x->d + x->n_owned, A->halo_epoch);
 	FSB_CUDA(cudaGetLastError());
+	if (c->boot && c->boot->in_process())
+		c->boot->rendezvous();
 	// my own push has long finished by now (the peers waited for it); ordering it before whatever
 	// the compute stream does next keeps later writers of x from racing with it
 	FSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));

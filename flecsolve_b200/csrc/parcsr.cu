@@ -11,6 +11,7 @@
 #include <thrust/iterator/transform_iterator.h>
 
 #include "fsb_internal.h"
+#include "setup_exchange.h"
 
 namespace fsb {
 
@@ -89,14 +90,8 @@ static void build_halo_plan(fsb_parcsr_s * A) {
 		}
 	}
 	// all-gather the P x P count matrix
-	int64_t * d_cnt = dev_alloc<int64_t>(static_cast<size_t>(P) * P);
-	FSB_CUDA(cudaMemcpyAsync(d_cnt + static_cast<size_t>(me) * P, recv_cnt.data(), P * sizeof(int64_t),
-	                         cudaMemcpyHostToDevice, c->stream));
-	FSB_NCCL(ncclAllGather(d_cnt + static_cast<size_t>(me) * P, d_cnt, P, ncclInt64, c->nccl, c->stream));
 	std::vector<int64_t> all(static_cast<size_t>(P) * P);
-	FSB_CUDA(cudaMemcpyAsync(all.data(), d_cnt, all.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-	FSB_CUDA(cudaStreamSynchronize(c->stream));
-	cudaFree(d_cnt);
+	c->boot->allgather(recv_cnt.data(), all.data(), P * sizeof(int64_t));
 
 	std::vector<int64_t> send_cnt(P, 0), send_off(P, 0);
 	int64_t send_total = 0;
@@ -105,28 +100,18 @@ static void build_halo_plan(fsb_parcsr_s * A) {
 		send_off[q] = send_total;
 		send_total += send_cnt[q];
 	}
-	// ship the requested global ids to their owners
-	int64_t * d_want = dev_alloc<int64_t>(A->colmap.size());
-	int64_t * d_asked = dev_alloc<int64_t>(static_cast<size_t>(send_total));
-	if (!A->colmap.empty())
-		FSB_CUDA(cudaMemcpyAsync(d_want, A->colmap.data(), A->colmap.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
-		                         c->stream));
-	FSB_NCCL(ncclGroupStart());
-	for (int q = 0; q < P; ++q) {
-		if (q == me)
-			continue;
-		if (recv_cnt[q] > 0)
-			FSB_NCCL(ncclSend(d_want + recv_off[q], recv_cnt[q], ncclInt64, q, c->nccl, c->stream));
-		if (send_cnt[q] > 0)
-			FSB_NCCL(ncclRecv(d_asked + send_off[q], send_cnt[q], ncclInt64, q, c->nccl, c->stream));
-	}
-	FSB_NCCL(ncclGroupEnd());
+	// every rank learns which of its entries the others need: rank q's ghost list is sorted by global id, so the ids it
+	// wants from me are one contiguous piece of it (owners are contiguous ranges)
+	const std::vector<std::vector<int64_t>> wanted = c->boot->gatherv(A->colmap, P);
 	std::vector<int64_t> asked(static_cast<size_t>(send_total));
-	if (send_total > 0)
-		FSB_CUDA(cudaMemcpyAsync(asked.data(), d_asked, asked.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-	FSB_CUDA(cudaStreamSynchronize(c->stream));
-	cudaFree(d_want);
-	cudaFree(d_asked);
+	for (int q = 0; q < P; ++q) {
+		if (q == me || send_cnt[q] == 0)
+			continue;
+		const std::vector<int64_t> & w = wanted[static_cast<size_t>(q)];
+		const auto first = std::lower_bound(w.begin(), w.end(), A->row_part[me]);
+		FSB_REQUIRE(w.end() - first >= send_cnt[q], "halo plan: inconsistent ghost counts");
+		std::copy(first, first + send_cnt[q], asked.begin() + send_off[q]);
+	}
 
 	std::vector<int32_t> send_idx(static_cast<size_t>(send_total));
 	bool need_pack = false;
@@ -181,6 +166,8 @@ __global__ void pack_kernel(const double * __restrict__ x, const int32_t * __res
 // Ghost update of x on the communication stream; the caller orders streams around it.
 static void halo_exchange_async(fsb_parcsr_s * A, fsb_vec_s * x) {
 	fsb_ctx_s * c = A->ctx;
+	if (!c->nccl)
+		throw error(FSB_ERR_STATE, "ghost exchange: no peer-memory path for this matrix and no NCCL communicator (rank group in one process)");
 	// x must be complete on the main stream before it is packed/sent
 	FSB_CUDA(cudaEventRecord(c->ev_main, c->stream));
 	FSB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_main, 0));

@@ -26,12 +26,14 @@
 //    (mg/jacobi.hh:73-89: skip the diagonal while summing, x = w/d (b - lpu) + (1-w) tmp) in the same pass.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
 
 #include "fsb_internal.h"
+#include "setup_exchange.h"
 #include "spmv_common.cuh"
 
 namespace fsb {
@@ -85,6 +87,7 @@ struct spmv_args {
 	int aux_mode; // 0 none; 1 staged with the block by a bulk copy; 2 u is x itself: read it from the x window at the
 	              // diagonal's position (CG's <Ap, p>: no extra bytes at all); 3 plain global load
 	unsigned long long * tl; // timeline slot of this launch or nullptr
+	setup_exchange * meet; // host side only: rendezvous of the ranks' threads right before the launch (in-process groups)
 };
 
 // ------------------------------------------------------------------------------------------------ shared pieces
@@ -922,6 +925,8 @@ static int resident_ctas(Kernel kern, const spmv_config & k, const char * what) 
 		size_t smem = 0;
 	};
 	static std::unordered_map<const void *, entry> cache;
+	static std::mutex guard; // the ranks of an in-process group launch from their own threads
+	std::lock_guard<std::mutex> lock(guard);
 	entry & e = cache[reinterpret_cast<const void *>(kern)];
 	if (e.threads != k.threads || e.smem != k.smem) {
 		// 227 KB per CTA in all; the variants with boundary phases keep up to 8.5 KB of it as static scratch
@@ -959,7 +964,11 @@ static int launch_kernel(Kernel kern, const spmv_args & a, const spmv_config & k
 		b.chunk = std::min(env_chunk, 4);
 	if (b.halo) // every CTA pushes its share of the boundary entries while its first stage is in flight: a few stores and
 		b.push_parts = grid; // one system fence each, so no CTA starts its row blocks later than the others
+	if (b.meet)
+		b.meet->rendezvous(); // after the occupancy queries above, which may load the kernel
 	launch_dependent(kern, dim3(grid), dim3(k.threads), k.smem, s, b);
+	if (b.meet)
+		b.meet->rendezvous(); // ... and nobody goes on before every rank's kernel is launched
 	return grid;
 }
 
@@ -1102,6 +1111,7 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const spmv_call & call, cuda
 		a.o_rows = A->offd.row_ids;
 		a.n_owned = A->n_local;
 	}
+	a.meet = (c->boot && (call.halo || a.xr)) ? c->boot.get() : nullptr; // the kernel waits for the peers' kernels of this step
 	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
 	a.tl = timeline_slot(c, call.halo ? TL_KIND_SPMV_FUSED : (rowlist ? TL_KIND_SPMV_OFFD : TL_KIND_SPMV) + (call.jacobi ? 8 : 0));
 	const bool prof = c->profile && s == c->stream;
@@ -1137,8 +1147,14 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const spmv_call & call, cuda
 void finalize_reduction(fsb_ctx_s * c, int n_partials, const pending & red) {
 	red_out r{};
 	fill_red_out(c, red, r);
+	if (c->boot && c->d_xrank && c->boot->in_process()) {
+		preload_kernel(fold_partials_kernel);
+		c->boot->rendezvous();
+	}
 	fold_partials_kernel<<<1, 256, 0, c->stream>>>(c->d_partials, n_partials, r, c->d_xrank);
 	FSB_CUDA(cudaGetLastError());
+	if (c->boot && c->d_xrank && c->boot->in_process())
+		c->boot->rendezvous();
 	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
 }
 

@@ -92,6 +92,12 @@ int fsb_device_count(void);
  * broadcast by the caller (any transport); NULL when nranks == 1.           */
 int fsb_nccl_unique_id(void * out128);
 int fsb_ctx_create(int device, int rank, int nranks, const void * nccl_unique_id, fsb_ctx_t * out);
+/* All ranks as threads of THIS process on ONE device: out[0 .. nranks) are the contexts of ranks 0 .. nranks-1 of one
+ * group.  Every collective call (matrix creation, anything that waits for a reduction) must then be made by nranks host
+ * threads, one per context, as nranks processes would.  The ranks' kernels share the device (row blocks small enough to
+ * be resident together: a kernel that waits for a peer spins on the device), ghost exchange and all-reduce go through
+ * the same peer-memory kernels as across GPUs -- for tests and for debugging a sharded run on one GPU, not for speed. */
+int fsb_ctx_create_group(int device, int nranks, fsb_ctx_t * out);
 int fsb_ctx_destroy(fsb_ctx_t ctx);
 int fsb_ctx_flush(fsb_ctx_t ctx); /* launch everything queued; no host wait */
 int fsb_ctx_sync(fsb_ctx_t ctx); /* flush + wait for the stream */

@@ -76,8 +76,9 @@ def config3_heat(world, ctx, nn=256, steps=10):
     u0 = np.where(mid(i) & mid(j) & mid(k), 50.0, 0.0)
     kw = dict(method="BDF2", time_rtol=1e-2, time_atol=1e-4, initial_dt=1e-2, max_dt=1e-2, min_dt=1e-6, final_time=0.1)
     opts = H.make_bdf_options(error_scaling="fixed-resolution", norm="inf", max_attempts=steps, **kw)
-    S.bdf_heat(u0, H.make_bdf_options(max_attempts=1, **kw), solver="gmres", rtol=1e-6, maxiter=10000, max_krylov_dim=50,
-               restart=True)  # warm-up: allocations
+    # warm-up: allocations, and the one-off run-time compilation of the integrator's statement groups that have no
+    # ahead-of-time kernel (cached per process)
+    S.bdf_heat(u0, opts, solver="gmres", rtol=1e-6, maxiter=10000, max_krylov_dim=50, restart=True)
     ctx.sync(); ctx.reset_stats()
     D.barrier(world)
     t0 = time.perf_counter()
@@ -123,7 +124,7 @@ def config4_multi(world, ctx, nn=256):
     b1 = rng.random(N)[lo:lo + n]
     b = np.concatenate([np.zeros(n), b1])
     x0 = np.full(2 * n, 2.0)
-    H.solve_multi2(ctx, A0, A1, b, x0, solver="bicgstab", rtol=1e-6, maxiter=3)  # warm-up
+    H.solve_multi2(ctx, A0, A1, b, x0, solver="bicgstab", rtol=1e-6, maxiter=8)  # warm-up (allocations, run-time kernels)
     ctx.sync(); ctx.reset_stats()
     D.barrier(world)
     t0 = time.perf_counter()

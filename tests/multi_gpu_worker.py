@@ -136,6 +136,59 @@ def main():
         assert ctx.stat("allreduces") == 0  # reductions went through peer memory inside the kernels
     S.close()
     B.destroy()
+
+    # ---- BASELINE configs 3 and 4 sharded: implicit heat step (BDF2 + GMRES through operator_adapter) and BiCGStab on a
+    # two-component vec::multi with the Dirichlet / Neumann+shift blocks -- against the same drivers on ONE rank
+    # (a private single-rank context on this rank's GPU)
+    solo = F.Context(world.local_rank)
+    nn = 12
+    dims = (nn, nn, nn * P if P > 1 else nn)
+    nloc, N = None, dims[0] * dims[1] * dims[2]
+    hgrid = 10.0 / (nn + 1)
+    rng3 = np.random.default_rng(3)
+    bfull = rng3.random(N)
+    g = np.arange(N)
+    gi, gj, gk = g % dims[0], (g // dims[0]) % dims[1], g // (dims[0] * dims[1])
+    mid = lambda a, m: (5 * a >= 2 * m) & (5 * a < 3 * m)
+    u0 = np.where(mid(gi, dims[0]) & mid(gj, dims[1]) & mid(gk, dims[2]), 50.0, 0.0)
+    bdf = dict(method="BDF2", time_rtol=1e-2, time_atol=1e-4, initial_dt=1e-2, max_dt=1e-2, min_dt=1e-6, final_time=0.1,
+               error_scaling="fixed-resolution", norm="inf", max_attempts=6)
+    res = {}
+    for tag, cx in (("sharded", ctx), ("solo", solo)):
+        Ah = F.ParCSR.stencil(cx, 7, *dims, 0.0, -1.0 / (hgrid * hgrid))
+        lo, hi = Ah.row_begin, Ah.row_begin + Ah.local_rows
+        Sh = H.Session(cx, Ah)
+        u, r, dts, good, iters = Sh.bdf_heat(u0[lo:hi], H.make_bdf_options(**bdf), solver="gmres", rtol=1e-6, maxiter=1000,
+                                             max_krylov_dim=30, restart=True)
+        A0 = F.ParCSR.stencil(cx, 7, *dims)
+        A1 = F.ParCSR.stencil(cx, 107, *dims, 1e-3, 1.0)
+        n0 = A0.local_rows
+        bb = np.concatenate([np.zeros(n0), bfull[lo:hi]])
+        xm, minfo, mhist = H.solve_multi2(cx, A0, A1, bb, np.full(2 * n0, 2.0), solver="bicgstab", rtol=1e-8, maxiter=500,
+                                          history_cap=600)
+        xc, cinfo, chist = H.solve_multi2(cx, A0, A1, bb, np.full(2 * n0, 2.0), solver="cg", rtol=1e-8, maxiter=500,
+                                          history_cap=600)
+        res[tag] = dict(lo=lo, hi=hi, u=u, steps=(r.steps, r.rejects, r.attempts), dts=dts, iters=iters, xm=xm, minfo=minfo,
+                        xc=xc, cinfo=cinfo, chist=chist)
+        Sh.close(); Ah.destroy(); A0.destroy(); A1.destroy()
+    a, b1 = res["sharded"], res["solo"]
+    lo, hi = a["lo"], a["hi"]
+    assert a["steps"] == b1["steps"], (a["steps"], b1["steps"])
+    assert np.allclose(a["dts"], b1["dts"], rtol=1e-6) and np.all(np.abs(a["iters"] - b1["iters"]) <= 1)
+    assert np.abs(a["u"] - b1["u"][lo:hi]).max() <= 1e-6 * max(1.0, np.abs(b1["u"]).max())
+    assert a["cinfo"].reason == b1["cinfo"].reason == "converged_rtol" and abs(a["cinfo"].iters - b1["cinfo"].iters) <= 1
+    m = min(len(a["chist"]), len(b1["chist"]), 30)
+    assert np.allclose(a["chist"][:m], b1["chist"][:m], rtol=1e-8)
+    n1 = hi - lo
+    for comp in range(2):
+        full = b1["xc"][comp * N:(comp + 1) * N][lo:hi]
+        assert np.abs(a["xc"][comp * n1:(comp + 1) * n1] - full).max() <= 1e-6
+    assert a["minfo"].reason == b1["minfo"].reason == "converged_rtol"
+    assert abs(a["minfo"].iters - b1["minfo"].iters) <= max(2, 0.1 * b1["minfo"].iters)
+    for comp in range(2):
+        full = b1["xm"][comp * N:(comp + 1) * N][lo:hi]
+        assert np.abs(a["xm"][comp * n1:(comp + 1) * n1] - full).max() <= 1e-5
+    solo.close()
     ctx.close()
     D.finalize(world)
     print(f"rank {me}/{P}: multi-gpu checks passed", flush=True)

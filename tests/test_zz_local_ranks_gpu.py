@@ -1,0 +1,151 @@
+"""The sharded path on ONE GPU: the ranks of a group are threads of this process sharing the device
+(fsb_ctx_create_group), so the colour split (topo/csr.hh:482-618), the ghost exchange inside the SpMV kernel, the
+cross-rank all-reduce inside the reduction kernels and the solvers on top of them run -- and are held against the
+oracle -- on a single-GPU box as well (tests/test_multi_gpu.py needs one GPU per rank).  Same checks as
+tests/multi_gpu_worker.py, sizes small enough for the ranks' kernels to be resident together."""
+import threading
+
+import numpy as np
+import pytest
+
+import oracle as O
+from flecsolve_b200 import _lib as F
+from flecsolve_b200 import dist as D
+from flecsolve_b200 import host as H
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ranks(nranks, body):
+    """body(ctx, rank) -> objects to destroy, on one thread per rank; re-raises the first failure.  Matrices are
+    destroyed only after every rank has drained its stream: releasing device memory waits for the whole device, and a
+    peer's kernel may be waiting for this rank's next launch."""
+    if F.device_count() == 0:
+        pytest.skip("no CUDA device")
+    ctxs = F.Context.group(0, nranks)
+    errors = [None] * nranks
+    gate = threading.Barrier(nranks)
+
+    def work(r):
+        garbage = []
+        try:
+            garbage = body(ctxs[r], r) or []
+        except BaseException as e:  # noqa: BLE001 - reported below
+            errors[r] = e
+            gate.abort()
+            return
+        ctxs[r].sync()
+        try:
+            gate.wait(timeout=60)
+        except threading.BrokenBarrierError:
+            return
+        for obj in garbage:
+            obj.close() if hasattr(obj, "close") else obj.destroy()
+
+    import faulthandler
+    import sys
+    faulthandler.dump_traceback_later(25, file=sys.stderr)  # where every rank is, should one of them never return
+    threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(nranks)]  # a stuck rank must not keep the process alive
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=30)
+    faulthandler.cancel_dump_traceback_later()
+    for e in errors:  # a rank that failed leaves its peers waiting in the next collective: report the cause first
+        if e is not None:
+            raise e
+    hung = [t for t in threads if t.is_alive()]
+    assert not hung, "a rank did not finish"
+    for c in ctxs:
+        c.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_split_spmv_reductions_and_jacobi(nranks):
+    P = nranks
+    rng0 = np.random.default_rng(0)
+    dims = (7, 6, 11)
+    rp, col, val = O.stencil_csr(27, *dims)
+    val = val * rng0.uniform(0.5, 1.5, val.size)
+    n = len(rp) - 1
+    part = D.equal_map(n, P)
+    M = O.ParCSR(rp, col, val, colours=P)
+    x = rng0.standard_normal(n)
+    ref = M.spmv(x)
+    b = M.spmv(np.linspace(1, 2, n))
+    x0 = rng0.standard_normal(n)
+    w = float(np.float32(2 / 3))
+    refj = M.jacobi_relax(w, 3, b, x0)
+
+    def body(ctx, me):
+        lo, hi = part[me], part[me + 1]
+        A = F.ParCSR.from_csr(ctx, n, part, rp[lo:hi + 1] - rp[lo], col[rp[lo]:rp[hi]], val[rp[lo]:rp[hi]])
+        for which in (0, 1):  # the oracle's colour `me` (topo/csr.hh color() / init_mats())
+            orp, ocol, oval, ocm = M.block(me, which)
+            drp, dcol, dval = A.download(which)
+            assert np.array_equal(drp, orp) and np.array_equal(dcol, ocol) and np.array_equal(dval, oval), ("split", which)
+        assert np.array_equal(A.colmap(), M.block(me, 1)[3])
+        assert A.info("fused_halo") == 1
+        xv, yv = A.vector(x[lo:hi]), A.vector()
+        launches = ctx.stat("launches")
+        A.spmv(xv, yv)
+        got = yv.download()
+        assert ctx.stat("launches") - launches == 1  # ghost exchange included
+        assert np.array_equal(got, ref[lo:hi]), np.abs(got - ref[lo:hi]).max()
+        d = xv.dot(yv)
+        assert abs(d - x @ ref) <= 1e-12 * np.abs(x * ref).sum()
+        assert xv.global_size() == n
+        assert xv.max() == x.max() and xv.min() == x.min() and xv.inf_norm() == np.abs(x).max()
+        A.spmv(xv, yv)
+        t = yv.dot_token(xv)
+        assert abs(ctx.get(t) - x @ ref) <= 1e-12 * np.abs(x * ref).sum()
+        assert ctx.stat("allreduces") == 0  # reductions crossed the ranks inside the kernels
+        bv, xj, tv = A.vector(b[lo:hi]), A.vector(x0[lo:hi]), A.vector()
+        A.jacobi_relax(w, 3, bv, xj, tv)
+        assert np.array_equal(xj.download(), refj[lo:hi])
+        # explicit ghost update (the copy plan of topo/csr.hh:237-245)
+        A.halo_exchange(xv)
+        ghosts = xv.download(A.local_rows + A.num_ghosts)[A.local_rows:]
+        assert np.array_equal(ghosts, x[A.colmap()])
+        return [xv, yv, bv, xj, tv, A]
+
+    run_ranks(nranks, body)
+
+
+@pytest.mark.parametrize("kind,dims", [(7, (12, 11, 13)), (27, (9, 8, 11)), (107, (7, 9, 8))])
+def test_device_generator_and_solvers(kind, dims):
+    P = 2
+    rp, col, val = O.stencil_csr(kind, *dims, 1e-3 if kind == 107 else 0.0, 1.0)
+    n = len(rp) - 1
+    M = O.ParCSR(rp, col, val, colours=P)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(n)
+    b = M.spmv(np.linspace(1, 2, n))
+    xo, oinfo, ohist = M.cg(b, dinv=M.dinv(), rtol=1e-9, maxiter=1000, history_cap=1000)
+
+    def body(ctx, me):
+        B = F.ParCSR.stencil(ctx, kind, *dims, 1e-3 if kind == 107 else 0.0, 1.0)
+        lo, hi = B.row_begin, B.row_begin + B.local_rows
+        assert [lo, hi] == list(M.partition()[me:me + 2])
+        for which in (0, 1):
+            orp, ocol, oval, ocm = M.block(me, which)
+            drp, dcol, dval = B.download(which)
+            assert np.array_equal(drp, orp) and np.array_equal(dcol, ocol) and np.array_equal(dval, oval), ("gen", which)
+        assert np.array_equal(B.colmap(), M.block(me, 1)[3])
+        xv, yv = B.vector(x[lo:hi]), B.vector()
+        B.spmv(xv, yv)
+        assert np.array_equal(yv.download(), M.spmv(x)[lo:hi])
+        S = H.Session(ctx, B)
+        for solver, lag in (("cg", 0), ("cg_device", 2), ("cg_sr", 2)):
+            xs, info, hist = S.solve(b[lo:hi], np.zeros(hi - lo), solver=solver, precond="dinv", rtol=1e-9, maxiter=1000,
+                                     history_cap=1000, lag=lag)
+            assert info.reason == "converged_rtol" and abs(info.iters - oinfo.iters) <= (2 if solver == "cg_sr" else 1), solver
+            m = min(len(hist), len(ohist), 25)
+            assert np.allclose(hist[:m], ohist[:m], rtol=1e-6 if solver == "cg_sr" else 1e-8), solver
+            assert np.abs(xs - xo[lo:hi]).max() <= 1e-6
+        xb, binfo, _ = S.solve(b[lo:hi], np.zeros(hi - lo), solver="bicgstab", precond="dinv", rtol=1e-9, maxiter=1000)
+        assert binfo.reason == "converged_rtol" and np.abs(xb - xo[lo:hi]).max() <= 1e-6
+        assert ctx.stat("halo_exchanges") > 0
+        return [S, xv, yv, B]
+
+    run_ranks(P, body)
