@@ -120,16 +120,21 @@ def pinned(n: int) -> np.ndarray:
     return torch.empty(n, dtype=torch.float64).pin_memory().numpy()
 
 
-def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str, with_e2e: bool, history_cap: int = 0) -> dict:
-    """one workload on the ranks of `world`: device-resident timing of K iterations, SpMV roofline, optionally e2e"""
+def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str, with_e2e: bool, history_cap: int = 0,
+            dictionary: bool = True) -> dict:
+    """one workload on the ranks of `world`: device-resident timing of K iterations, SpMV roofline, optionally e2e.
+    dictionary=False: the matrix is built with FSB_OPT_SPMV_DICTIONARY off, i.e. as any matrix with more than 256 distinct
+    values is held (fp64 value per nonzero)"""
     from flecsolve_b200 import _lib as F
     from flecsolve_b200 import dist as D
     from flecsolve_b200 import host as H
 
     kind, nx, ny, nz, precond = WORKLOADS[workload]
     t0 = time.time()
+    ctx.set_option("spmv_dictionary", 1 if dictionary else 0)
     A = F.ParCSR.stencil(ctx, kind, nx, ny, nz)
     ctx.sync()
+    ctx.set_option("spmv_dictionary", 1)
     n_local, n_global = A.local_rows, A.global_rows
     nnz_local = A.nnz(0) + A.nnz(1)
     nnz_global = int(D.sum_over_ranks(world, nnz_local))
@@ -192,7 +197,11 @@ def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str
     iter_bytes = 12 * nnz + off * N + (108 - 4) * N + 8 * A.num_ghosts  # 12 nnz + 108 N (int32 offsets)
     # bytes of the format the device really streams (window format: 8 + 2 per nonzero, 16-bit block-relative row offsets)
     window = A.info("window_format") == 1
-    fmt_bytes = (10 * nnz + 2 * (2 * N + A.info("row_blocks")) if window else 12 * nnz + off * (N + 1)) + 16 * N + 16 * A.num_ghosts
+    dictionary = A.info("value_dictionary") if window else 0
+    if dictionary:  # 1-byte value index + 16-bit position per slot (rows padded to 8 slots), 3 x 16-bit row meta
+        fmt_bytes = 3 * A.info("dictionary_slots") + 2 * (3 * N + A.info("row_blocks")) + 16 * N + 16 * A.num_ghosts
+    else:
+        fmt_bytes = (10 * nnz + 2 * (2 * N + A.info("row_blocks")) if window else 12 * nnz + off * (N + 1)) + 16 * N + 16 * A.num_ghosts
     spmv_avg_ms = spmv_ms / max(spmv_n, 1)  # per SpMV: all its launches (one, unless the two-launch transports are in use)
     spmv_gbs = spmv_bytes / spmv_avg_ms / 1e6 if spmv_avg_ms > 0 else 0.0
     iter_gbs = iter_bytes / ms_per_step / 1e6
@@ -200,9 +209,14 @@ def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str
         "workload": describe(workload), "value": 1000.0 / ms_per_step, "ms_per_step": ms_per_step,
         "rows": n_global, "nnz": nnz_global, "partition": f"{world.size} z-slab(s) of {n_local} rows",
         "gpu_launches": int(info.window_launches), "setup_seconds": setup_s,
-        "device_format": ("window: fp64 value + 16-bit position in the row block's staged x segments per nonzero (10 B), "
+        "device_format": (f"window + value dictionary: the matrix holds {dictionary} distinct values, so the device streams a 1-byte "
+                          "value index + 16-bit position in the row block's staged x segments per nonzero (3 B, rows padded to 8 "
+                          "slots) and multiplies the same fp64 values in the same order (general matrices: 10 B per nonzero, "
+                          "see `general_values`)" if dictionary else
+                          "window: fp64 value + 16-bit position in the row block's staged x segments per nonzero (10 B), "
                           "16-bit block-relative row offsets" if window else
                           f"csr: fp64 value + int32 column per nonzero (12 B), int{off * 8} row offsets"),
+        "value_dictionary": int(dictionary),
         "spmv_launches_per_product": split.get("launches_per_spmv"),
         "fused_halo": bool(A.info("fused_halo")),
         "roofline": {
@@ -213,7 +227,8 @@ def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str
             "launches_timed": spmv_n, "share_of_step": spmv_avg_ms / ms_per_step if ms_per_step > 0 else None,
             "format_bytes_per_launch": fmt_bytes, "achieved_format_gbs": fmt_bytes / spmv_avg_ms / 1e6 if spmv_avg_ms > 0 else 0.0,
             "note": "achieved = SURVEY 8(d) algorithmic bytes (12 B/nnz CSR) / time; the device streams format_bytes "
-                    "(window format: 10 B/nnz), so achieved may exceed the copy peak while achieved_format cannot",
+                    "(value dictionary: ~3.4 B/nnz, window format: 10 B/nnz), so achieved may exceed the copy peak while "
+                    "achieved_format cannot",
             "iteration": {"algorithmic_bytes": iter_bytes, "achieved": iter_gbs, "frac": iter_gbs / peak,
                           "frac_of_nominal_8TBs": iter_gbs / 8000.0},
         },
@@ -274,11 +289,27 @@ def run_ours(args):
     head = measure(world, ctx, args.workload, W, K, args.repeats, args.solver, with_e2e=True, history_cap=W + K)
     clocks = sampler.stop() if sampler else {}
     gpu_hist = head.pop("_history")
+
+    def general_values(full, wl, w, k):
+        """the same workload held as a matrix with more than 256 distinct values is (no value dictionary)"""
+        if not full.get("value_dictionary"):
+            return None
+        g = measure(world, ctx, wl, w, k, 1, args.solver, with_e2e=False, dictionary=False)
+        return {"what": "same solver and system, matrix built with FSB_OPT_SPMV_DICTIONARY off: the SpMV streams the fp64 "
+                        "values (window format, 10 B per nonzero) as for any matrix with more than 256 distinct values",
+                "value": g["value"], "ms_per_step": g["ms_per_step"], "device_format": g["device_format"],
+                "spmv_avg_launch_ms": g["roofline"]["avg_launch_ms"], "spmv_frac_of_peak": g["roofline"]["frac"],
+                "spmv_format_gbs": g["roofline"]["achieved_format_gbs"],
+                "iteration_frac_of_peak": g["roofline"]["iteration"]["frac"],
+                "other_solver": {"solver": g["other_solver"]["solver"], "value": g["other_solver"]["value"]}}
+
+    head["general_values"] = general_values(head, args.workload, W, K)
     extra = {}
     if not args.no_extra_workloads:
         for wl in EXTRA_WORKLOADS.get(args.workload, []):
             r = measure(world, ctx, wl, 5, 30, 1, args.solver, with_e2e=False)
             r.pop("_history", None)
+            r["general_values"] = general_values(r, wl, 5, 30)
             extra[wl] = r
 
     line = {
@@ -312,6 +343,7 @@ def run_ours(args):
         "solver": head["solver"],
         "other_solver": head["other_solver"],
         "single_reduction_solver": head["single_reduction_solver"],
+        "general_values": head.get("general_values"),
         "spmv_launches_per_product": head["spmv_launches_per_product"],
         "fused_halo": head["fused_halo"],
         "clocks": clocks,
@@ -464,7 +496,7 @@ def main():
     ap.add_argument("--no-extra-workloads", action="store_true", help="skip the 27-point 512^3 block")
     ap.add_argument("--repeats", type=int, default=3, help="timed solves of W+K iterations; the median one is reported")
     ap.add_argument("--solver", default="cg", choices=["cg", "cg_device"],
-                    help="cg: flecsolve's CG template unchanged (headline); cg_device: scalars kept on the device")
+                    help="cg: op::cg, the same call sequence as the reference's template (headline); cg_device: scalars kept on the device")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -186,7 +186,7 @@ def device_count() -> int:
 STAT = {"launches": 0, "fused_statements": 1, "halo_exchanges": 2, "allreduces": 3, "host_syncs": 4,
         "unmatched_groups": 5, "wait_ns": 6, "flush_ns": 7, "jit_groups": 8}
 OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3, "profile": 4, "reproducible": 5, "jit": 6,
-       "timeline": 7}
+       "timeline": 7, "spmv_dictionary": 8}
 
 
 class Context:
@@ -466,7 +466,7 @@ class ParCSR:
     def row_begin(self): return lib().fsb_parcsr_row_begin(self.h)
     def nnz(self, which=0): return lib().fsb_parcsr_local_nnz(self.h, which)
 
-    INFO = {"window_format": 0, "row_blocks": 1, "window_x": 2, "fused_halo": 3, "wide_offsets": 4}
+    INFO = {"window_format": 0, "row_blocks": 1, "window_x": 2, "fused_halo": 3, "wide_offsets": 4, "value_dictionary": 5, "dictionary_slots": 6}
 
     def info(self, key: str) -> int: return lib().fsb_parcsr_info(self.h, self.INFO[key])
 

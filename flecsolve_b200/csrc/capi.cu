@@ -344,6 +344,9 @@ int fsb_ctx_set_option(fsb_ctx_t c, int option, int64_t value) {
 		case FSB_OPT_JIT:
 			c->jit = value != 0;
 			break;
+		case FSB_OPT_SPMV_DICTIONARY:
+			c->spmv_dictionary = value != 0;
+			break;
 		case FSB_OPT_TIMELINE:
 			FSB_CUDA(cudaStreamSynchronize(c->stream));
 			cudaFree(c->d_timeline);
@@ -1043,6 +1046,8 @@ int64_t fsb_parcsr_info(fsb_parcsr_t A, int key) {
 	case FSB_INFO_WINDOW_X: return A->diag.win_xcap;
 	case FSB_INFO_FUSED_HALO: return A->halo_p2p != nullptr && A->diag.has_offd_map && !A->nbrs.empty();
 	case FSB_INFO_WIDE_OFFSETS: return A->diag.wide;
+	case FSB_INFO_VALUE_DICTIONARY: return A->diag.vidx ? A->diag.n_dict : 0;
+	case FSB_INFO_DICTIONARY_SLOTS: return A->diag.vidx ? A->diag.dict_slots : 0;
 	default: return -1;
 	}
 }

@@ -153,6 +153,7 @@ struct fsb_ctx_s {
 	bool jit = true; // statement groups without a compiled instantiation: compile one at run time (jit.cu); FSB_JIT=0 turns it off
 	int spmv_rows_per_cta = 0; // 0 = auto
 	int spmv_threads = 0;
+	bool spmv_dictionary = true; // FSB_OPT_SPMV_DICTIONARY
 
 	cudaEvent_t timers[16] = {};
 	bool profile = false;
@@ -212,6 +213,16 @@ struct csr_block {
 	uint16_t * rp16 = nullptr; // [n_rows + n_blk] row offsets relative to the block's first nonzero
 	void * segs = nullptr; // [n_blk][16] x segments per row block
 	int win_xcap = 0; // max x entries staged by one row block
+	// value dictionary (window format only): at most 256 distinct values, one byte per nonzero
+	// (rows padded to multiples of 8 slots, row blocks to multiples of 16: spmv.cu, build_value_dictionary)
+	uint8_t * vidx = nullptr; // [dict_slots] index of the slot's value in vdict
+	uint16_t * plcol = nullptr; // [dict_slots] its local column (lcol in the padded order)
+	uint16_t * pmeta = nullptr; // [3 n_rows + n_blk] per row block: slot offsets, row lengths, diagonal positions
+	std::vector<unsigned long long> dict_keys; // bit patterns of the distinct values (<= 256), ascending; empty: no dictionary
+	double * vdict = nullptr; // [256] the distinct values, ascending bit patterns
+	int n_dict = 0;
+	int max_blk_pnnz = 0; // slots of the largest row block
+	int64_t dict_slots = 0;
 };
 
 struct neighbour {
@@ -320,6 +331,8 @@ void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x);
 
 void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * host_rowptr);
 void build_window_format(fsb_ctx_s * c, csr_block & B, int64_t n_cols);
+void probe_value_dictionary(fsb_ctx_s * c, csr_block & B); // before build_blocks
+void build_value_dictionary(fsb_ctx_s * c, csr_block & B); // after build_window_format
 void attach_offd_rows(fsb_ctx_s * c, csr_block & D, const csr_block & O);
 void extract_dinv(fsb_parcsr_s * A, double * d);
 void halo_p2p_setup(fsb_parcsr_s * A, const std::vector<int64_t> & dest_off);

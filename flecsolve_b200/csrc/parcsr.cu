@@ -42,6 +42,10 @@ static void free_block(csr_block & B) {
 	cudaFree(B.lcol);
 	cudaFree(B.rp16);
 	cudaFree(B.segs);
+	cudaFree(B.vidx);
+	cudaFree(B.plcol);
+	cudaFree(B.pmeta);
+	cudaFree(B.vdict);
 	B = csr_block{};
 }
 
@@ -65,8 +69,10 @@ static void upload_block(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t
 	if (row_ids)
 		B.row_ids = dev_upload<int32_t>(c, *row_ids);
 	FSB_CUDA(cudaStreamSynchronize(c->stream));
-	if (B.n_rows > 0)
+	if (B.n_rows > 0) {
+		probe_value_dictionary(c, B);
 		build_blocks(c, B, &rowptr);
+	}
 }
 
 // ------------------------------------------------------------------ halo plan (general)
@@ -344,6 +350,7 @@ fsb_parcsr_s * fsb_parcsr_create_impl(fsb_ctx_s * c, int64_t n_global, const int
 		}
 	upload_block(c, A->diag, drp, dcol, dval, nullptr);
 	build_window_format(c, A->diag, A->n_local);
+	build_value_dictionary(c, A->diag);
 	if (!orows.empty())
 		upload_block(c, A->offd, orp, ocol, oval, &orows);
 	if (P > 1)
@@ -630,8 +637,10 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 		stencil_fill_diag_kernel<int><<<grid, T, 0, c->stream>>>(G, static_cast<int *>(D.rowptr), D.col, D.val);
 	FSB_CUDA(cudaGetLastError());
 	D.max_blk_nnz = width; // row width bound for the uniform block builder
+	probe_value_dictionary(c, D);
 	build_blocks(c, D, nullptr);
 	build_window_format(c, D, n);
+	build_value_dictionary(c, D);
 
 	// ---- offd block over the rows that touch a neighbouring slab
 	if (A->n_ghost > 0) {

@@ -26,11 +26,16 @@
 //    (mg/jacobi.hh:73-89: skip the diagonal while summing, x = w/d (b - lpu) + (1-w) tmp) in the same pass.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
+#include <thrust/execution_policy.h>
+#include <thrust/functional.h>
+#include <thrust/reduce.h>
+#include <thrust/scan.h>
 
 #include "fsb_internal.h"
 #include "setup_exchange.h"
@@ -86,6 +91,11 @@ struct spmv_args {
 	int acap; // its capacity per stage when it is staged with the block (aux_mode 1)
 	int aux_mode; // 0 none; 1 staged with the block by a bulk copy; 2 u is x itself: read it from the x window at the
 	              // diagonal's position (CG's <Ap, p>: no extra bytes at all); 3 plain global load
+	// value dictionary (window format of a matrix with <= 256 distinct values): one byte per nonzero instead of eight
+	const uint8_t * vidx; // [padded slots] index into vdict, or nullptr
+	const double * vdict; // [256]
+	const uint16_t * plcol; // [padded slots] local columns in the same padded order
+	const uint16_t * pmeta; // per row block: nrows + 1 slot offsets, nrows row lengths, nrows diagonal positions
 	unsigned long long * tl; // timeline slot of this launch or nullptr
 	setup_exchange * meet; // host side only: rendezvous of the ranks' threads right before the launch (in-process groups)
 };
@@ -502,7 +512,11 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_stream_kernel(const 
 
 // Stage layout: [val 8 cap][x window 8 xcap][u or b 8 acap][local columns 2 cap][row offsets 2 rcap].
 // Same roles as above; the producer additionally stages the block's x segments, so consumers read shared memory only.
-template<int NSTAGE, bool DOT, bool HALO, int JAC>
+// VD ("value dictionary"): the matrix holds at most 256 distinct values (every constant-coefficient stencil, graph
+// Laplacians, ...): the stage carries one byte per nonzero [value index 1 cap] instead of the fp64 value and the
+// consumers look the value up in a 2 KB table in shared memory -- 3 B instead of 10 B of HBM traffic per nonzero, the
+// same doubles multiplied in the same order.
+template<int NSTAGE, bool DOT, bool HALO, int JAC, bool VD>
 __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_window_kernel(const __grid_constant__ spmv_args a) {
 	constexpr int UNROLL = 8;
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -510,7 +524,8 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_window_kernel(const 
 	__shared__ blk_desc sdesc[NSTAGE];
 	__shared__ double scratch[32];
 	__shared__ double srow[HALO ? ROWS_MAX : 1], sdg[(HALO && JAC == 1) ? ROWS_MAX : 1];
-	const size_t off_x = static_cast<size_t>(a.cap) * 8;
+	__shared__ double sdict[VD ? 256 : 1];
+	const size_t off_x = static_cast<size_t>(a.cap) * (VD ? 1 : 8);
 	const size_t off_a = off_x + static_cast<size_t>(a.xcap) * 8;
 	const size_t off_c = off_a + static_cast<size_t>(a.acap) * 8;
 	const size_t off_r = off_c + static_cast<size_t>(a.cap) * 2;
@@ -525,6 +540,10 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_window_kernel(const 
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	if constexpr (VD) {
+		if (tid < 256)
+			sdict[tid] = a.vdict[tid];
 	}
 	__syncthreads();
 	grid_dependency_wait(); // everything above is independent of the previous kernel (programmatic dependent launch)
@@ -564,6 +583,11 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_window_kernel(const 
 			d.o0 = word(dw, 5);
 			d.ocnt = word(dw, 6);
 			d.rp0 = word(dw, 7);
+			if constexpr (VD) {
+				d.zp0 = static_cast<long long>(static_cast<unsigned>(word(dw, 10))) | (static_cast<long long>(word(dw, 11)) << 32);
+				d.pnnz = word(dw, 12);
+				d.rpp0 = word(dw, 13);
+			}
 			// position of every segment inside the staged window: exclusive prefix sum of the lengths
 			int soff = sg.len;
 #pragma unroll
@@ -576,22 +600,29 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_window_kernel(const 
 			soff -= sg.len;
 			const int s = it % NSTAGE;
 			unsigned char * sbase = smem + s * stage_bytes;
-			const long long za = d.z0 & ~7LL; // 16-byte aligned start of the 16-bit stream
-			const long long cnt = ((d.z0 + d.nnz + 7) & ~7LL) - za;
-			const long long ra = d.rp0 & ~7LL;
-			const long long rcnt = ((static_cast<long long>(d.rp0) + 2 * d.nrows + 1 + 7) & ~7LL) - ra;
+			const long long za = VD ? d.zp0 : (d.z0 & ~7LL); // 16-byte aligned start of the per-nonzero streams
+			const long long cnt = VD ? d.pnnz : ((d.z0 + d.nnz + 7) & ~7LL) - za;
+			const long long ra = (VD ? d.rpp0 : d.rp0) & ~7LL;
+			const long long rcnt = ((static_cast<long long>(VD ? d.rpp0 : d.rp0) + (VD ? 3 : 2) * d.nrows + 1 + 7) & ~7LL) - ra;
 			const long long aa = d.r0 & ~1LL; // row-aligned operand: rows [r0, r0 + nrows), 16-byte granular
 			const long long acnt = a.aux_mode == 1 ? ((static_cast<long long>(d.r0) + d.nrows + 1) & ~1LL) - aa : 0;
 			if (lane == 0) {
 				if (it >= NSTAGE)
 					mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
 				sdesc[s] = d;
-				mbar_expect_tx(&full[s], static_cast<uint32_t>(cnt * 10 + rcnt * 2 + (static_cast<long long>(xlen) + acnt) * 8));
+				mbar_expect_tx(&full[s], static_cast<uint32_t>(cnt * (VD ? 3 : 10) + rcnt * 2 + (static_cast<long long>(xlen) + acnt) * 8));
 				if (acnt > 0)
 					tma_load_1d(sbase + off_a, a.aux + aa, static_cast<uint32_t>(acnt * 8), &full[s]);
-				tma_load_1d(sbase, a.val + za, static_cast<uint32_t>(cnt * 8), &full[s]);
-				tma_load_1d(sbase + off_c, a.lcol + za, static_cast<uint32_t>(cnt * 2), &full[s]);
-				tma_load_1d(sbase + off_r, a.rp16 + ra, static_cast<uint32_t>(rcnt * 2), &full[s]);
+				if constexpr (VD) {
+					tma_load_1d(sbase, a.vidx + za, static_cast<uint32_t>(cnt), &full[s]);
+					tma_load_1d(sbase + off_c, a.plcol + za, static_cast<uint32_t>(cnt * 2), &full[s]);
+					tma_load_1d(sbase + off_r, a.pmeta + ra, static_cast<uint32_t>(rcnt * 2), &full[s]);
+				}
+				else {
+					tma_load_1d(sbase, a.val + za, static_cast<uint32_t>(cnt * 8), &full[s]);
+					tma_load_1d(sbase + off_c, a.lcol + za, static_cast<uint32_t>(cnt * 2), &full[s]);
+					tma_load_1d(sbase + off_r, a.rp16 + ra, static_cast<uint32_t>(rcnt * 2), &full[s]);
+				}
 			}
 			__syncwarp();
 			if (lane < WIN_MAXSEG && sg.len > 0) // one bulk copy per segment, issued by the lane that holds it
@@ -629,36 +660,67 @@ __global__ void __launch_bounds__(SPMV_MAX_THREADS, 2) spmv_window_kernel(const 
 			if (d.nrows < 0)
 				break;
 			const unsigned char * base = smem + s * stage_bytes;
-			const long long za = d.z0 & ~7LL;
-			const double * sv = reinterpret_cast<const double *>(base) + (d.z0 - za);
 			const double * xs = reinterpret_cast<const double *>(base + off_x);
 			const double * sa = reinterpret_cast<const double *>(base + off_a) + (d.r0 & 1);
 			const int aux_mode = a.aux_mode;
-			const uint16_t * sl = reinterpret_cast<const uint16_t *>(base + off_c) + (d.z0 - za);
-			const uint16_t * srp = reinterpret_cast<const uint16_t *>(base + off_r) + (d.rp0 & 7);
 			const int r0 = d.r0, nrows = d.nrows;
 			const bool boundary = HALO && d.ocnt > 0;
-			const uint16_t * sdk = srp + nrows + 1; // position of the diagonal entry inside each row (or WIN_NO_DIAG)
+			// plain stream: values, local columns and row offsets as the matrix has them
+			const long long za = d.z0 & ~7LL;
+			const double * sv = reinterpret_cast<const double *>(base) + (d.z0 - za);
+			const uint16_t * sl = reinterpret_cast<const uint16_t *>(base + off_c) + (VD ? 0 : d.z0 - za);
+			const uint16_t * srp = reinterpret_cast<const uint16_t *>(base + off_r) + ((VD ? d.rpp0 : d.rp0) & 7);
+			// dictionary stream: rows start at multiples of 8 slots, so a trip of 8 nonzeros is one 8-byte load of value
+			// indices and one 16-byte load of local columns
+			const uint8_t * sv8 = base;
+			const uint16_t * slen = srp + nrows + 1; // (VD) nonzeros of each row
+			const uint16_t * sdk = VD ? slen + nrows : srp + nrows + 1; // position of the diagonal entry inside each row (or WIN_NO_DIAG)
 			for (int i = ctid; i < nrows; i += nconsumers) {
-				const int p0 = srp[i], p1 = srp[i + 1];
+				const int p0 = srp[i];
+				const int p1 = VD ? p0 + static_cast<int>(slen[i]) : static_cast<int>(srp[i + 1]);
 				const unsigned dk = sdk[i];
 				const int pd = dk != WIN_NO_DIAG ? p0 + static_cast<int>(dk) : -1; // the row's diagonal entry
 				const bool have_diag = pd >= 0;
 				double sum = 0.0, dg = 0.0, xold = 0.0;
-				for (int p = p0; p < p1; p += UNROLL) {
-					double prod[UNROLL];
+				if constexpr (VD) {
+					for (int p = p0; p < p1; p += UNROLL) {
+						const uint2 iv = *reinterpret_cast<const uint2 *>(sv8 + p);
+						const uint4 cv = *reinterpret_cast<const uint4 *>(sl + p);
+						const unsigned cw[4] = {cv.x, cv.y, cv.z, cv.w};
+						double prod[UNROLL];
 #pragma unroll
-					for (int k = 0; k < UNROLL; ++k)
-						if (p + k < p1 && (JAC == 0 || p + k != pd)) // a Jacobi sweep leaves the diagonal out of the sum
-							prod[k] = __dmul_rn(sv[p + k], xs[sl[p + k]]);
+						for (int k = 0; k < UNROLL; ++k) { // padding slots hold index 0 / column 0 and are dropped below
+							const unsigned vi = ((k < 4 ? iv.x : iv.y) >> (8 * (k & 3))) & 0xffu;
+							const unsigned lc = (cw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+							prod[k] = __dmul_rn(sdict[vi], xs[lc]);
+						}
 #pragma unroll
-					for (int k = 0; k < UNROLL; ++k)
-						if (p + k < p1 && (JAC == 0 || p + k != pd))
-							sum = __dadd_rn(sum, prod[k]);
+						for (int k = 0; k < UNROLL; ++k) {
+							const bool keep = p + k < p1 && (JAC == 0 || p + k != pd); // a Jacobi sweep leaves the diagonal out
+							const double t = __dadd_rn(sum, prod[k]);
+							sum = keep ? t : sum;
+						}
+					}
+				}
+				else {
+					for (int p = p0; p < p1; p += UNROLL) {
+						double prod[UNROLL];
+#pragma unroll
+						for (int k = 0; k < UNROLL; ++k)
+							if (p + k < p1 && (JAC == 0 || p + k != pd)) // a Jacobi sweep leaves the diagonal out of the sum
+								prod[k] = __dmul_rn(sv[p + k], xs[sl[p + k]]);
+#pragma unroll
+						for (int k = 0; k < UNROLL; ++k)
+							if (p + k < p1 && (JAC == 0 || p + k != pd))
+								sum = __dadd_rn(sum, prod[k]);
+					}
 				}
 				if ((JAC != 0 || aux_mode == 2) && have_diag) { // x[row] sits in the window where the diagonal entry points
 					xold = xs[sl[pd]];
-					dg = sv[pd];
+					if constexpr (VD)
+						dg = sdict[sv8[pd]];
+					else
+						dg = sv[pd];
 				}
 				double auxv = 0.0;
 				if (aux_mode == 1)
@@ -880,24 +942,31 @@ static int env_int(const char * name, int dflt) {
 	return v ? std::atoi(v) : dflt;
 }
 
-static spmv_config configure(const fsb_ctx_s * c, const csr_block & B, bool window, bool staged_operand) {
+static spmv_config configure(const fsb_ctx_s * c, const csr_block & B, bool window, bool staged_operand, bool vd = false) {
 	static const int env_stages = env_int("FSB_SPMV_STAGES", 0);
 	static const int env_threads = env_int("FSB_SPMV_THREADS", 0);
 	static const int env_ctas = env_int("FSB_SPMV_CTAS_PER_SM", 0);
 	spmv_config k{};
 	k.cap = ((B.max_blk_nnz + 16 + 7) / 8) * 8; // + alignment slack on both ends
+	if (vd)
+		k.cap = B.max_blk_pnnz; // the padded stream: every block starts and ends on a 16-slot boundary
 	if (k.cap < 64)
 		k.cap = 64;
-	k.rcap = (((window ? 2 : 1) * B.max_blk_rows + 1 + 16 + 7) / 8) * 8;
+	k.rcap = (((vd ? 3 : window ? 2 : 1) * B.max_blk_rows + 1 + 16 + 7) / 8) * 8;
 	k.xcap = window ? ((B.win_xcap + 7) / 8) * 8 : 0;
 	k.acap = (window && staged_operand) ? ((B.max_blk_rows + 2 + 7) / 8) * 8 : 0;
-	const size_t stage_bytes = window ? static_cast<size_t>(k.cap) * 10 + static_cast<size_t>(k.xcap + k.acap) * 8 + static_cast<size_t>(k.rcap) * 2
+	const size_t stage_bytes = window ? static_cast<size_t>(k.cap) * (vd ? 3 : 10) + static_cast<size_t>(k.xcap + k.acap) * 8 + static_cast<size_t>(k.rcap) * 2
 	                                  : static_cast<size_t>(k.cap) * 12 + static_cast<size_t>(k.rcap) * (B.wide ? 8 : 4);
 	// consumer threads: one per row of a block, at most 512
 	int consumers = env_threads > 0 ? env_threads : (c->spmv_threads > 0 ? c->spmv_threads : 512);
 	consumers = std::min(consumers, 512);
 	while (consumers > 64 && consumers / 2 >= B.max_blk_rows)
 		consumers /= 2;
+	// dictionary stream: the pass is latency-bound (bytes in flight), not HBM-bound: short rows run two per thread, which
+	// leaves room for a third resident CTA (measured: 0.153 ms against 0.203 ms on 7-pt 256^3)
+	if (vd && env_threads <= 0 && c->spmv_threads <= 0 && B.max_blk_rows > 0 && B.max_blk_nnz / B.max_blk_rows < 16)
+		while (consumers > 64 && consumers >= B.max_blk_rows)
+			consumers /= 2;
 	k.threads = consumers + 32;
 	// Measured on B200 (profiles/r1_spmv_sweep.txt): throughput follows the number of resident
 	// consumer threads (>= 1024 per SM saturates HBM); a second stage only pays when it does not
@@ -1024,10 +1093,11 @@ static int launch_stream(const spmv_args & a, const spmv_config & k, const spmv_
 #undef FSB_SPMV_LAUNCH
 }
 
-template<int NSTAGE>
+template<int NSTAGE, bool VD>
 static int launch_window(const spmv_args & a, const spmv_config & k, const spmv_call & call, cudaStream_t s) {
 	const bool dot = call.dot_u != nullptr, halo = a.halo != nullptr;
-#define FSB_SPMV_LAUNCH(DOT, HALO, JAC) return launch_kernel(spmv_window_kernel<NSTAGE, DOT, HALO, JAC>, a, k, s, "window")
+#define FSB_SPMV_LAUNCH(DOT, HALO, JAC) \
+	return launch_kernel(spmv_window_kernel<NSTAGE, DOT, HALO, JAC, VD>, a, k, s, VD ? "window+dictionary" : "window")
 	if (call.jacobi == 1) {
 		if (halo)
 			FSB_SPMV_LAUNCH(false, true, 1);
@@ -1059,9 +1129,11 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const spmv_call & call, cuda
 	int aux_mode = aux ? 1 : 0;
 	if (aux && call.jacobi == 0 && aux == call.x)
 		aux_mode = 2;
-	spmv_config k = configure(c, B, window, aux_mode == 1);
+	static const bool dict_allowed = env_int("FSB_SPMV_DICT", 1) != 0;
+	const bool vd = window && B.vidx != nullptr && dict_allowed && c->spmv_dictionary;
+	spmv_config k = configure(c, B, window, aux_mode == 1, vd);
 	if (aux_mode == 1) {
-		const spmv_config lean = configure(c, B, window, false);
+		const spmv_config lean = configure(c, B, window, false, vd);
 		const size_t per_sm = 227 * 1024;
 		if (per_sm / (lean.smem + 1536) > per_sm / (k.smem + 1536) || lean.nstage > k.nstage) {
 			k = lean;
@@ -1097,6 +1169,10 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const spmv_call & call, cuda
 	a.jb = call.jacobi_b;
 	a.omega = call.omega;
 	a.lcol = B.lcol;
+	a.vidx = vd ? B.vidx : nullptr;
+	a.vdict = B.vdict;
+	a.plcol = B.plcol;
+	a.pmeta = B.pmeta;
 	a.rp16 = B.rp16;
 	a.segs = static_cast<const x_segment *>(B.segs);
 	if (call.halo) {
@@ -1127,11 +1203,16 @@ int launch_spmv(fsb_ctx_s * c, const csr_block & B, const spmv_call & call, cuda
 		c->prof_tag[c->prof_used / 2] = rowlist ? 1 : 0;
 	}
 	int grid;
-	if (window)
-		grid = k.nstage >= 4   ? launch_window<4>(a, k, call, s)
-		       : k.nstage == 3 ? launch_window<3>(a, k, call, s)
-		       : k.nstage == 2 ? launch_window<2>(a, k, call, s)
-		                       : launch_window<1>(a, k, call, s);
+	if (window && vd)
+		grid = k.nstage >= 4   ? launch_window<4, true>(a, k, call, s)
+		       : k.nstage == 3 ? launch_window<3, true>(a, k, call, s)
+		       : k.nstage == 2 ? launch_window<2, true>(a, k, call, s)
+		                       : launch_window<1, true>(a, k, call, s);
+	else if (window)
+		grid = k.nstage >= 4   ? launch_window<4, false>(a, k, call, s)
+		       : k.nstage == 3 ? launch_window<3, false>(a, k, call, s)
+		       : k.nstage == 2 ? launch_window<2, false>(a, k, call, s)
+		                       : launch_window<1, false>(a, k, call, s);
 	else if (B.wide)
 		grid = k.nstage >= 2 ? launch_stream<long long, 2>(a, k, call, rowlist, s) : launch_stream<long long, 1>(a, k, call, rowlist, s);
 	else
@@ -1204,7 +1285,16 @@ void build_blocks(fsb_ctx_s * c, csr_block & B, const std::vector<int64_t> * hos
 		// wide rows are headed for the window format, which runs best with ~17 KB stages, two per CTA and five CTAs per
 		// SM (27-point: 64 rows; measured in profiles/r2_spmv_window_sweep.txt); short rows keep 512-row blocks
 		if (env_int("FSB_SPMV_WINDOW", 1) != 0 && !B.row_ids) {
-			if (width >= 16)
+			if (!B.dict_keys.empty()) {
+				// dictionary stream (3 B per slot, rows padded to 8 slots): a stage is mostly x window, which costs less per
+				// row the more rows a block has -- 4096 slots per block (profiles/r2_spmv_dictionary_sweep.txt)
+				rows = std::max(32, std::min(ROWS_MAX, 4096 / ((width + 7) / 8 * 8)));
+				int p2 = 32;
+				while (p2 * 2 <= rows)
+					p2 *= 2;
+				rows = p2;
+			}
+			else if (width >= 16)
 				rows = std::min(rows, 64);
 			else if (rows == ROWS_MAX)
 				rows = 448; // two stages of a 7-point block + its x segments, two CTAs per SM, in every kernel variant
@@ -1286,6 +1376,231 @@ void build_window_format(fsb_ctx_s * c, csr_block & B, int64_t n_cols) {
 	B.win_xcap = h[1];
 	if (std::getenv("FSB_SPMV_DEBUG"))
 		fprintf(stderr, "[fsb] window format: %d blocks, <= %d x entries staged per block (limit %d)\n", B.n_blk, h[1], xcap_limit);
+}
+
+// ------------------------------------------------------------------------------------------------ value dictionary
+
+constexpr unsigned DICT_SLOTS = 4096; // open-addressing table of value bit patterns; gives up beyond 256 distinct ones
+constexpr unsigned long long DICT_EMPTY = ~0ULL; // (a NaN pattern; a matrix that holds it gets no dictionary)
+
+// state[0] = distinct values seen, state[1] = 1: more than 256 (or the table cannot hold them): no dictionary
+__global__ void __launch_bounds__(256) collect_values_kernel(const double * __restrict__ val, long long nnz, unsigned long long * table,
+                                                            int * state) {
+	volatile int * given_up = state + 1;
+	unsigned long long last = DICT_EMPTY;
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	int trips = 0;
+	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+		if ((++trips & 63) == 0 && *given_up)
+			return;
+		const unsigned long long key = static_cast<unsigned long long>(__double_as_longlong(val[i]));
+		if (key == last)
+			continue;
+		last = key;
+		if (key == DICT_EMPTY || *given_up) {
+			*given_up = 1;
+			return;
+		}
+		unsigned h = static_cast<unsigned>((key * 0x9E3779B97F4A7C15ULL) >> 40) & (DICT_SLOTS - 1);
+		for (unsigned probes = 0;; ++probes) {
+			if (probes >= DICT_SLOTS) {
+				*given_up = 1;
+				return;
+			}
+			const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(table + h);
+			if (cur == key)
+				break;
+			if (cur == DICT_EMPTY) {
+				const unsigned long long prev = atomicCAS(table + h, DICT_EMPTY, key);
+				if (prev == DICT_EMPTY) {
+					if (atomicAdd(state, 1) + 1 > 256)
+						*given_up = 1;
+					break;
+				}
+				if (prev == key)
+					break;
+			}
+			h = (h + 1) & (DICT_SLOTS - 1);
+		}
+	}
+}
+
+// slots of every row block in the dictionary stream: rows padded to multiples of 8, blocks to multiples of 16
+template<class OffT>
+__global__ void padded_sizes_kernel(const OffT * __restrict__ rowptr, const int32_t * __restrict__ blk_row, int n_blk,
+                                    long long * __restrict__ slots) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_blk)
+		return;
+	long long t = 0;
+	for (int r = blk_row[b]; r < blk_row[b + 1]; ++r)
+		t += (static_cast<long long>(rowptr[r + 1]) - static_cast<long long>(rowptr[r]) + 7) & ~7LL;
+	slots[b] = (t + 15) & ~15LL;
+}
+
+// The dictionary stream of one row block per CTA: value index (position of val[q] among the sorted distinct bit patterns)
+// and local column of every nonzero, each row starting at a multiple of 8 slots (padding: index 0, column 0), and the
+// block's row meta [nrows + 1 slot offsets | nrows row lengths | nrows diagonal positions].
+template<class OffT>
+__global__ void __launch_bounds__(256) build_padded_kernel(const OffT * __restrict__ rowptr, const int32_t * __restrict__ blk_row,
+                                                          const double * __restrict__ val, const uint16_t * __restrict__ lcol,
+                                                          const uint16_t * __restrict__ rp16, const unsigned long long * __restrict__ keys,
+                                                          int n_keys, const long long * __restrict__ zp0,
+                                                          const long long * __restrict__ slots, blk_desc * __restrict__ desc,
+                                                          uint8_t * __restrict__ pidx, uint16_t * __restrict__ plcol,
+                                                          uint16_t * __restrict__ pmeta) {
+	using Scan = cub::BlockScan<int, 256>;
+	__shared__ typename Scan::TempStorage tmp;
+	__shared__ unsigned long long sk[256];
+	const int b = blockIdx.x, tid = threadIdx.x;
+	const int r0 = blk_row[b], nrows = blk_row[b + 1] - r0;
+	sk[tid] = tid < n_keys ? keys[tid] : DICT_EMPTY;
+	uint16_t * meta = pmeta + 3 * static_cast<size_t>(r0) + b;
+	const uint16_t * old_diag = rp16 + 2 * static_cast<size_t>(r0) + b + nrows + 1;
+	long long q0[2] = {0, 0};
+	int len[2] = {0, 0}, plen[2] = {0, 0}, off[2] = {0, 0};
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		const int i = 2 * tid + k;
+		if (i < nrows) {
+			q0[k] = static_cast<long long>(rowptr[r0 + i]);
+			len[k] = static_cast<int>(static_cast<long long>(rowptr[r0 + i + 1]) - q0[k]);
+			plen[k] = (len[k] + 7) & ~7;
+		}
+	}
+	int total = 0;
+	Scan(tmp).ExclusiveSum(plen, off, total);
+	__syncthreads(); // sk
+	const long long z = zp0[b];
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		const int i = 2 * tid + k;
+		if (i >= nrows)
+			continue;
+		meta[i] = static_cast<uint16_t>(off[k]);
+		meta[nrows + 1 + i] = static_cast<uint16_t>(len[k]);
+		meta[2 * nrows + 1 + i] = old_diag[i];
+		for (int j = 0; j < plen[k]; ++j) {
+			unsigned vi = 0, lc = 0;
+			if (j < len[k]) {
+				const unsigned long long key = static_cast<unsigned long long>(__double_as_longlong(val[q0[k] + j]));
+				int lo = 0, hi = n_keys - 1;
+				while (lo < hi) {
+					const int mid = (lo + hi) >> 1;
+					if (sk[mid] < key)
+						lo = mid + 1;
+					else
+						hi = mid;
+				}
+				vi = static_cast<unsigned>(lo);
+				lc = lcol[q0[k] + j];
+			}
+			pidx[z + off[k] + j] = static_cast<uint8_t>(vi);
+			plcol[z + off[k] + j] = static_cast<uint16_t>(lc);
+		}
+	}
+	const int padded = static_cast<int>(slots[b]);
+	for (int j = total + tid; j < padded; j += 256) {
+		pidx[z + j] = 0;
+		plcol[z + j] = 0;
+	}
+	if (tid == 0) {
+		meta[nrows] = static_cast<uint16_t>(total);
+		desc[b].zp0 = z;
+		desc[b].pnnz = padded;
+		desc[b].rpp0 = 3 * r0 + b;
+	}
+}
+
+// Does the block hold at most 256 distinct values?  Called right after the values are on the device and BEFORE the row
+// blocks are cut (build_blocks sizes them for the stream the kernel will read): leaves the sorted bit patterns in
+// B.dict_keys, or nothing.  Distinct = distinct bit patterns, so -0.0, NaN payloads and denormals survive: the kernel
+// multiplies exactly the doubles the matrix holds.
+void probe_value_dictionary(fsb_ctx_s * c, csr_block & B) {
+	B.dict_keys.clear();
+	if (B.nnz == 0 || B.row_ids || !c->spmv_dictionary || env_int("FSB_SPMV_DICT", 1) == 0 || env_int("FSB_SPMV_WINDOW", 1) == 0)
+		return;
+	unsigned long long * table = nullptr;
+	int * state = nullptr;
+	FSB_CUDA(cudaMalloc(&table, DICT_SLOTS * sizeof(unsigned long long)));
+	FSB_CUDA(cudaMalloc(&state, 2 * sizeof(int)));
+	FSB_CUDA(cudaMemsetAsync(table, 0xff, DICT_SLOTS * sizeof(unsigned long long), c->stream));
+	FSB_CUDA(cudaMemsetAsync(state, 0, 2 * sizeof(int), c->stream));
+	const int grid = static_cast<int>(std::min<long long>((B.nnz + 255) / 256, SM_COUNT * 8LL));
+	collect_values_kernel<<<grid, 256, 0, c->stream>>>(B.val, B.nnz, table, state);
+	FSB_CUDA(cudaGetLastError());
+	std::vector<unsigned long long> h(DICT_SLOTS);
+	int hs[2] = {0, 0};
+	FSB_CUDA(cudaMemcpyAsync(h.data(), table, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaMemcpyAsync(hs, state, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(state);
+	cudaFree(table);
+	std::vector<unsigned long long> keys;
+	for (unsigned long long k : h)
+		if (k != DICT_EMPTY)
+			keys.push_back(k);
+	if (hs[1] != 0 || keys.empty() || keys.size() > 256)
+		return;
+	std::sort(keys.begin(), keys.end());
+	B.dict_keys = keys;
+}
+
+// A block in the window format whose values are at most 256 distinct doubles (probe_value_dictionary) also gets the
+// dictionary stream: one byte (value index) + 16-bit local column per nonzero (spmv_window_kernel<..., VD = true>).
+// Call after build_window_format and before attach_offd_rows (the descriptors are still in row order).
+void build_value_dictionary(fsb_ctx_s * c, csr_block & B) {
+	const std::vector<unsigned long long> keys = B.dict_keys;
+	if (!B.lcol || B.nnz == 0 || B.max_blk_rows > 512 || keys.empty())
+		return;
+	unsigned long long * table = nullptr;
+	FSB_CUDA(cudaMalloc(&table, 256 * sizeof(unsigned long long)));
+	std::vector<double> dict(256, 0.0);
+	std::memcpy(dict.data(), keys.data(), keys.size() * sizeof(double));
+	FSB_CUDA(cudaMemcpyAsync(table, keys.data(), keys.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+	FSB_CUDA(cudaMalloc(&B.vdict, 256 * sizeof(double)));
+	FSB_CUDA(cudaMemcpyAsync(B.vdict, dict.data(), 256 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	// where every row block starts in the padded stream
+	long long *slots = nullptr, *zp0 = nullptr;
+	FSB_CUDA(cudaMalloc(&slots, static_cast<size_t>(B.n_blk) * sizeof(long long)));
+	FSB_CUDA(cudaMalloc(&zp0, static_cast<size_t>(B.n_blk) * sizeof(long long)));
+	if (B.wide)
+		padded_sizes_kernel<long long><<<(B.n_blk + 255) / 256, 256, 0, c->stream>>>(static_cast<const long long *>(B.rowptr), B.blk_row,
+		                                                                              B.n_blk, slots);
+	else
+		padded_sizes_kernel<int><<<(B.n_blk + 255) / 256, 256, 0, c->stream>>>(static_cast<const int *>(B.rowptr), B.blk_row, B.n_blk, slots);
+	FSB_CUDA(cudaGetLastError());
+	const auto pol = thrust::cuda::par.on(c->stream);
+	thrust::exclusive_scan(pol, slots, slots + B.n_blk, zp0);
+	const long long most = thrust::reduce(pol, slots, slots + B.n_blk, 0LL, thrust::maximum<long long>());
+	long long last[2] = {0, 0};
+	FSB_CUDA(cudaMemcpyAsync(&last[0], zp0 + B.n_blk - 1, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaMemcpyAsync(&last[1], slots + B.n_blk - 1, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	const long long total = last[0] + last[1];
+	FSB_CUDA(cudaMalloc(&B.vidx, static_cast<size_t>(total) + 64));
+	FSB_CUDA(cudaMalloc(&B.plcol, (static_cast<size_t>(total) + 64) * sizeof(uint16_t)));
+	FSB_CUDA(cudaMalloc(&B.pmeta, (3 * static_cast<size_t>(B.n_rows) + B.n_blk + 32) * sizeof(uint16_t)));
+	auto * desc = static_cast<blk_desc *>(B.blk_desc);
+	if (B.wide)
+		build_padded_kernel<long long><<<B.n_blk, 256, 0, c->stream>>>(static_cast<const long long *>(B.rowptr), B.blk_row, B.val, B.lcol,
+		                                                               B.rp16, table, static_cast<int>(keys.size()), zp0, slots, desc,
+		                                                               B.vidx, B.plcol, B.pmeta);
+	else
+		build_padded_kernel<int><<<B.n_blk, 256, 0, c->stream>>>(static_cast<const int *>(B.rowptr), B.blk_row, B.val, B.lcol, B.rp16, table,
+		                                                         static_cast<int>(keys.size()), zp0, slots, desc, B.vidx, B.plcol,
+		                                                         B.pmeta);
+	FSB_CUDA(cudaGetLastError());
+	FSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(table);
+	cudaFree(slots);
+	cudaFree(zp0);
+	B.n_dict = static_cast<int>(keys.size());
+	B.max_blk_pnnz = static_cast<int>(most);
+	B.dict_slots = total;
+	if (std::getenv("FSB_SPMV_DEBUG"))
+		fprintf(stderr, "[fsb] value dictionary: %d distinct values; %lld slots for %lld nonzeros (3 B each), <= %d per row block\n",
+		        B.n_dict, total, static_cast<long long>(B.nnz), B.max_blk_pnnz);
 }
 
 // Fused ghost exchange: tell every row block of the owned-column block which rows of the off-process block it owns,

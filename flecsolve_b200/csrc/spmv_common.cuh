@@ -60,8 +60,12 @@ struct blk_desc {
 	int rp0; // window format: where the block's 16-bit row offsets start in rp16[]
 	int seg_slot; // window format: where the block's WIN_MAXSEG segment slots start in segs[]
 	int pad;
+	// value-dictionary stream (spmv.cu: build_value_dictionary): every row padded to a multiple of 8 slots
+	long long zp0; // first slot of the block (multiple of 16)
+	int pnnz; // slots of the block (multiple of 16)
+	int rpp0; // where the block's row meta starts in pmeta[]: nrows + 1 slot offsets, nrows lengths, nrows diagonal positions
 };
-static_assert(sizeof(blk_desc) == 40, "descriptor layout");
+static_assert(sizeof(blk_desc) == 56, "descriptor layout");
 
 // window format: a contiguous piece of x that a row block reads, staged in shared memory by one bulk copy
 struct x_segment {

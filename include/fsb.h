@@ -64,6 +64,10 @@ enum fsb_option {
 	                   the fallback when libnvrtc is not available; 0 (or FSB_JIT=0 in the environment): never compile */
 	,
 	FSB_OPT_TIMELINE = 7 /* n > 0: keep a device-side timeline of the next n kernel launches (fsb_ctx_timeline_read); 0: off */
+	,
+	FSB_OPT_SPMV_DICTIONARY = 8 /* 1 (default): y = A x of a matrix with at most 256 distinct values streams a one-byte value
+	                               index per nonzero instead of the fp64 value (FSB_INFO_VALUE_DICTIONARY; same doubles, same
+	                               order, same bits); 0 (or FSB_SPMV_DICT=0 in the environment): always stream the values */
 };
 
 enum fsb_stat {
@@ -315,13 +319,19 @@ int64_t fsb_parcsr_local_nnz(fsb_parcsr_t A, int which /* 0 diag, 1 offd */);
  *   FSB_INFO_ROW_BLOCKS     row blocks (units of work of the SpMV pipeline) of the owned-column block
  *   FSB_INFO_WINDOW_X       x entries the largest row block stages (window format)
  *   FSB_INFO_FUSED_HALO     1 when y = A x is ONE launch that also does the ghost exchange over peer memory
- *   FSB_INFO_WIDE_OFFSETS   1 when row offsets are 64-bit (local nnz >= 2^31)                                 */
+ *   FSB_INFO_WIDE_OFFSETS   1 when row offsets are 64-bit (local nnz >= 2^31)
+ *   FSB_INFO_VALUE_DICTIONARY  number of distinct values of the owned-column block when there are at most 256 of them
+ *                           and the block has the window format -- the SpMV then streams 3 B per slot (one-byte value
+ *                           index + 16-bit position; rows padded to multiples of 8 slots, FSB_INFO_DICTIONARY_SLOTS)
+ *                           instead of 10 B per nonzero; 0 otherwise                                                */
 enum fsb_parcsr_info_key {
 	FSB_INFO_WINDOW_FORMAT = 0,
 	FSB_INFO_ROW_BLOCKS = 1,
 	FSB_INFO_WINDOW_X = 2,
 	FSB_INFO_FUSED_HALO = 3,
-	FSB_INFO_WIDE_OFFSETS = 4
+	FSB_INFO_WIDE_OFFSETS = 4,
+	FSB_INFO_VALUE_DICTIONARY = 5,
+	FSB_INFO_DICTIONARY_SLOTS = 6 /* slots of the dictionary stream: nonzeros + the padding of every row to a multiple of 8 */
 };
 int64_t fsb_parcsr_info(fsb_parcsr_t A, int key);
 /* copy the split representation back to the host (tests: compare with the

@@ -103,6 +103,8 @@ def stencil_csr(kind: int, nx: int, ny: int, nz: int = 1, diag_shift: float = 0.
 
 def csr_spmv(rowptr, col, val, x) -> np.ndarray:
     y = np.zeros(len(rowptr) - 1)
+    rowptr, col = np.ascontiguousarray(rowptr, dtype=np.int64), np.ascontiguousarray(col, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float64)
     lib().orc_csr_spmv(len(rowptr) - 1, _i(rowptr), _i(col), _d(val), _d(np.ascontiguousarray(x, dtype=np.float64)), _d(y))
     return y
 

@@ -38,7 +38,7 @@ def launches(src, dst, title):
     return agg
 
 
-def full(reps, dst, title):
+def full(reps, dst, title, key="spmv_stream"):
     out = [title]
     first = {}
     for rep in reps:
@@ -53,7 +53,7 @@ def full(reps, dst, title):
             for w in WANT:
                 if w in idx:
                     out.append(f"  {w:84s} {row[idx[w]]} {units[idx[w]]}")
-            if "spmv_stream" in name and "spmv" not in first:
+            if key in name and "spmv" not in first:
                 def gb(key):
                     v, u = float(row[idx[key]]), units[idx[key]]
                     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
@@ -66,7 +66,37 @@ def full(reps, dst, title):
     return first
 
 
+def round2():
+    """round 2: scripts/gpu/r2_final.sh left r2_launches.csv, r2_final_{spmv7,ew,spmv27_512}.ncu-rep, r2_bench_*.json"""
+    import shutil
+    launches(os.path.join(G, "r2_launches.csv"), os.path.join(P, "r2_launches_cg_poisson7_256.txt"),
+             "# round 2: ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 300, python bench.py --steps 20 --warmup 5 "
+             "--no-cpu-baseline --no-extra-workloads --repeats 1\n# (7-pt 256^3 Jacobi-CG; the window covers the CG flavours "
+             "bench.py times: op::cg, cg_device, cg_sr)")
+    f = full([os.path.join(G, "r2_final_spmv7.ncu-rep"), os.path.join(G, "r2_final_spmv27_512.ncu-rep"),
+              os.path.join(G, "r2_final_ew.ncu-rep")], os.path.join(P, "r2_ncu_full_summary.txt"),
+             "# round 2: ncu --set full --clock-control none --import-source on; spmv_window_kernel inside bench.py (7-pt 256^3, "
+             "fused <Ap,p>), the same kernel on 27-pt 512^3 (scripts/gpu/spmv_sweep.py 27 512 512 dotx), CG's element-wise kernels",
+             key="spmv_window")
+    if "spmv" in f:
+        s = f["spmv"]
+        s["algorithmic_bytes_per_launch"] = 12 * 117047296 + 4 * (16777216 + 1) + 16 * 16777216
+        s["format_bytes_per_launch"] = 1506092180
+        s["traffic_over_algorithmic"] = s["dram_bytes_per_launch"] / s["algorithmic_bytes_per_launch"]
+        s["traffic_over_format"] = s["dram_bytes_per_launch"] / s["format_bytes_per_launch"]
+        json.dump(s, open(os.path.join(P, "r2_spmv_ncu_summary.json"), "w"), indent=1)
+        print(s)
+    for name in ("r2_bench_n1.json", "r2_bench_ref.json", "r2_bench_n8.json", "r2_n2_bench.json"):
+        src = os.path.join(G, name)
+        if os.path.exists(src):
+            lines = [l for l in open(src).read().splitlines() if l.startswith("{")]
+            if lines:
+                json.dump(json.loads(lines[-1]), open(os.path.join(P, name.replace("r2_n2_bench", "r2_bench_n2")), "w"), indent=1)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "r2":
+        return round2()
     launches(os.path.join(G, "launches_r1.csv"), os.path.join(P, "r1_launches_cg_poisson7_256.txt"),
              "# round 1: ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 260, python bench.py --steps 20 --warmup 5\n"
              "# (7-pt 256^3 Jacobi-CG; the window covers both CG flavours bench.py times: op::cg = spmv + p_cg_update + "

@@ -290,6 +290,69 @@ def test_window_format_general_matrices(ctx):
     xv.destroy(); yv.destroy(); A.destroy()
 
 
+@pytest.mark.parametrize("kind,dims", [(7, (19, 17, 23)), (27, (12, 9, 10)), (5, (40, 37, 1))])
+@pytest.mark.parametrize("distinct", [1, 2, 3, 255, 256, 257, 5000])
+def test_value_dictionary_bit_exact(ctx, kind, dims, distinct):
+    """matrices with at most 256 distinct values stream one byte per nonzero (spmv_window_kernel<..., VD>): the same bits
+    as the reference's row loop -- plain, with the fused dots and in a Jacobi sweep -- with -0.0, denormals and huge values
+    in the table; 257 distinct values and more keep the fp64 stream; switching the option off changes nothing"""
+    rp, col, val = O.stencil_csr(kind, *dims)
+    n = len(rp) - 1
+    rng = np.random.default_rng(distinct + kind)
+    table = rng.standard_normal(distinct) * 10.0 ** rng.integers(-3, 4, distinct)
+    if distinct >= 3:
+        table[:3] = [-0.0, 5e-324, 1e300]
+    pick = rng.integers(0, distinct, val.size)
+    pick[:distinct] = np.arange(distinct)  # every entry of the table occurs
+    val = table[pick]
+    diag = np.flatnonzero(col == np.repeat(np.arange(n), np.diff(rp)))
+    val[diag] = np.where(np.abs(val[diag]) < 1e-200, 3.0, val[diag])  # Jacobi divides by the diagonal
+    expected = len(np.unique(val.view(np.uint64)))
+    M = O.ParCSR(rp, col, val, colours=1)
+    A = F.ParCSR.from_csr(ctx, n, [0, n], rp, col, val)
+    assert A.info("window_format") == 1
+    assert A.info("value_dictionary") == (expected if expected <= 256 else 0)
+    x = rng.standard_normal(n)
+    ref = O.csr_spmv(rp, col, val, x)
+    xv, yv, uv = A.vector(x), A.vector(), A.vector(rng.standard_normal(n))
+    w = float(np.float32(2 / 3))
+    b = rng.standard_normal(n)
+    refj = M.jacobi_relax(w, 2, b, x)
+    for dictionary in (1, 0):
+        ctx.set_option("spmv_dictionary", dictionary)
+        A.spmv(xv, yv)
+        assert np.array_equal(yv.download().view(np.uint64), ref.view(np.uint64))
+        A.spmv(xv, yv)
+        t = yv.dot_token(xv)  # CG's <Ap, p>: the operand comes out of the staged x window
+        assert abs(ctx.get(t) - ref @ x) <= 1e-12 * (np.abs(ref) @ np.abs(x))
+        A.spmv(xv, yv)
+        t = yv.dot_token(uv)
+        assert abs(ctx.get(t) - ref @ uv.download()) <= 1e-12 * (np.abs(ref) @ np.abs(uv.download()))
+        bv, xj, tv = A.vector(b), A.vector(x), A.vector()
+        A.jacobi_relax(w, 2, bv, xj, tv)
+        assert np.array_equal(xj.download(), refj, equal_nan=True)
+        for v in (bv, xj, tv):
+            v.destroy()
+    ctx.set_option("spmv_dictionary", 1)
+    for v in (xv, yv, uv):
+        v.destroy()
+    A.destroy()
+
+
+def test_value_dictionary_of_the_generated_operators(ctx):
+    """the device generator's constant-coefficient stencils have 2 distinct values (3 with a diagonal shift)"""
+    for kind, shift, want in ((7, 0.0, 2), (27, 0.0, 2), (7, 1e-3, 2), (107, 1e-3, None)):
+        A = F.ParCSR.stencil(ctx, kind, 20, 18, 22, shift, 1.0)
+        got = A.info("value_dictionary")
+        rp, col, val = A.download(0)
+        assert got == len(np.unique(val.view(np.uint64))) and (want is None or got == want)
+        x = np.random.default_rng(kind).standard_normal(A.local_rows)
+        xv, yv = A.vector(x), A.vector()
+        A.spmv(xv, yv)
+        assert np.array_equal(yv.download(), O.csr_spmv(rp, col, val, x))
+        xv.destroy(); yv.destroy(); A.destroy()
+
+
 def test_large_stencil_properties(ctx):
     """256^3 7-point (BASELINE config 2): size-independent checks."""
     nn = 256
