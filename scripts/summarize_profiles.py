@@ -86,12 +86,12 @@ def round2():
         s["traffic_over_format"] = s["dram_bytes_per_launch"] / s["format_bytes_per_launch"]
         json.dump(s, open(os.path.join(P, "r2_spmv_ncu_summary.json"), "w"), indent=1)
         print(s)
-    for name in ("r2_bench_n1.json", "r2_bench_ref.json", "r2_bench_n8.json", "r2_n2_bench.json"):
+    for name in ("r2_bench_n1.json", "r2_bench_ref.json", "r2_bench_n2.json", "r2_bench_n4.json", "r2_bench_n8.json"):
         src = os.path.join(G, name)
         if os.path.exists(src):
             lines = [l for l in open(src).read().splitlines() if l.startswith("{")]
             if lines:
-                json.dump(json.loads(lines[-1]), open(os.path.join(P, name.replace("r2_n2_bench", "r2_bench_n2")), "w"), indent=1)
+                json.dump(json.loads(lines[-1]), open(os.path.join(P, name), "w"), indent=1)
 
 
 def main():
