@@ -147,6 +147,8 @@ def _declare(L: C.CDLL) -> None:
     f("fsb_vec_box_upload_all", C.c_int, _p, _pd)
     f("fsb_vec_box_download_all", C.c_int, _p, _pd)
     f("fsb_parcsr_create_box_stencil", C.c_int, _p, C.c_int, _pi64, _pi64, _pi64, _dbl, _pd, C.POINTER(_p))
+    f("fsb_parcsr_create_box_fvm", C.c_int, _p, C.c_int, _pi64, _pi64, _pi64, _dbl, _dbl, _dbl, _pd, _pd, C.POINTER(_pd),
+      C.POINTER(_p))
     f("fsb_scalar_create", C.c_int, _p, C.POINTER(C.c_int32))
     f("fsb_scalar_destroy", C.c_int, _p, C.c_int32)
     f("fsb_scalar_set", C.c_int, _p, C.c_int32, _dbl)
@@ -307,6 +309,19 @@ class Context:
         hnd = _p()
         check(lib().fsb_parcsr_create_box_stencil(self.h, len(e), e.ctypes.data_as(_pi64), l.ctypes.data_as(_pi64),
                                                   h.ctypes.data_as(_pi64), center, _dptr(o), C.byref(hnd)))
+        return ParCSR(self, hnd)
+
+    def box_fvm(self, extents, lo, hi, beta: float, alpha: float, vol: float, kface, a, bface) -> "ParCSR":
+        """finite-volume diffusion operator -beta div(b grad u) + alpha vol a u from its coefficient fields (padded arrays)"""
+        e, l, h = (np.ascontiguousarray(v, dtype=np.int64) for v in (extents, lo, hi))
+        k = np.ascontiguousarray(kface, dtype=np.float64)
+        av = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        bs = [np.ascontiguousarray(b, dtype=np.float64).ravel() for b in bface]
+        assert av.size == int(np.prod(e)) and all(b.size == av.size for b in bs) and len(bs) == len(e) == k.size
+        ptrs = (_pd * len(bs))(*[_dptr(b) for b in bs])
+        hnd = _p()
+        check(lib().fsb_parcsr_create_box_fvm(self.h, len(e), e.ctypes.data_as(_pi64), l.ctypes.data_as(_pi64),
+                                              h.ctypes.data_as(_pi64), beta, alpha, vol, _dptr(k), _dptr(av), ptrs, C.byref(hnd)))
         return ParCSR(self, hnd)
 
     # device scalars (fsb.h "device scalars")

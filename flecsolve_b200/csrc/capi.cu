@@ -20,6 +20,8 @@ fsb_parcsr_s * fsb_parcsr_create_impl(fsb_ctx_s *, int64_t, const int64_t *, con
 fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s *, int, int64_t, int64_t, int64_t, double, double);
 fsb_parcsr_s * fsb_parcsr_create_box_stencil_impl(fsb_ctx_s *, int, const int64_t *, const int64_t *, const int64_t *, double,
                                                   const double *);
+fsb_parcsr_s * fsb_parcsr_create_box_fvm_impl(fsb_ctx_s *, int, const int64_t *, const int64_t *, const int64_t *, double, double, double,
+                                              const double *, const double *, const double * const *);
 void fsb_parcsr_destroy_impl(fsb_parcsr_s *);
 void fsb_parcsr_jacobi_relax_impl(fsb_parcsr_s *, double, int64_t, fsb_vec_s *, fsb_vec_s *, fsb_vec_s *);
 
@@ -661,6 +663,7 @@ int fsb_vec_box_upload_all(fsb_vec_t v, const double * host) {
 		flush(v->ctx);
 		FSB_CUDA(cudaMemcpyAsync(v->d, host, v->shape.storage() * sizeof(double), cudaMemcpyHostToDevice, v->ctx->stream));
 		FSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+		v->halo_valid = false; // ghost planes (several ranks) are stale from here on
 	});
 }
 int fsb_vec_box_download_all(fsb_vec_t v, double * host) {
@@ -1027,6 +1030,15 @@ int fsb_parcsr_create_box_stencil(fsb_ctx_t c, int dim, const int64_t * extents,
 	});
 }
 
+int fsb_parcsr_create_box_fvm(fsb_ctx_t c, int dim, const int64_t * extents, const int64_t * lo, const int64_t * hi, double beta,
+                              double alpha, double vol, const double * kface, const double * a, const double * const * bface,
+                              fsb_parcsr_t * out) {
+	return guarded([&] {
+		FSB_REQUIRE(c && extents && lo && hi && out, "bad arguments");
+		*out = fsb_parcsr_create_box_fvm_impl(c, dim, extents, lo, hi, beta, alpha, vol, kface, a, bface);
+	});
+}
+
 int fsb_parcsr_destroy(fsb_parcsr_t A) {
 	return guarded([&] {
 		if (A)
@@ -1071,7 +1083,7 @@ int fsb_parcsr_download(fsb_parcsr_t A, int which, int64_t * rowptr, int32_t * c
 					std::copy(t.begin(), t.end(), rp.begin());
 				}
 			}
-			if (B.row_ids || which == 1) {
+			if ((B.row_ids && !A->box) || which == 1) { // (a structured-grid operator's row ids are storage offsets; its rows are the dofs in order)
 				std::vector<int32_t> ids(static_cast<size_t>(B.n_rows));
 				if (B.n_rows > 0)
 					FSB_CUDA(cudaMemcpy(ids.data(), B.row_ids, ids.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -1144,7 +1156,7 @@ int fsb_parcsr_jacobi_relax(fsb_parcsr_t A, double omega, int64_t nrelax, fsb_ve
 int fsb_parcsr_halo_exchange(fsb_parcsr_t A, fsb_vec_t x) {
 	return guarded([&] {
 		FSB_REQUIRE(A && x, "null argument");
-		FSB_REQUIRE(!A->box && !x->box, "halo_exchange: structured-grid operators are single-rank");
+		FSB_REQUIRE(A->box == x->box, "halo_exchange: a structured-grid operator takes structured-grid vectors (and only those)");
 		halo_exchange(A, x);
 	});
 }

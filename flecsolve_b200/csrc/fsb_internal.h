@@ -260,6 +260,8 @@ struct fsb_parcsr_s {
 	// padded array, so boundary layers are read like any other entry (one rank only)
 	bool box = false;
 	fsb::box_shape shape;
+	// box operator over several ranks (slabs along the last axis): where the neighbours' planes go inside the padded array
+	long long box_split = -1, box_off[2] = {0, 0};
 };
 
 namespace fsb {

@@ -33,8 +33,10 @@ __global__ void __launch_bounds__(HALO_THREADS) halo_unpack_kernel(const halo_de
 	const unsigned char * src = halo_landing(h.base[h.me], static_cast<int>(epoch & 1), h.gmax);
 	const unsigned flag = static_cast<unsigned>(epoch);
 	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < h.n_ghost; i += stride)
-		ghosts[i] = halo_ghost(h, src, i, flag); // every entry validates itself
+	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < h.n_ghost; i += stride) {
+		const long long at = h.box_split < 0 ? i : (i < h.box_split ? h.box_off[0] + i : h.box_off[1] + (i - h.box_split));
+		ghosts[at] = halo_ghost(h, src, i, flag); // every entry validates itself
+	}
 	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -90,6 +92,9 @@ void halo_p2p_setup(fsb_parcsr_s * A, const std::vector<int64_t> & dest_off) {
 	}
 	h.send_idx = A->d_send_idx;
 	h.n_ghost = A->n_ghost;
+	h.box_split = A->box ? A->box_split : -1;
+	h.box_off[0] = A->box_off[0];
+	h.box_off[1] = A->box_off[1];
 	h.gmax = gmax;
 	FSB_CUDA(cudaMalloc(&h.counters, 2 * sizeof(unsigned)));
 	FSB_CUDA(cudaMemset(h.counters, 0, 2 * sizeof(unsigned)));
@@ -144,7 +149,7 @@ void halo_p2p_unpack(fsb_parcsr_s * A, fsb_vec_s * x) {
 		c->boot->rendezvous();
 	}
 	halo_unpack_kernel<<<A->halo_unpack_ctas, HALO_THREADS, 0, c->stream>>>(static_cast<const halo_dev *>(A->halo_p2p),
-	                                                                         x->d + x->n_owned, A->halo_epoch);
+	                                                                         A->box ? x->d : x->d + x->n_owned, A->halo_epoch);
 	FSB_CUDA(cudaGetLastError());
 	if (c->boot && c->boot->in_process())
 		c->boot->rendezvous();

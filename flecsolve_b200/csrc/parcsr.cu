@@ -207,6 +207,7 @@ void halo_exchange(fsb_parcsr_s * A, fsb_vec_s * x) {
 	if (c->nranks == 1 || A->nbrs.empty())
 		return;
 	FSB_REQUIRE(x->n_owned == A->n_local && x->n_ghost >= A->n_ghost, "halo_exchange: vector does not match the matrix");
+	FSB_REQUIRE(!A->box || (x->box && x->shape == A->shape), "halo_exchange: vector does not live on the operator's box");
 	if (A->halo_p2p) {
 		halo_p2p_push(A, x);
 		halo_p2p_unpack(A, x);
@@ -232,9 +233,15 @@ void spmv_group(fsb_ctx_s * c, const pending & sp, const pending * dot) {
 		call.dot_u = other->d; // other == y gives sum y^2
 		call.x_padded = call.x_padded && other->padded; // the window kernel stages u with bulk copies as well
 	}
-	if (A->box) { // columns and row ids are storage offsets of the padded arrays: one launch, no ghost exchange
+	if (A->box) { // columns and row ids are storage offsets of the padded arrays: one launch
+		if (c->nranks > 1 && !A->nbrs.empty() && !(x->halo_valid && x->halo_for == A->id)) {
+			// slabs over several ranks: refresh the ghost planes of x (the neighbours' outermost dof planes) first
+			halo_p2p_push(A, x);
+			halo_p2p_unpack(A, x);
+		}
 		call.fold = dot;
 		launch_spmv(c, A->diag, call, c->stream);
+		y->halo_valid = false;
 		return;
 	}
 	const bool multi = c->nranks > 1 && !A->nbrs.empty();
@@ -710,25 +717,27 @@ fsb_parcsr_s * fsb_parcsr_create_stencil_impl(fsb_ctx_s * c, int kind, int64_t n
 	return A;
 }
 
-// Structured-grid operator: the (2 dim + 1)-point stencil  center * u(i) + sum_axis off[axis] *
-// (u(i - e_axis) + u(i + e_axis))  over the interior sub-box of a padded array, assembled as CSR whose column
-// indices (and row_ids) are storage offsets into the padded array.  Rows follow the dof order (x fastest),
-// entries ascend in storage offset, and every neighbour is stored -- boundary layers hold the Dirichlet data and
-// are read like any other entry, as the reference's matrix-free stencil does on its narray mesh
-// (examples/poisson/mesh.hh:92-134, poisson.cc:44-82).  One rank only.
-fsb_parcsr_s * fsb_parcsr_create_box_stencil_impl(fsb_ctx_s * c, int dim, const int64_t * ext, const int64_t * lo,
-                                                  const int64_t * hi, double center, const double * off) {
-	flush(c);
-	FSB_REQUIRE(c->nranks == 1, "structured-grid operators are single-rank in this version");
-	FSB_REQUIRE(dim >= 1 && dim <= 3, "box stencil: dim must be 1, 2 or 3");
+// ------------------------------------------------------------------ structured-grid (narray) operators, SURVEY 8(f) N3
+
+// The operator's box, checked; several ranks: slabs along the LAST axis in rank order, every rank with its own padded array.
+static box_shape checked_box(int dim, const int64_t * ext, const int64_t * lo, const int64_t * hi) {
+	FSB_REQUIRE(dim >= 1 && dim <= 3, "box operator: dim must be 1, 2 or 3");
 	box_shape b;
 	for (int k = 0; k < dim; ++k) {
-		FSB_REQUIRE(lo[k] >= 1 && hi[k] <= ext[k] - 1 && lo[k] <= hi[k], "box stencil: the interior needs one boundary layer per side");
+		FSB_REQUIRE(lo[k] >= 1 && hi[k] <= ext[k] - 1 && lo[k] <= hi[k], "box operator: the interior needs one boundary layer per side");
 		b.ext[k] = ext[k];
 		b.lo[k] = lo[k];
 		b.n[k] = hi[k] - lo[k];
 	}
-	FSB_REQUIRE(b.storage() < (1LL << 31), "box stencil: padded array exceeds int32 offsets");
+	FSB_REQUIRE(b.storage() < (1LL << 31), "box operator: padded array exceeds int32 offsets");
+	return b;
+}
+
+// Rows follow the dof order (x fastest), entries ascend in storage offset, every neighbour is stored: boundary layers
+// hold boundary data (or, towards a neighbouring rank, ghost copies) and are read like any other entry.
+// coef(at, axis, side) -> value of the entry towards the lower (side 0) / upper (side 1) neighbour; diag(at) -> centre.
+template<class Coef, class Diag>
+static fsb_parcsr_s * assemble_box_operator(fsb_ctx_s * c, int dim, const box_shape & b, Coef && coef, Diag && diag) {
 	const int64_t n = b.dofs();
 	const int64_t stride[3] = {1, b.ext[0], b.ext[0] * b.ext[1]};
 	const int width = 2 * dim + 1;
@@ -743,13 +752,13 @@ fsb_parcsr_s * fsb_parcsr_create_box_stencil_impl(fsb_ctx_s * c, int dim, const 
 		rows[i] = static_cast<int32_t>(at);
 		for (int a = dim - 1; a >= 0; --a) {
 			col[k] = static_cast<int32_t>(at - stride[a]);
-			val[k++] = off[a];
+			val[k++] = coef(at, a, 0);
 		}
 		col[k] = static_cast<int32_t>(at);
-		val[k++] = center;
+		val[k++] = diag(at);
 		for (int a = 0; a < dim; ++a) {
 			col[k] = static_cast<int32_t>(at + stride[a]);
-			val[k++] = off[a];
+			val[k++] = coef(at, a, 1);
 		}
 	}
 	rp[n] = n * width;
@@ -761,7 +770,93 @@ fsb_parcsr_s * fsb_parcsr_create_box_stencil_impl(fsb_ctx_s * c, int dim, const 
 	A->n_global = A->n_local = n;
 	A->row_part = {0, n};
 	upload_block(c, A->diag, rp, col, val, &rows);
+	if (c->nranks > 1) {
+		// Slabs along the last axis: the pad plane of that axis facing rank r -+ 1 is a ghost plane -- it mirrors the
+		// neighbour's outermost dof plane (whole padded plane, boundary pads of the other axes included) and is refreshed
+		// before the operator reads it, FleCSI's ghost copy of an narray field.  Collective.
+		const int P = c->nranks, me = c->rank, last = dim - 1;
+		const int64_t plane = b.storage() / b.ext[last];
+		struct slab {
+			long long plane, n_last;
+		};
+		const std::vector<slab> all = c->boot->gather(slab{static_cast<long long>(plane), static_cast<long long>(b.n[last])}, P);
+		long long total = 0;
+		for (const slab & s : all) {
+			FSB_REQUIRE(s.plane == plane, "box operator: the ranks' slabs differ in the extents across the partitioned axis");
+			FSB_REQUIRE(s.n_last >= 1, "box operator: every rank needs at least one dof plane");
+			total += s.n_last * (b.dofs() / b.n[last]);
+		}
+		A->n_global = total;
+		std::vector<int64_t> dest_off;
+		int64_t landing = 0;
+		if (me > 0) { // lower neighbour: gets my first dof plane, fills the pad plane below it
+			neighbour nb{};
+			nb.rank = me - 1;
+			nb.send_count = nb.recv_count = plane;
+			nb.contiguous_start = b.lo[last] * plane;
+			nb.recv_offset = landing;
+			A->nbrs.push_back(nb);
+			dest_off.push_back(me - 1 > 0 ? plane : 0); // I am its upper neighbour: second in its landing area if it has a lower one
+			A->box_off[0] = (b.lo[last] - 1) * plane;
+			landing += plane;
+		}
+		A->box_split = landing;
+		if (me < P - 1) { // upper neighbour: gets my last dof plane, fills the pad plane above it
+			neighbour nb{};
+			nb.rank = me + 1;
+			nb.send_count = nb.recv_count = plane;
+			nb.contiguous_start = (b.lo[last] + b.n[last] - 1) * plane;
+			nb.recv_offset = landing;
+			A->nbrs.push_back(nb);
+			dest_off.push_back(0); // I am its lower neighbour: first in its landing area
+			A->box_off[1] = (b.lo[last] + b.n[last]) * plane;
+			landing += plane;
+		}
+		A->n_ghost = landing;
+		halo_p2p_setup(A, dest_off);
+		FSB_REQUIRE(A->halo_p2p || A->nbrs.empty(), "box operator over several ranks needs the peer-memory ghost exchange");
+	}
 	return A;
+}
+
+// The (2 dim + 1)-point stencil  center * u(i) + sum_axis off[axis] * (u(i - e_axis) + u(i + e_axis))  over the interior
+// sub-box of a padded array, as the reference's matrix-free stencil does on its narray mesh
+// (examples/poisson/mesh.hh:92-134, poisson.cc:44-82).
+fsb_parcsr_s * fsb_parcsr_create_box_stencil_impl(fsb_ctx_s * c, int dim, const int64_t * ext, const int64_t * lo,
+                                                  const int64_t * hi, double center, const double * off) {
+	flush(c);
+	const box_shape b = checked_box(dim, ext, lo, hi);
+	return assemble_box_operator(
+		c, dim, b, [&](int64_t, int a, int) { return off[a]; }, [&](int64_t) { return center; });
+}
+
+// The finite-volume diffusion operator of physics/volume_diffusion/diffusion.hh:84-207,
+//     v = -beta div(b grad u) + alpha vol a u :
+//   flux_axis(c) = b_axis(c) (dA_axis / dx_axis) (u(c + e_axis) - u(c))        (update_flux, :115-160)
+//   du(c) = sum_axis flux_axis(c) - flux_axis(c - e_axis)                       (sum_cell_flux, :162-181)
+//   v(c)  = -beta du(c) + alpha vol a(c) u(c)                                   (operate, :183-203)
+// assembled as CSR: the entry towards c + e_axis is -(beta (b_axis(c) k_axis)), towards c - e_axis
+// -(beta (b_axis(c - e_axis) k_axis)), the centre beta * sum_axis (b_axis(c) k_axis + b_axis(c - e_axis) k_axis) + (alpha vol) a(c),
+// k_axis = dA_axis / dx_axis = kface[axis].  a and b_axis are padded arrays with the box's extents; b_axis(c) is the
+// coefficient of the face between c and c + e_axis (so the faces of the boundary layers take part, as in the reference).
+fsb_parcsr_s * fsb_parcsr_create_box_fvm_impl(fsb_ctx_s * c, int dim, const int64_t * ext, const int64_t * lo, const int64_t * hi,
+                                              double beta, double alpha, double vol, const double * kface, const double * a,
+                                              const double * const * bface) {
+	flush(c);
+	const box_shape b = checked_box(dim, ext, lo, hi);
+	FSB_REQUIRE(kface && a && bface, "box fvm: null coefficient array");
+	for (int k = 0; k < dim; ++k)
+		FSB_REQUIRE(bface[k], "box fvm: null face coefficient array");
+	const int64_t stride[3] = {1, b.ext[0], b.ext[0] * b.ext[1]};
+	auto face = [&](int64_t at, int ax) { return bface[ax][at] * kface[ax]; };
+	return assemble_box_operator(
+		c, dim, b, [&](int64_t at, int ax, int side) { return -(beta * face(side ? at : at - stride[ax], ax)); },
+		[&](int64_t at) {
+			double s = 0.0;
+			for (int ax = 0; ax < dim; ++ax)
+				s += face(at, ax) + face(at - stride[ax], ax);
+			return beta * s + (alpha * vol) * a[at];
+		});
 }
 
 void fsb_parcsr_destroy_impl(fsb_parcsr_s * A) {

@@ -86,6 +86,10 @@ struct halo_dev {
 	long long recv_count[HALO_MAX_NBR]; // entries nbr k sends me
 	const int32_t * send_idx; // packed send lists (general partitions)
 	long long n_ghost; // my ghost entries
+	// structured-grid (box) vectors: the ghost entries are pad planes inside the padded array, not an interval behind the
+	// owned entries: landing entries [0, box_split) go to x[box_off[0] + i], the rest to x[box_off[1] + i - box_split];
+	// box_split < 0: contiguous ghost interval
+	long long box_split, box_off[2];
 	long long gmax; // landing-area capacity (max ghost count over ranks)
 	unsigned char * base[8]; // every rank's block: [spare 16 x 8][ack 8 x 8][pad to 256][landing 0][landing 1], 16 B per entry
 	unsigned * counters; // local: [1] unpack CTAs done

@@ -117,5 +117,37 @@ private:
 	fsb_parcsr_t handle_ = nullptr;
 };
 
+// finite-volume diffusion operator  -beta div(b grad u) + alpha vol a u  of physics/volume_diffusion/diffusion.hh:84-207 on
+// an narray topology, assembled from its coefficient fields (fsb_parcsr_create_box_fvm): a, b[axis] are host arrays over
+// the padded array (cells; faces between a cell and its upper neighbour), kface[axis] = dA_axis / dx_axis
+template<class Scalar, unsigned Dim>
+struct box_fvm : op::base<> {
+	using topo_t = topo::narray<Scalar, Dim>;
+
+	box_fvm(typename topo_t::topology & t, Scalar beta, Scalar alpha, Scalar vol, std::array<Scalar, Dim> kface, const Scalar * a,
+	        std::array<const Scalar *, Dim> b)
+		: topo(&t) {
+		device::check(fsb_parcsr_create_box_fvm(t.ctx.handle(), static_cast<int>(Dim), t.ext.data(), t.lo.data(), t.hi.data(), beta,
+		                                        alpha, vol, kface.data(), a, b.data(), &handle_));
+	}
+	box_fvm(const box_fvm &) = delete;
+	box_fvm(box_fvm && o) noexcept : topo(o.topo), handle_(o.handle_) { o.handle_ = nullptr; }
+	~box_fvm() {
+		if (handle_)
+			fsb_parcsr_destroy(handle_);
+	}
+
+	template<class D, class R>
+	void apply(const D & x, R & y) const {
+		device::check(fsb_parcsr_spmv(handle_, x.data.handle(), y.data.handle()));
+	}
+	fsb_parcsr_t handle() const { return handle_; }
+
+	typename topo_t::topology * topo;
+
+private:
+	fsb_parcsr_t handle_ = nullptr;
+};
+
 }
 #endif

@@ -271,12 +271,26 @@ int fsb_ctx_halt_disarm(fsb_ctx_t ctx, int * was_halted);
  * over the dofs of such a box as CSR whose column indices are storage offsets of the padded array,
  * so boundary layers take part exactly as in the reference's stencil operators
  * (examples/poisson/poisson.cc:44-82); fsb_parcsr_spmv runs it through the same SpMV kernel
- * (fused dot included).  One rank only in this version.                                            */
+ * (fused dot included).
+ * fsb_parcsr_create_box_fvm assembles the finite-volume diffusion operator of
+ * physics/volume_diffusion/diffusion.hh:84-207,  v = -beta div(b grad u) + alpha vol a u,  from its coefficient fields:
+ *     flux_axis(c) = b_axis(c) kface[axis] (u(c + e_axis) - u(c)),   kface[axis] = dA_axis / dx_axis,
+ *     v(c) = -beta sum_axis (flux_axis(c) - flux_axis(c - e_axis)) + alpha vol a(c) u(c);
+ * a and b_axis (host pointers) are padded arrays with the box's extents, b_axis(c) = coefficient of the face between
+ * c and c + e_axis.  Entries: towards c +- e_axis  -(beta (b kface)),  centre  beta sum (b kface) + (alpha vol) a(c).
+ * Several ranks: the mesh is cut into slabs along its LAST axis, one per rank in rank order, and every rank passes the
+ * extents of ITS padded array (the same across the other axes).  The pad plane of the last axis that faces a
+ * neighbouring rank is a ghost plane: it mirrors the neighbour's outermost dof plane and fsb_parcsr_spmv /
+ * fsb_parcsr_halo_exchange refresh it over peer memory before the operator reads it (FleCSI's ghost copy of an narray
+ * field); all other pad layers hold boundary data.  Both creators are collective then.                               */
 int fsb_vec_create_box(fsb_ctx_t ctx, int dim, const int64_t * extents, const int64_t * lo, const int64_t * hi, fsb_vec_t * out);
 int fsb_vec_box_upload_all(fsb_vec_t v, const double * host);
 int fsb_vec_box_download_all(fsb_vec_t v, double * host);
 int fsb_parcsr_create_box_stencil(fsb_ctx_t ctx, int dim, const int64_t * extents, const int64_t * lo, const int64_t * hi,
                                   double center, const double * off, fsb_parcsr_t * out);
+int fsb_parcsr_create_box_fvm(fsb_ctx_t ctx, int dim, const int64_t * extents, const int64_t * lo, const int64_t * hi, double beta,
+                              double alpha, double vol, const double * kface, const double * a, const double * const * bface,
+                              fsb_parcsr_t * out);
 
 /* ---- parallel CSR matrix ------------------------------------------------
  * Device image of mat::parcsr (matrices/parcsr.hh:101-177) on the topology

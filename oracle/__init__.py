@@ -202,3 +202,38 @@ class ParCSR:
               right_precond=True, restart=False, history_cap=0):
         return self._solve("orc_gmres", b, x0, dinv, maxiter, rtol, use_zero_guess, history_cap,
                            extra=(max_krylov_dim, int(right_precond), int(restart)))
+
+
+def fvm_diffusion_apply(u, a, bface, beta: float, alpha: float, vol: float, kface, lo, hi) -> np.ndarray:
+    """The reference's matrix-free finite-volume diffusion operator  v = -beta div(b grad u) + alpha vol a u  on one
+    padded array (physics/volume_diffusion/diffusion.hh): arrays are indexed [k][j][i] (x fastest), as the mdspans there.
+      update_flux   (:115-160)  f_x[k][j][i] = b_x[k][j][i] * (dA_x * i_dx) * (u[k][j][i+1] - u[k][j][i])   (same for y, z)
+      sum_cell_flux (:162-181)  du[k][j][i] = (f_x[k][j][i] - f_x[k][j][i-1]) + (f_y[..j..] - f_y[..j-1..]) + (f_z[k] - f_z[k-1])
+      operate       (:183-203)  v[k][j][i]  = (-beta * du[k][j][i]) + (alpha * vol * a[k][j][i] * u[k][j][i])
+    kface[axis] = dA_axis * i_dx_axis.  lo/hi: the dof box per axis (x first); v is returned for the dofs, 0 elsewhere.
+    1-D and 2-D boxes are the same expressions without the missing axes (a sum of fewer differences)."""
+    u = np.asarray(u, dtype=np.float64)
+    dim = u.ndim
+    a = np.asarray(a, dtype=np.float64).reshape(u.shape)
+    flux = []
+    for ax in range(dim):  # ax 0 = x = the LAST numpy axis
+        npax = dim - 1 - ax
+        b = np.asarray(bface[ax], dtype=np.float64).reshape(u.shape)
+        f = np.zeros_like(u)
+        upper = [slice(None)] * dim
+        lower = [slice(None)] * dim
+        upper[npax] = slice(1, None)
+        lower[npax] = slice(0, -1)
+        f[tuple(lower)] = b[tuple(lower)] * kface[ax] * (u[tuple(upper)] - u[tuple(lower)])
+        flux.append(f)
+    box = tuple(slice(lo[dim - 1 - d], hi[dim - 1 - d]) for d in range(dim))  # numpy axis d is mesh axis dim-1-d
+    du = None
+    for ax in range(dim):
+        npax = dim - 1 - ax
+        shifted = tuple(slice(s.start - 1, s.stop - 1) if d == npax else s for d, s in enumerate(box))
+        term = flux[ax][box] - flux[ax][shifted]
+        du = term if du is None else du + term
+    v = np.zeros_like(u)
+    v[box] = (-beta * du) + (alpha * vol * a[box] * u[box])
+    return v
+

@@ -149,3 +149,108 @@ def test_device_generator_and_solvers(kind, dims):
         return [S, xv, yv, B]
 
     run_ranks(P, body)
+
+
+@pytest.mark.parametrize("nranks,dims", [(2, (9, 7, 10)), (3, (6, 5, 11)), (2, (11, 8))])
+def test_structured_grid_operators_over_slabs(nranks, dims):
+    """narray fields cut into slabs along the last axis, one padded array per rank: the pad plane facing a
+    neighbour is a ghost plane refreshed by the operator (FleCSI's ghost copy) -- the stencil and the assembled finite-volume
+    operator equal the one-array results (stencil: bit for bit), reductions span the ranks, and a CG written on the C ABI's
+    vector calls converges to the same iterate as on one rank"""
+    P = nranks
+    dim = len(dims)
+    rng = np.random.default_rng(dim * 10 + P)
+    ext = tuple(n + 2 for n in dims)  # global padded array, x first
+    gshape = ext[::-1]
+    lo, hi = (1,) * dim, tuple(n + 1 for n in dims)
+    ug = rng.standard_normal(gshape)  # boundary layers hold data too
+    a = rng.uniform(0.5, 2.0, gshape)
+    bface = [rng.uniform(0.5, 2.0, gshape) for _ in range(dim)]
+    kface = list(rng.uniform(0.5, 2.0, dim))
+    beta, alpha, vol = 1.3, 0.7, 0.11
+    off = [-1.0, -1.25, -0.5][:dim]
+    center = 2.0 * sum(-o for o in off) + 0.3
+    box = tuple(slice(1, n + 1) for n in dims[::-1])
+    # one-array references
+    sten = np.zeros(gshape)
+    terms = [(off[ax], np.roll(ug, 1, axis=dim - 1 - ax)) for ax in reversed(range(dim))] + [(center, ug)]
+    terms += [(off[ax], np.roll(ug, -1, axis=dim - 1 - ax)) for ax in range(dim)]
+    for c, arr in terms:
+        sten = sten + c * arr
+    fvm = O.fvm_diffusion_apply(ug, a, bface, beta, alpha, vol, kface, lo, hi)
+    # slabs of the last mesh axis = numpy axis 0
+    cuts = D.equal_map(dims[-1], P)
+    bvec = rng.standard_normal(gshape)
+
+    def cg(ctx, A, mk, b, iters):  # unpreconditioned CG on box vectors through the C ABI
+        x, r, p, w = mk(), mk(), mk(), mk()
+        x.set_scalar(0.0); r.copy(b); p.copy(b)
+        rho = ctx.get(r.dot_token(r))
+        hist = [rho]
+        for _ in range(iters):
+            A.spmv(p, w)
+            alpha_ = rho / ctx.get(w.dot_token(p))
+            x.linear_sum(alpha_, p, 1.0, x)
+            r.linear_sum(-alpha_, w, 1.0, r)
+            rho_new = ctx.get(r.dot_token(r))
+            hist.append(rho_new)
+            p.linear_sum(rho_new / rho, p, 1.0, r)
+            rho = rho_new
+        return x, hist, [r, p, w]
+
+    # the same CG on ONE rank (whole array) as the reference for the solver check
+    solo = F.Context(0)
+    As = solo.box_stencil(ext, lo, hi, center, off)
+    mk_s = lambda: solo.box_vector(ext, lo, hi).upload_all(np.zeros(ug.size))
+    bs = mk_s().upload_all(bvec.ravel())
+    xs, hist_solo, junk = cg(solo, As, mk_s, bs, 12)
+    x_solo = xs.download_all().reshape(gshape)
+    for v in [xs, bs] + junk:
+        v.destroy()
+    As.destroy(); solo.close()
+
+    def body(ctx, me):
+        z0, z1 = cuts[me], cuts[me + 1]  # my dof planes (0-based among the dofs of the last axis)
+        lext = ext[:-1] + (z1 - z0 + 2,)
+        llo, lhi = (1,) * dim, tuple(n + 1 for n in dims[:-1]) + (z1 - z0 + 1,)
+        mine = slice(z0, z1 + 2)  # padded planes of the global array that are my padded array
+
+        def local(arr, poison=False):
+            out = arr[mine].copy()
+            if poison:  # ghost planes start out wrong: the operator must refresh them
+                if me > 0:
+                    out[0] = 7.0
+                if me < P - 1:
+                    out[-1] = -7.0
+            return out
+
+        x = ctx.box_vector(lext, llo, lhi).upload_all(local(ug, poison=True).ravel())
+        y = ctx.box_vector(lext, llo, lhi).upload_all(np.zeros(x.n + x.n_ghost))
+        lbox = (slice(1, z1 - z0 + 1),) + box[1:]
+        gbox = (slice(z0 + 1, z1 + 1),) + box[1:]
+        A = ctx.box_stencil(lext, llo, lhi, center, off)
+        assert A.global_rows == int(np.prod(dims)) and A.local_rows == x.n
+        A.spmv(x, y)
+        got = y.download_all().reshape(lext[::-1])
+        assert np.array_equal(got[lbox], sten[gbox])
+        # the ghost planes of x now hold the neighbours' planes, boundary pads of the other axes included
+        xa = x.download_all().reshape(lext[::-1])
+        assert np.array_equal(xa, ug[mine])
+        d = ctx.get(y.dot_token(x))
+        want = float(np.sum(sten[box] * ug[box]))
+        assert abs(d - want) <= 1e-12 * float(np.sum(np.abs(sten[box] * ug[box])))
+        B = ctx.box_fvm(lext, llo, lhi, beta, alpha, vol, kface, local(a), [local(b) for b in bface])
+        x.upload_all(local(ug, poison=True).ravel())  # a write invalidates the ghost planes
+        B.spmv(x, y)
+        got = y.download_all().reshape(lext[::-1])
+        assert np.abs(got[lbox] - fvm[gbox]).max() <= 1e-12 * np.abs(fvm[box]).max()
+        B.halo_exchange(x)
+        mk = lambda: ctx.box_vector(lext, llo, lhi).upload_all(np.zeros(x.n + x.n_ghost))
+        b = mk().upload_all(local(bvec).ravel())
+        xs, hist, junk = cg(ctx, A, mk, b, 12)
+        assert np.allclose(hist, hist_solo, rtol=1e-10)
+        assert np.abs(xs.download_all().reshape(lext[::-1])[lbox] - x_solo[gbox]).max() <= 1e-10 * np.abs(x_solo).max()
+        return [x, y, b, xs] + junk + [A, B]
+
+    run_ranks(P, body)
+
