@@ -1,6 +1,5 @@
 """The example applications (examples/): flecsolve-shaped user code over the header layer.
-Building them needs no GPU and is part of the CPU suite; running them is done when the whole suite runs on
-a GPU box (not selected by `-m gpu`: first exercised on hardware in round 2)."""
+Building them needs no GPU and is part of the CPU suite; running them is part of `-m gpu`."""
 import os
 import re
 import subprocess
@@ -21,9 +20,10 @@ def _build():
 
 def test_examples_build():
     _build()
-    assert os.path.exists(os.path.join(OUT, "poisson")) and os.path.exists(os.path.join(OUT, "implicit"))
+    assert all(os.path.exists(os.path.join(OUT, name)) for name in ("poisson", "implicit", "diffusion"))
 
 
+@pytest.mark.gpu
 def test_examples_run():
     if F.device_count() == 0:
         pytest.skip("no CUDA device")
@@ -39,3 +39,12 @@ def test_examples_run():
     m = re.search(r"(\d+) steps \((\d+) attempts, (\d+) rejected\), max u = ([0-9.]+), heat ([0-9.]+) -> ([0-9.]+)", r.stdout)
     assert m, r.stdout
     assert int(m.group(1)) >= 10 and 0.0 < float(m.group(4)) <= 50.0 and float(m.group(6)) <= float(m.group(5)) * (1 + 1e-9)
+    # examples/equilibrium_diffusion: v1 (Dirichlet sides) drains towards 0, v2 (zero-flux sides) keeps its constant
+    r = subprocess.run([os.path.join(OUT, "diffusion"), "48", os.path.join(ROOT, "examples", "equilibrium_diffusion", "diffusion.cfg")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"converged after (\d+) iterations.*v1 in \[([0-9.e+-]+), ([0-9.e+-]+)\], v2 in \[([0-9.]+), ([0-9.]+)\]", r.stdout)
+    assert m, r.stdout
+    assert 10 < int(m.group(1)) <= 500 and abs(float(m.group(2))) < 1e-3 and abs(float(m.group(3))) < 1e-3, r.stdout
+    assert abs(float(m.group(4)) - 2.0) < 1e-9 and abs(float(m.group(5)) - 2.0) < 1e-9, r.stdout
+
