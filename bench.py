@@ -329,6 +329,7 @@ def run_ours(args):
             "workload": head["workload"],
             "rows": head["rows"], "nnz": head["nnz"], "partition": head["partition"],
             "device_format": head["device_format"],
+            "value_dictionary": head.get("value_dictionary", 0),
             "l2_policy": "inputs larger than L2 (per-iteration working set %.2f GB >> 126 MB)"
                          % (head["roofline"]["iteration"]["algorithmic_bytes"] / 1e9),
             "timed": f"iterations {W + 1}..{W + K} of one solve (rtol 0), CUDA events on the library stream, max over ranks; "
@@ -355,10 +356,15 @@ def run_ours(args):
     if os.path.exists(tp) and args.workload == "poisson7_256" and world.size == 1:
         try:
             t = json.load(open(tp))
-            line["roofline"]["traffic"] = t.get("dram_bytes_per_launch")
-            line["roofline"]["traffic_source"] = ("not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the "
-                                                  "same kernel on the same workload from the committed ncu --set full capture "
-                                                  "profiles/r2_spmv_ncu_summary.json")
+            # the capture names the instantiation it measured; only quote it for the format this run used
+            if bool(t.get("value_dictionary")) == bool(head.get("value_dictionary")):
+                line["roofline"]["traffic"] = t.get("dram_bytes_per_launch")
+                line["roofline"]["traffic_source"] = ("not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of "
+                                                      "the same kernel instantiation on the same workload from the committed "
+                                                      "ncu --set full capture profiles/r2_spmv_ncu_summary.json (" +
+                                                      str(t.get("kernel")) + ")")
+            if t.get("general_format"):
+                line["roofline"]["traffic_general_format"] = t["general_format"]
         except Exception:
             pass
     if world.is_root and world.size == 1:

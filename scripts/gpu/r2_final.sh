@@ -12,10 +12,14 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 3
     python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-workloads --repeats 1 > $O/r2_bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:spmv_window -s 30 -c 1 -f -o $O/r2_final_spmv7 \
     python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-workloads --repeats 1 > $O/r2_ncu_spmv7.log 2>&1
+FSB_SPMV_DICT=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:spmv_window -s 30 -c 1 -f -o $O/r2_final_spmv7_general \
+    python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-workloads --repeats 1 > $O/r2_ncu_spmv7_general.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ew_program -s 60 -c 3 -f -o $O/r2_final_ew \
     python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-workloads --repeats 1 > $O/r2_ncu_ew.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_window -s 5 -c 1 -f -o $O/r2_final_spmv27_512 \
     python scripts/gpu/spmv_sweep.py 27 512 512 dotx > $O/r2_ncu_spmv27.log 2>&1
+FSB_SPMV_DICT=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_window -s 5 -c 1 -f -o $O/r2_final_spmv27_512_general \
+    python scripts/gpu/spmv_sweep.py 27 512 512 dotx > $O/r2_ncu_spmv27_general.log 2>&1
 fi
 python - <<'PY'
 import json

@@ -73,17 +73,38 @@ def round2():
              "# round 2: ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 300, python bench.py --steps 20 --warmup 5 "
              "--no-cpu-baseline --no-extra-workloads --repeats 1\n# (7-pt 256^3 Jacobi-CG; the window covers the CG flavours "
              "bench.py times: op::cg, cg_device, cg_sr)")
-    f = full([os.path.join(G, "r2_final_spmv7.ncu-rep"), os.path.join(G, "r2_final_spmv27_512.ncu-rep"),
-              os.path.join(G, "r2_final_ew.ncu-rep")], os.path.join(P, "r2_ncu_full_summary.txt"),
+    f = full([p for p in (os.path.join(G, "r2_final_spmv7.ncu-rep"), os.path.join(G, "r2_final_spmv27_512.ncu-rep"),
+                          os.path.join(G, "r2_final_spmv27_512_general.ncu-rep"), os.path.join(G, "r2_final_ew.ncu-rep"))
+              if os.path.exists(p)], os.path.join(P, "r2_ncu_full_summary.txt"),
              "# round 2: ncu --set full --clock-control none --import-source on; spmv_window_kernel inside bench.py (7-pt 256^3, "
              "fused <Ap,p>), the same kernel on 27-pt 512^3 (scripts/gpu/spmv_sweep.py 27 512 512 dotx), CG's element-wise kernels",
              key="spmv_window")
     if "spmv" in f:
         s = f["spmv"]
+        # template arguments <NSTAGE, DOT, HALO, JAC, VD>: VD = value dictionary
+        s["value_dictionary"] = s["kernel"].replace(" ", "").endswith("true>(spmv_args)") or ",true>" in s["kernel"].replace(" ", "")[-24:]
         s["algorithmic_bytes_per_launch"] = 12 * 117047296 + 4 * (16777216 + 1) + 16 * 16777216
-        s["format_bytes_per_launch"] = 1506092180
+        bench = os.path.join(G, "r2_bench_n1.json")
+        fmt = None
+        if os.path.exists(bench):
+            lines = [l for l in open(bench).read().splitlines() if l.startswith("{")]
+            if lines:
+                fmt = json.loads(lines[-1])["roofline"].get("format_bytes_per_launch")
+        s["format_bytes_per_launch"] = fmt
         s["traffic_over_algorithmic"] = s["dram_bytes_per_launch"] / s["algorithmic_bytes_per_launch"]
-        s["traffic_over_format"] = s["dram_bytes_per_launch"] / s["format_bytes_per_launch"]
+        if fmt:
+            s["traffic_over_format"] = s["dram_bytes_per_launch"] / fmt
+        # the general (10 B per nonzero) window kernel, captured with the dictionary off
+        g = full([os.path.join(G, "r2_final_spmv7_general.ncu-rep")], os.path.join(P, "r2_ncu_full_summary_general.txt"),
+                 "# round 2: the same capture with FSB_SPMV_DICT=0 (window format, fp64 values: what a general matrix runs)",
+                 key="spmv_window") if os.path.exists(os.path.join(G, "r2_final_spmv7_general.ncu-rep")) else {}
+        if "spmv" in g:
+            gg = g["spmv"]
+            s["general_format"] = {"kernel": gg["kernel"], "dram_bytes_per_launch": gg["dram_bytes_per_launch"],
+                                   "format_bytes_per_launch": 1506092180,
+                                   "traffic_over_format": gg["dram_bytes_per_launch"] / 1506092180,
+                                   "traffic_over_algorithmic": gg["dram_bytes_per_launch"] / s["algorithmic_bytes_per_launch"],
+                                   "gpu_time_us_under_ncu": gg["gpu_time_us_under_ncu"], "source": gg["source"]}
         json.dump(s, open(os.path.join(P, "r2_spmv_ncu_summary.json"), "w"), indent=1)
         print(s)
     for name in ("r2_bench_n1.json", "r2_bench_ref.json", "r2_bench_n2.json", "r2_bench_n4.json", "r2_bench_n8.json"):
