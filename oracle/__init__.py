@@ -38,9 +38,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            import sys
-            sys.path.insert(0, os.path.dirname(_HERE))
-            from flecsolve_b200 import build as _b
+            from oracle import build as _b
             _b.build_oracle()
         L = C.CDLL(LIB_PATH)
         L.orc_max_threads.restype = C.c_int
