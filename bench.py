@@ -226,6 +226,7 @@ def measure(world, ctx, workload: str, W: int, K: int, repeats: int, solver: str
             "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
             "launches_timed": spmv_n, "share_of_step": spmv_avg_ms / ms_per_step if ms_per_step > 0 else None,
             "format_bytes_per_launch": fmt_bytes, "achieved_format_gbs": fmt_bytes / spmv_avg_ms / 1e6 if spmv_avg_ms > 0 else 0.0,
+            "frac_format": fmt_bytes / spmv_avg_ms / 1e6 / peak if spmv_avg_ms > 0 else 0.0,
             "note": "achieved = SURVEY 8(d) algorithmic bytes (12 B/nnz CSR) / time; the device streams format_bytes "
                     "(value dictionary: ~3.4 B/nnz, window format: 10 B/nnz), so achieved may exceed the copy peak while "
                     "achieved_format cannot",

@@ -10,17 +10,23 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/r2_bench_
 if [ "$1" != "quick" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 300 --csv --log-file $O/r2_launches.csv \
     python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-workloads --repeats 1 > $O/r2_bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:spmv_window -s 30 -c 1 -f -o $O/r2_final_spmv7 \
+timeout 600 ncu --set full --clock-control none -k regex:spmv_window -s 30 -c 1 -f -o $O/r2_final_spmv7 \
     python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-workloads --repeats 1 > $O/r2_ncu_spmv7.log 2>&1
-FSB_SPMV_DICT=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:spmv_window -s 30 -c 1 -f -o $O/r2_final_spmv7_general \
+FSB_SPMV_DICT=0 timeout 600 ncu --set full --clock-control none -k regex:spmv_window -s 30 -c 1 -f -o $O/r2_final_spmv7_general \
     python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-workloads --repeats 1 > $O/r2_ncu_spmv7_general.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:ew_program -s 60 -c 3 -f -o $O/r2_final_ew \
+timeout 600 ncu --set full --clock-control none -k regex:ew_program -s 60 -c 3 -f -o $O/r2_final_ew \
     python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-workloads --repeats 1 > $O/r2_ncu_ew.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_window -s 5 -c 1 -f -o $O/r2_final_spmv27_512 \
+timeout 900 ncu --set full --clock-control none -k regex:spmv_window -s 5 -c 1 -f -o $O/r2_final_spmv27_512 \
     python scripts/gpu/spmv_sweep.py 27 512 512 dotx > $O/r2_ncu_spmv27.log 2>&1
-FSB_SPMV_DICT=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_window -s 5 -c 1 -f -o $O/r2_final_spmv27_512_general \
+FSB_SPMV_DICT=0 timeout 900 ncu --set full --clock-control none -k regex:spmv_window -s 5 -c 1 -f -o $O/r2_final_spmv27_512_general \
     python scripts/gpu/spmv_sweep.py 27 512 512 dotx > $O/r2_ncu_spmv27_general.log 2>&1
 fi
+# keep what comes back small (gpurun merges at most 64 MiB): raw metric tables instead of the reports
+for r in $O/r2_final_*.ncu-rep; do
+  [ -f "$r" ] || continue
+  ncu -i "$r" --page raw --csv > "${r%.ncu-rep}.raw.csv" 2>/dev/null
+  case "$r" in *r2_final_spmv7.ncu-rep) ;; *) rm -f "$r";; esac
+done
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/r2_bench_n1.json').read().strip().splitlines()[-1])

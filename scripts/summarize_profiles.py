@@ -42,8 +42,12 @@ def full(reps, dst, title, key="spmv_stream"):
     out = [title]
     first = {}
     for rep in reps:
-        r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
-        rows = list(csv.reader(r.stdout.splitlines()))
+        pre = rep[:-len(".ncu-rep")] + ".raw.csv"  # extracted on the GPU box (scripts/gpu/r2_final.sh) to keep the download small
+        if os.path.exists(pre):
+            text = open(pre).read()
+        else:
+            text = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(text.splitlines()))
         rows = [x for x in rows if len(x) > 20]
         hdr, units = rows[0], rows[1]
         idx = {h: i for i, h in enumerate(hdr)}
@@ -75,14 +79,16 @@ def round2():
              "bench.py times: op::cg, cg_device, cg_sr)")
     f = full([p for p in (os.path.join(G, "r2_final_spmv7.ncu-rep"), os.path.join(G, "r2_final_spmv27_512.ncu-rep"),
                           os.path.join(G, "r2_final_spmv27_512_general.ncu-rep"), os.path.join(G, "r2_final_ew.ncu-rep"))
-              if os.path.exists(p)], os.path.join(P, "r2_ncu_full_summary.txt"),
+              if os.path.exists(p) or os.path.exists(p[:-len(".ncu-rep")] + ".raw.csv")], os.path.join(P, "r2_ncu_full_summary.txt"),
              "# round 2: ncu --set full --clock-control none --import-source on; spmv_window_kernel inside bench.py (7-pt 256^3, "
              "fused <Ap,p>), the same kernel on 27-pt 512^3 (scripts/gpu/spmv_sweep.py 27 512 512 dotx), CG's element-wise kernels",
              key="spmv_window")
     if "spmv" in f:
         s = f["spmv"]
         # template arguments <NSTAGE, DOT, HALO, JAC, VD>: VD = value dictionary
-        s["value_dictionary"] = s["kernel"].replace(" ", "").endswith("true>(spmv_args)") or ",true>" in s["kernel"].replace(" ", "")[-24:]
+        import re
+        m = re.search(r"<([^>]*)>", s["kernel"])
+        s["value_dictionary"] = bool(m) and m.group(1).replace(" ", "").split(",")[-1] in ("1", "true")
         s["algorithmic_bytes_per_launch"] = 12 * 117047296 + 4 * (16777216 + 1) + 16 * 16777216
         bench = os.path.join(G, "r2_bench_n1.json")
         fmt = None
@@ -97,7 +103,8 @@ def round2():
         # the general (10 B per nonzero) window kernel, captured with the dictionary off
         g = full([os.path.join(G, "r2_final_spmv7_general.ncu-rep")], os.path.join(P, "r2_ncu_full_summary_general.txt"),
                  "# round 2: the same capture with FSB_SPMV_DICT=0 (window format, fp64 values: what a general matrix runs)",
-                 key="spmv_window") if os.path.exists(os.path.join(G, "r2_final_spmv7_general.ncu-rep")) else {}
+                 key="spmv_window") if (os.path.exists(os.path.join(G, "r2_final_spmv7_general.ncu-rep")) or
+                                        os.path.exists(os.path.join(G, "r2_final_spmv7_general.raw.csv"))) else {}
         if "spmv" in g:
             gg = g["spmv"]
             s["general_format"] = {"kernel": gg["kernel"], "dram_bytes_per_launch": gg["dram_bytes_per_launch"],
