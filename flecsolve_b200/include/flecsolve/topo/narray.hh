@@ -4,7 +4,8 @@
 // examples/heat_equation/mesh.hh, examples/equilibrium_diffusion mesh): per axis a number of interior
 // ("logical") points plus boundary/ghost layers, `dofs<space>()` = the interior sub-box in colexicographic
 // order (index_util.hh:33-71), geometry (xdelta, ydelta) from the bounding box.  This header is the
-// one-colour device counterpart: storage per field = the padded array (fsb_vec_create_box), every vec::core
+// device counterpart (one padded array per rank; several ranks = slabs along the last axis whose facing pad planes are ghost
+// planes the operators refresh, see fsb.h): storage per field = the padded array (fsb_vec_create_box), every vec::core
 // operation runs over the dofs only, and operators read the boundary layers (mat::box_stencil below).
 #ifndef FLECSOLVE_B200_TOPO_NARRAY_HH
 #define FLECSOLVE_B200_TOPO_NARRAY_HH

@@ -1,0 +1,20 @@
+"""Scratch: host-side cost of a CG iteration (flush = statement queue -> launches, wait = polling for reduction results)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np
+from bench import WORKLOADS, x_true
+from flecsolve_b200 import _lib as F, host as H
+nn = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+ctx = F.Context(0)
+A = F.ParCSR.stencil(ctx, 7, nn, nn, nn)
+S = H.Session(ctx, A)
+xt = A.vector(x_true(0, A.local_rows)); A.spmv(xt, S.b); ctx.sync()
+for solver in ("cg", "cg_device"):
+    S.x.zero(); S.solve(solver=solver, precond="dinv", maxiter=50, rtol=0.0, lag=2)
+    S.x.zero(); ctx.sync(); ctx.reset_stats()
+    t0 = time.perf_counter()
+    S.solve(solver=solver, precond="dinv", maxiter=400, rtol=0.0, lag=2)
+    ctx.sync(); dt = time.perf_counter() - t0
+    it = 400
+    print(f"{nn}^3 {solver}: {dt/it*1e6:.1f} us/iteration wall; flush {ctx.stat('flush_ns')/it/1e3:.2f} us, wait {ctx.stat('wait_ns')/it/1e3:.2f} us, "
+          f"host syncs {ctx.stat('host_syncs')/it:.2f}, launches {ctx.stat('launches')/it:.2f} per iteration")
