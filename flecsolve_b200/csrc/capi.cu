@@ -263,8 +263,10 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 		if (!c)
 			return;
 		flush(c);
+		fsb::speculation_release(c);
 		cudaStreamSynchronize(c->stream);
 		cudaStreamSynchronize(c->comm_stream);
+		fsb::speculation_destroy(c);
 		for (void * p : c->peer_mailbox)
 			if (p && c->boot)
 				c->boot->unshare(p);
@@ -348,6 +350,11 @@ int fsb_ctx_set_option(fsb_ctx_t c, int option, int64_t value) {
 			break;
 		case FSB_OPT_SPMV_DICTIONARY:
 			c->spmv_dictionary = value != 0;
+			break;
+		case FSB_OPT_SPECULATE:
+			c->speculate = value != 0;
+			if (!c->speculate)
+				fsb::speculation_release(c);
 			break;
 		case FSB_OPT_TIMELINE:
 			FSB_CUDA(cudaStreamSynchronize(c->stream));
@@ -952,7 +959,9 @@ static void wait_token(fsb_ctx_t c, fsb_token_t tok) {
 	FSB_REQUIRE(c, "null context");
 	FSB_REQUIRE(tok > 0 && tok < c->next_token, "unknown reduction token");
 	FSB_REQUIRE(tok + FSB_RED_RING > c->next_token - 1, "reduction token expired");
-	flush(c);
+	flush(c, true);
+	if (c->speculate)
+		fsb::speculate_after_flush(c); // the kernel the host will most likely ask for next goes in behind the one it waits for
 	const auto t_begin = std::chrono::steady_clock::now();
 	const int slot = static_cast<int>(tok % FSB_RED_RING);
 	if (c->nranks > 1 && !c->d_xrank) {
@@ -975,6 +984,8 @@ static void wait_token(fsb_ctx_t c, fsb_token_t tok) {
 			}
 		}
 		c->h_results[slot] = v;
+		if (fsb::speculation_failed(c))
+			throw fsb::error(FSB_ERR_STATE, "a kernel launched ahead of its coefficients (FSB_OPT_SPECULATE) never heard from the host");
 		if (c->h_xrank_error && *(volatile int *)c->h_xrank_error) {
 			static const char * what[] = {"", "a reduction's all-reduce", "the acknowledgement of a ghost landing buffer",
 			                              "ghost entries"};

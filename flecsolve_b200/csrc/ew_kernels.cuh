@@ -120,6 +120,68 @@ __device__ __forceinline__ void grid_dependency_wait() {
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// Late-bound coefficients ("armed" launches, fuser.cu): a kernel whose coefficients the host computes from a reduction
+// it is still waiting for can be launched AHEAD of that result -- it becomes resident behind its predecessor and waits
+// here for a word in mapped host memory instead of for a launch: {sequence number << 2 | verdict}.  GO: the coefficients
+// are in late_host::s; ABORT: the host went another way, the kernel leaves without touching anything.  CTA 0 watches
+// the host word and republishes it in device memory for the other CTAs (one reader on PCIe, the rest in L2).
+constexpr unsigned LATE_GO = 1, LATE_ABORT = 2;
+struct late_host { // mapped pinned host memory, written by the host
+	unsigned long long word;
+	double s[MAXSC];
+};
+struct late_dev { // device memory, written by CTA 0 (one reader on PCIe; every other CTA reads L2)
+	unsigned long long word;
+	double s[MAXSC];
+};
+// thread 0 of every CTA; returns the verdict and, for LATE_GO, leaves the first NS coefficients in sc[] (shared memory)
+template<int NS>
+__device__ __forceinline__ unsigned late_wait(const late_host * host, late_dev * dev, unsigned seq, bool leader, int * error_flag,
+                                              double * sc) {
+	const long long t0 = clock64();
+	for (;;) {
+		unsigned long long w;
+		if (leader)
+			asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(&host->word) : "memory");
+		else
+			asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(&dev->word) : "memory");
+		bool gone = false;
+		if (leader && static_cast<unsigned>(w >> 2) != seq && clock64() - t0 > 20000000000LL) {
+			*reinterpret_cast<volatile int *>(error_flag) = 4; // ~10 s: the host is gone; fail loudly instead of hanging
+			w = (static_cast<unsigned long long>(seq) << 2) | LATE_ABORT;
+			gone = true;
+		}
+		if (static_cast<unsigned>(w >> 2) != seq)
+			continue;
+		const unsigned verdict = static_cast<unsigned>(w & 3);
+		__threadfence(); // the word first, then what it guards
+		if (verdict == LATE_GO) {
+			// the host stored them before the word (release).  All loads are issued before the first use: the leader's
+			// cross PCIe, one latency for the lot; it then passes them on
+			double v[NS > 0 ? NS : 1];
+#pragma unroll
+			for (int k = 0; k < NS; ++k) {
+				if (leader)
+					asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v[k]) : "l"(&host->s[k]));
+				else
+					asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v[k]) : "l"(&dev->s[k]));
+			}
+#pragma unroll
+			for (int k = 0; k < NS; ++k) {
+				sc[k] = v[k];
+				if (leader)
+					asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(&dev->s[k]), "d"(v[k]) : "memory");
+			}
+		}
+		if (leader) {
+			__threadfence(); // coefficients before the word
+			asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(&dev->word), "l"(w) : "memory");
+		}
+		(void)gone;
+		return verdict;
+	}
+}
+
 struct ew_args {
 	double * v[MAXV];
 	double s[MAXSC];
@@ -138,6 +200,11 @@ struct ew_args {
 	int partial_stride;
 	const xrank_info * xr; // nullptr on one rank
 	unsigned long long * tl; // timeline slot of this launch or nullptr
+	// armed launch: coefficients arrive through `late` (mapped host memory) once word == late_seq << 2 | LATE_GO
+	const late_host * late; // nullptr: coefficients are s[] above
+	late_dev * late_relay; // device copy of word and coefficients for the CTAs other than 0
+	int * late_error; // mapped host int, set when the host never answered
+	unsigned late_seq;
 	red_out r[MAXR];
 };
 
@@ -367,6 +434,20 @@ __device__ __forceinline__ void ew_program_body(const ew_args & a) {
 				sc[k] = a.snum[k] < 0 ? a.s[k] : __dmul_rn(a.s[k], __ddiv_rn(a.sdev[a.snum[k]], a.sdev[a.sden[k]]));
 			run(sc, acc);
 		}
+	}
+	else if (a.late) { // armed launch: wait for the host's verdict, then take the coefficients it left
+		__shared__ unsigned verdict;
+		__shared__ double late_sc[MAXSC];
+		if (threadIdx.x == 0)
+			verdict = late_wait<P.ns>(a.late, a.late_relay, a.late_seq, blockIdx.x == 0, a.late_error, late_sc);
+		__syncthreads();
+		if (verdict != LATE_GO)
+			return; // nothing has been touched
+		double sc[MAXSC];
+#pragma unroll
+		for (int k = 0; k < P.ns; ++k)
+			sc[k] = late_sc[k];
+		run(sc, acc);
 	}
 	else
 		run(a.s, acc);

@@ -18,6 +18,7 @@ namespace fsb {
 struct xrank_info;
 struct red_out;
 struct setup_exchange;
+struct speculation; // fuser.cu: armed launches (FSB_OPT_SPECULATE)
 constexpr int MAX_SCALARS = 64; // device scalars per context; slot 0 is the constant 1.0
 }
 
@@ -174,6 +175,8 @@ struct fsb_ctx_s {
 	uint64_t next_vec_id = 1;
 	uint64_t next_mat_id = 1;
 	std::vector<void *> deferred_free; // in-process rank groups: vector storage released with the context
+	bool speculate = false; // FSB_OPT_SPECULATE
+	fsb::speculation * spec = nullptr; // created on first use
 };
 
 struct fsb_vec_s {
@@ -298,7 +301,11 @@ void preload_kernel(Kernel kern) {
 
 // queue / fuser (fuser.cu)
 void enqueue(fsb_ctx_s * c, const pending & p);
-void flush(fsb_ctx_s * c);
+void flush(fsb_ctx_s * c, bool waiting = false); // waiting: called by a host that is about to wait for a reduction
+void speculate_after_flush(fsb_ctx_s * c); // wait_token: launch the expected next group ahead of the result (FSB_OPT_SPECULATE)
+void speculation_release(fsb_ctx_s * c); // tell an armed kernel to leave (any path that blocks on the device without a flush)
+void speculation_destroy(fsb_ctx_s * c);
+bool speculation_failed(const fsb_ctx_s * c); // an armed kernel waited ~10 s for the host and gave up
 int64_t new_token(fsb_ctx_s * c, int nccl_op);
 
 // kernels (declared here, defined in their .cu)

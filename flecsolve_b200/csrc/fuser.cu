@@ -451,9 +451,234 @@ static void publish_multi_rank(fsb_ctx_s * c, const pending * q, int len) {
 			finish_reduction_nccl(c, q[i]);
 }
 
-void flush(fsb_ctx_s * c) {
-	if (c->queue.empty())
+// ---------------------------------------------------------------- armed launches (FSB_OPT_SPECULATE)
+//
+// A Krylov loop written against the vector API alternates "wait for a reduction" and "launch the statements whose
+// coefficients come from it" (cg.hh:98-131: three such round trips per iteration).  Each costs the result's way to the
+// host, the host's arithmetic, a launch call (~3.7 us here) and the launch latency.  The loop is periodic, so the
+// queue remembers, per launched group, which group followed the wait after it; the next time the host waits at that
+// point, that group's kernel is launched AHEAD of the result with its coefficients left open (ew_kernels.cuh:
+// late_wait).  When the host then issues exactly that group -- same kernel, same vectors, the reduction tokens the
+// kernel was given -- the coefficients and a GO word in mapped memory replace the launch; anything else, and the kernel
+// is told to leave (it has touched nothing).  Plain reductions and immediate coefficients only; registered kernels only.
+constexpr int LATE_RING = 8;
+
+struct follower {
+	launcher_t launch = nullptr;
+	double * v[MAXV] = {};
+	int nv = 0, ns = 0, nr = 0, n_red = 0;
+	long long n = 0;
+	int red_slot[MAXR] = {}; // canonical slot of the j-th reduction statement, in statement order
+	int red_op[MAXR] = {};
+	bool confirmed = false; // seen twice in a row behind the same group: worth launching ahead
+	bool same_group(const follower & o) const {
+		if (launch != o.launch || nv != o.nv || n != o.n || n_red != o.n_red)
+			return false;
+		for (int k = 0; k < nv; ++k)
+			if (v[k] != o.v[k])
+				return false;
+		for (int j = 0; j < n_red; ++j)
+			if (red_slot[j] != o.red_slot[j] || red_op[j] != o.red_op[j])
+				return false;
+		return true;
+	}
+};
+
+struct speculation {
+	late_host * h_late = nullptr; // [LATE_RING], mapped pinned
+	late_host * h_late_dev = nullptr;
+	late_dev * d_relay = nullptr; // [LATE_RING]
+	int * h_error = nullptr; // mapped: an armed kernel gave up waiting
+	int * h_error_dev = nullptr;
+	unsigned seq = 0;
+	std::unordered_map<uint64_t, follower> followers;
+	uint64_t last_sig = 0; // the last group the current flush launched
+	bool last_valid = false;
+	uint64_t learn_sig = 0; // the group the host last waited behind
+	bool learning = false;
+	bool armed = false;
+	follower armed_f;
+	unsigned armed_seq = 0;
+	int64_t armed_tokens[MAXR] = {};
+};
+
+static uint64_t sig_mix(uint64_t h, uint64_t v) {
+	h ^= v + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
+	return h;
+}
+
+static speculation * spec_of(fsb_ctx_s * c) {
+	if (!c->spec) {
+		auto * sp = new speculation;
+		FSB_CUDA(cudaHostAlloc(&sp->h_late, sizeof(late_host) * LATE_RING, cudaHostAllocMapped));
+		std::memset(sp->h_late, 0, sizeof(late_host) * LATE_RING);
+		FSB_CUDA(cudaHostGetDevicePointer(&sp->h_late_dev, sp->h_late, 0));
+		FSB_CUDA(cudaMalloc(&sp->d_relay, sizeof(late_dev) * LATE_RING));
+		FSB_CUDA(cudaMemset(sp->d_relay, 0, sizeof(late_dev) * LATE_RING));
+		FSB_CUDA(cudaHostAlloc(&sp->h_error, sizeof(int), cudaHostAllocMapped));
+		*sp->h_error = 0;
+		FSB_CUDA(cudaHostGetDevicePointer(&sp->h_error_dev, sp->h_error, 0));
+		c->spec = sp;
+	}
+	return c->spec;
+}
+
+static void late_verdict(speculation * sp, unsigned verdict) {
+	late_host & h = sp->h_late[sp->armed_seq % LATE_RING];
+	__atomic_store_n(&h.word, (static_cast<unsigned long long>(sp->armed_seq) << 2) | verdict, __ATOMIC_RELEASE);
+	sp->armed = false;
+}
+
+void speculation_release(fsb_ctx_s * c) {
+	speculation * sp = c->spec;
+	if (!sp)
 		return;
+	sp->learning = false;
+	if (sp->armed) {
+		late_verdict(sp, LATE_ABORT);
+		c->stats[FSB_STAT_ARMED_MISSES]++;
+	}
+}
+
+bool speculation_failed(const fsb_ctx_s * c) { return c->spec && *reinterpret_cast<volatile int *>(c->spec->h_error) != 0; }
+
+void speculation_destroy(fsb_ctx_s * c) {
+	speculation * sp = c->spec;
+	if (!sp)
+		return;
+	cudaFreeHost(sp->h_late);
+	cudaFreeHost(sp->h_error);
+	cudaFree(sp->d_relay);
+	delete sp;
+	c->spec = nullptr;
+}
+
+// the group just bound as the template of a launch ahead of time, or false if it does not qualify
+static bool follower_of(const fsb_ctx_s * c, const bound_group & g, const pending * q, int len, follower & f) {
+	if (!g.launch || g.dev || g.box || c->halt_armed)
+		return false;
+	f = follower{};
+	f.launch = g.launch;
+	f.nv = g.prog.nv;
+	f.ns = g.prog.ns;
+	f.nr = g.prog.nr;
+	f.n = g.args.n;
+	for (int k = 0; k < f.nv; ++k)
+		f.v[k] = g.args.v[k];
+	for (int i = 0; i < len; ++i) {
+		if (q[i].kind != pending::RED)
+			continue;
+		if (q[i].store >= 0 || q[i].halt_mode != 0 || q[i].n_post != 0 || f.n_red >= MAXR)
+			return false; // reductions that feed device scalars or the halt flag belong to the device-scalar solvers
+		f.red_slot[f.n_red] = g.prog.st[i].z;
+		f.red_op[f.n_red] = q[i].op;
+		++f.n_red;
+	}
+	return true;
+}
+
+static uint64_t sig_of_group(const bound_group & g) {
+	uint64_t h = sig_mix(0x45, reinterpret_cast<uint64_t>(g.launch));
+	for (int k = 0; k < g.prog.nv; ++k)
+		h = sig_mix(h, reinterpret_cast<uint64_t>(g.args.v[k]));
+	return sig_mix(h, static_cast<uint64_t>(g.args.n));
+}
+static uint64_t sig_of_spmv(const pending & sp, const pending * dot) {
+	uint64_t h = sig_mix(0x53, reinterpret_cast<uint64_t>(sp.A));
+	h = sig_mix(h, reinterpret_cast<uint64_t>(sp.x->d));
+	h = sig_mix(h, reinterpret_cast<uint64_t>(sp.y->d));
+	return dot ? sig_mix(h, reinterpret_cast<uint64_t>((dot->x == sp.y ? dot->y : dot->x)->d)) : h;
+}
+
+// does the group the host issued equal the one that is armed?  (then only its coefficients travel)
+static bool matches_armed(const speculation * sp, const bound_group & g, const pending * q, int len) {
+	const follower & f = sp->armed_f;
+	if (g.launch != f.launch || g.dev || g.box || g.args.n != f.n || g.prog.nv != f.nv || g.prog.nr != f.nr)
+		return false;
+	for (int k = 0; k < f.nv; ++k)
+		if (g.args.v[k] != f.v[k])
+			return false;
+	int j = 0;
+	for (int i = 0; i < len; ++i) {
+		if (q[i].kind != pending::RED)
+			continue;
+		if (j >= f.n_red || q[i].store >= 0 || q[i].halt_mode != 0 || q[i].n_post != 0 || q[i].token != sp->armed_tokens[j] ||
+		    g.prog.st[i].z != f.red_slot[j])
+			return false;
+		++j;
+	}
+	return j == f.n_red;
+}
+
+// wait_token, right after its flush: the host is about to wait behind the group that flush launched last.  Remember to
+// learn what it issues next, and if that is known from the last time round, launch it now with open coefficients.
+void speculate_after_flush(fsb_ctx_s * c) {
+	if (c->trace || c->d_timeline || c->halt_armed || (c->boot && c->boot->in_process()) || (c->nranks > 1 && !c->d_xrank))
+		return;
+	speculation * sp = spec_of(c);
+	if (!sp->last_valid || sp->armed)
+		return;
+	sp->last_valid = false;
+	sp->learn_sig = sp->last_sig;
+	sp->learning = true;
+	const auto it = sp->followers.find(sp->last_sig);
+	if (it == sp->followers.end() || !it->second.confirmed)
+		return;
+	const follower & f = it->second;
+	ew_args a{};
+	for (int k = 0; k < f.nv; ++k)
+		a.v[k] = f.v[k];
+	a.n = f.n;
+	a.partials = c->d_partials;
+	a.counter = c->d_counter;
+	a.partial_stride = MAX_RED_BLOCKS;
+	a.xr = c->d_xrank;
+	a.sdev = c->d_scalars;
+	for (int k = 0; k < MAXSC; ++k)
+		a.snum[k] = a.sden[k] = -1;
+	for (int j = 0; j < f.n_red; ++j) { // the tokens the host's next reductions will get
+		pending red{};
+		red.kind = pending::RED;
+		red.op = f.red_op[j];
+		red.token = c->next_token + j;
+		sp->armed_tokens[j] = red.token;
+		fill_red_out(c, red, a.r[f.red_slot[j]]);
+	}
+	sp->armed_seq = ++sp->seq;
+	const int slot = static_cast<int>(sp->armed_seq % LATE_RING);
+	a.late = sp->h_late_dev + slot;
+	a.late_relay = sp->d_relay + slot;
+	a.late_error = sp->h_error_dev;
+	a.late_seq = sp->armed_seq;
+	const long long want = ((f.n + 1) / 2 + EW_BLOCK - 1) / EW_BLOCK;
+	const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, MAX_RED_BLOCKS)));
+	f.launch(a, grid, c->stream);
+	FSB_CUDA(cudaGetLastError());
+	c->stats[FSB_STAT_KERNEL_LAUNCHES]++;
+	sp->armed_f = f;
+	sp->armed = true;
+}
+
+// internal breakdown of the flush time (stats 9..12, ns): binding a group, the element-wise launch call, the SpMV launch call
+// (preparation + cudaLaunchKernelEx), group formation
+struct lap {
+	int64_t & acc;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	explicit lap(int64_t & a) : acc(a) {}
+	~lap() { acc += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+void flush(fsb_ctx_s * c, bool waiting) {
+	if (c->queue.empty()) {
+		if (!waiting) // whoever flushes without statements is about to touch the stream or the device; a host that merely
+			speculation_release(c); // reads another result of the kernel it already waited for is not
+		if (c->spec)
+			c->spec->last_valid = false;
+		return;
+	}
+	speculation * const sp = c->spec;
+	if (sp)
+		sp->last_valid = false;
 	struct stopwatch {
 		fsb_ctx_s * c;
 		std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -494,9 +719,21 @@ void flush(fsb_ctx_s * c) {
 					break;
 				}
 			}
+			if (sp && i == 0) { // the host went on with a product: nothing that could be armed
+				if (sp->learning)
+					sp->followers.erase(sp->learn_sig);
+				speculation_release(c);
+			}
+			if (sp) {
+				sp->last_sig = sig_of_spmv(q[i], dot);
+				sp->last_valid = true;
+			}
 			if (c->trace)
 				fprintf(stderr, "[fsb %d] launch: spmv%s%s\n", c->rank, dot ? " + dot #" : "", dot ? std::to_string(dot->token).c_str() : "");
-			spmv_group(c, q[i], dot);
+			{
+				lap t(c->stats[11]);
+				spmv_group(c, q[i], dot);
+			}
 			if (dot) {
 				publish_multi_rank(c, dot, 1);
 				c->stats[FSB_STAT_FUSED_STATEMENTS] += 2;
@@ -550,16 +787,52 @@ void flush(fsb_ctx_s * c) {
 		// program kernel; a run that exceeds the slot limits is cut at the longest prefix that fits
 		bound_group g;
 		int len = j - i;
-		for (; len >= 1; --len)
-			if (bind_group(c, &q[i], len, g, true))
-				break;
+		{
+			lap t(c->stats[9]);
+			for (; len >= 1; --len)
+				if (bind_group(c, &q[i], len, g, true))
+					break;
+		}
 		if (len < 1)
 			throw error(FSB_ERR_STATE, "no kernel for statement: " + describe(&q[i], 1));
+		bool ran_armed = false;
+		if (sp && i == 0) { // first group after a wait: is it the one that was launched ahead?  what follows that wait?
+			if (sp->learning) {
+				follower f;
+				if (follower_of(c, g, &q[i], len, f)) {
+					const auto known = sp->followers.find(sp->learn_sig);
+					f.confirmed = known != sp->followers.end() && known->second.same_group(f);
+					sp->followers[sp->learn_sig] = f;
+				}
+				else
+					sp->followers.erase(sp->learn_sig);
+				sp->learning = false;
+			}
+			if (sp->armed) {
+				if (matches_armed(sp, g, &q[i], len)) {
+					late_host & h = sp->h_late[sp->armed_seq % LATE_RING];
+					for (int k = 0; k < g.prog.ns; ++k)
+						h.s[k] = g.args.s[k];
+					late_verdict(sp, LATE_GO); // release store: the coefficients are visible before the word
+					c->stats[FSB_STAT_ARMED_HITS]++;
+					ran_armed = true;
+				}
+				else
+					speculation_release(c);
+			}
+		}
+		if (sp) {
+			sp->last_sig = sig_of_group(g);
+			sp->last_valid = g.launch != nullptr;
+		}
 		if (!g.launch)
 			c->stats[FSB_STAT_UNMATCHED_GROUPS]++;
 		if (c->trace)
 			fprintf(stderr, "[fsb %d] launch%s: %s\n", c->rank, g.launch ? "" : " (generic)", describe(&q[i], len).c_str());
-		if (n > 0 || (g.nr > 0 && c->nranks > 1)) {
+		if (ran_armed) {
+			// the kernel is already resident: it picked the coefficients up and is running
+		}
+		else if (n > 0 || (g.nr > 0 && c->nranks > 1)) {
 			long long packets = layout_of(q[i])->box ? n : (n + 1) / 2; // box layout: one element per thread and trip
 			long long want = (packets + EW_BLOCK - 1) / EW_BLOCK;
 			const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, MAX_RED_BLOCKS)));
@@ -574,6 +847,7 @@ void flush(fsb_ctx_s * c) {
 					launch_interp(g, -1, c->stream);
 				c->boot->rendezvous();
 			}
+			lap t(c->stats[10]);
 			if (g.launch)
 				g.launch(g.args, grid, c->stream);
 			else if (jk) {

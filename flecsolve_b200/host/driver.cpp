@@ -263,6 +263,22 @@ int fsbh_solve(void * sv, const fsbh_options * o, const double * b_host, double 
 		const auto t_solve = clk::now();
 		recorder rec{S.ctx.handle(), history, history_cap, o->ev_start, o->ev_stop};
 		solve_info si;
+		// inside the solver call nothing but this library talks to the device: let it launch the statement groups of the
+		// Krylov loop ahead of the reductions their coefficients come from (FSB_OPT_SPECULATE; FSB_SPECULATE=0: off)
+		struct speculation_scope {
+			fsb_ctx_t ctx;
+			bool on;
+			explicit speculation_scope(fsb_ctx_t c) : ctx(c) {
+				const char * e = std::getenv("FSB_SPECULATE");
+				on = !(e && std::atoi(e) == 0);
+				if (on)
+					fsb_ctx_set_option(ctx, FSB_OPT_SPECULATE, 1);
+			}
+			~speculation_scope() {
+				if (on)
+					fsb_ctx_set_option(ctx, FSB_OPT_SPECULATE, 0);
+			}
+		} speculating(S.ctx.handle());
 		if (o->precond == 1) {
 			if (!S.dinv)
 				S.dinv = std::make_unique<op::core<op::diagonal_inverse<double, std::size_t>>>(S.A);

@@ -65,6 +65,15 @@ enum fsb_option {
 	,
 	FSB_OPT_TIMELINE = 7 /* n > 0: keep a device-side timeline of the next n kernel launches (fsb_ctx_timeline_read); 0: off */
 	,
+	FSB_OPT_SPECULATE = 9 /* 1: while the host waits for a reduction, the statement group that followed this point of the
+	                         program last time is launched AHEAD of the result, with its coefficients left open; when the
+	                         host then issues exactly that group, only the coefficients are handed over (a word in mapped
+	                         memory) instead of a launch, otherwise the armed kernel is told to leave.  Takes the launch out
+	                         of every host round trip of a Krylov iteration.  Default 0: an armed kernel occupies the
+	                         device until the next call into this library, so the caller must not block on the device
+	                         by other means in between -- the solver drivers switch it on for the duration of a solve.
+	                         Setting it to 0 releases whatever is armed. */
+	,
 	FSB_OPT_SPMV_DICTIONARY = 8 /* 1 (default): y = A x of a matrix with at most 256 distinct values streams a one-byte value
 	                               index per nonzero instead of the fp64 value (FSB_INFO_VALUE_DICTIONARY; same doubles, same
 	                               order, same bits); 0 (or FSB_SPMV_DICT=0 in the environment): always stream the values */
@@ -79,7 +88,9 @@ enum fsb_stat {
 	FSB_STAT_UNMATCHED_GROUPS = 5, /* groups launched through the generic program kernel (no compile-time instantiation) */
 	FSB_STAT_WAIT_NS = 6, /* host time spent waiting for reduction results (fsb_red_get / fsb_red_wait) */
 	FSB_STAT_FLUSH_NS = 7, /* host time spent turning queued statements into launches */
-	FSB_STAT_JIT_GROUPS = 8 /* groups launched through a run-time compiled kernel */
+	FSB_STAT_JIT_GROUPS = 8, /* groups launched through a run-time compiled kernel */
+	FSB_STAT_ARMED_HITS = 13, /* FSB_OPT_SPECULATE: groups that ran in a kernel launched ahead of the host's coefficients */
+	FSB_STAT_ARMED_MISSES = 14 /* ... kernels launched ahead that had to be told to leave */
 };
 
 const char * fsb_last_error(void);

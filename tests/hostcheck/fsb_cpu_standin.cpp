@@ -148,6 +148,7 @@ int fsb_ctx_destroy(fsb_ctx_t c) {
 	delete c;
 	return FSB_OK;
 }
+int fsb_ctx_set_option(fsb_ctx_t, int, int64_t) { return FSB_OK; } // tuning knobs of the device library: nothing to do here
 int fsb_ctx_flush(fsb_ctx_t) {
 	trace_mark("FLUSH");
 	return FSB_OK;
