@@ -269,8 +269,10 @@ int fsbh_solve(void * sv, const fsbh_options * o, const double * b_host, double 
 			fsb_ctx_t ctx;
 			bool on;
 			explicit speculation_scope(fsb_ctx_t c) : ctx(c) {
+				// measured (profiles/r2_speculation.txt): -15 % ... -1 % per iteration on one GPU (64^3 ... 256^3), -5 % on two
+				// at 1-2 M rows per rank, but +5 % on eight (256^3: 102.5 against 97.3 us) -- on by default on one rank only
 				const char * e = std::getenv("FSB_SPECULATE");
-				on = !(e && std::atoi(e) == 0);
+				on = e ? std::atoi(e) != 0 : fsb_ctx_nranks(ctx) == 1;
 				if (on)
 					fsb_ctx_set_option(ctx, FSB_OPT_SPECULATE, 1);
 			}
