@@ -186,7 +186,8 @@ def device_count() -> int:
 
 
 STAT = {"launches": 0, "fused_statements": 1, "halo_exchanges": 2, "allreduces": 3, "host_syncs": 4,
-        "unmatched_groups": 5, "wait_ns": 6, "flush_ns": 7, "jit_groups": 8, "armed_hits": 13, "armed_misses": 14}
+        "unmatched_groups": 5, "wait_ns": 6, "flush_ns": 7, "jit_groups": 8, "bind_ns": 9, "ew_launch_ns": 10, "spmv_launch_ns": 11,
+        "armed_hits": 13, "armed_misses": 14}
 OPT = {"fusion": 0, "spmv_rows_per_cta": 1, "spmv_threads": 2, "trace": 3, "profile": 4, "reproducible": 5, "jit": 6,
        "timeline": 7, "spmv_dictionary": 8, "speculate": 9}
 

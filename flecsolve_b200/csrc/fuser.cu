@@ -659,8 +659,7 @@ void speculate_after_flush(fsb_ctx_s * c) {
 	sp->armed = true;
 }
 
-// internal breakdown of the flush time (stats 9..12, ns): binding a group, the element-wise launch call, the SpMV launch call
-// (preparation + cudaLaunchKernelEx), group formation
+// breakdown of the flush time (FSB_STAT_BIND_NS, FSB_STAT_EW_LAUNCH_NS, FSB_STAT_SPMV_LAUNCH_NS)
 struct lap {
 	int64_t & acc;
 	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -731,7 +730,7 @@ void flush(fsb_ctx_s * c, bool waiting) {
 			if (c->trace)
 				fprintf(stderr, "[fsb %d] launch: spmv%s%s\n", c->rank, dot ? " + dot #" : "", dot ? std::to_string(dot->token).c_str() : "");
 			{
-				lap t(c->stats[11]);
+				lap t(c->stats[FSB_STAT_SPMV_LAUNCH_NS]);
 				spmv_group(c, q[i], dot);
 			}
 			if (dot) {
@@ -788,7 +787,7 @@ void flush(fsb_ctx_s * c, bool waiting) {
 		bound_group g;
 		int len = j - i;
 		{
-			lap t(c->stats[9]);
+			lap t(c->stats[FSB_STAT_BIND_NS]);
 			for (; len >= 1; --len)
 				if (bind_group(c, &q[i], len, g, true))
 					break;
@@ -847,7 +846,7 @@ void flush(fsb_ctx_s * c, bool waiting) {
 					launch_interp(g, -1, c->stream);
 				c->boot->rendezvous();
 			}
-			lap t(c->stats[10]);
+			lap t(c->stats[FSB_STAT_EW_LAUNCH_NS]);
 			if (g.launch)
 				g.launch(g.args, grid, c->stream);
 			else if (jk) {

@@ -89,6 +89,9 @@ enum fsb_stat {
 	FSB_STAT_WAIT_NS = 6, /* host time spent waiting for reduction results (fsb_red_get / fsb_red_wait) */
 	FSB_STAT_FLUSH_NS = 7, /* host time spent turning queued statements into launches */
 	FSB_STAT_JIT_GROUPS = 8, /* groups launched through a run-time compiled kernel */
+	FSB_STAT_BIND_NS = 9, /* parts of FSB_STAT_FLUSH_NS: matching statement groups with kernels, */
+	FSB_STAT_EW_LAUNCH_NS = 10, /* ... the launch calls of element-wise kernels, */
+	FSB_STAT_SPMV_LAUNCH_NS = 11, /* ... preparing and launching SpMV kernels */
 	FSB_STAT_ARMED_HITS = 13, /* FSB_OPT_SPECULATE: groups that ran in a kernel launched ahead of the host's coefficients */
 	FSB_STAT_ARMED_MISSES = 14 /* ... kernels launched ahead that had to be told to leave */
 };
