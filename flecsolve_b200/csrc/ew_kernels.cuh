@@ -145,11 +145,9 @@ __device__ __forceinline__ unsigned late_wait(const late_host * host, late_dev *
 			asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(&host->word) : "memory");
 		else
 			asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(&dev->word) : "memory");
-		bool gone = false;
 		if (leader && static_cast<unsigned>(w >> 2) != seq && clock64() - t0 > 20000000000LL) {
 			*reinterpret_cast<volatile int *>(error_flag) = 4; // ~10 s: the host is gone; fail loudly instead of hanging
 			w = (static_cast<unsigned long long>(seq) << 2) | LATE_ABORT;
-			gone = true;
 		}
 		if (static_cast<unsigned>(w >> 2) != seq)
 			continue;
@@ -177,7 +175,6 @@ __device__ __forceinline__ unsigned late_wait(const late_host * host, late_dev *
 			__threadfence(); // coefficients before the word
 			asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(&dev->word), "l"(w) : "memory");
 		}
-		(void)gone;
 		return verdict;
 	}
 }
