@@ -516,6 +516,7 @@ int fsb_ctx_profile_read(fsb_ctx_t c, double * spmv_ms, int64_t * spmv_launches)
 int fsb_vec_create(fsb_ctx_t c, int64_t n_owned, int64_t n_ghost, fsb_vec_t * out) {
 	return guarded([&] {
 		FSB_REQUIRE(c && out && n_owned >= 0 && n_ghost >= 0, "bad arguments");
+		fsb::speculation_release(c); // cudaMalloc waits for the device: nothing may sit there waiting for the host
 		auto * v = new fsb_vec_s;
 		v->ctx = c;
 		v->n_owned = n_owned;
@@ -649,6 +650,7 @@ int fsb_vec_create_box(fsb_ctx_t c, int dim, const int64_t * extents, const int6
 			b.n[k] = hi[k] - lo[k];
 		}
 		FSB_REQUIRE(b.storage() < (1LL << 31), "box: padded array exceeds int32 offsets");
+		fsb::speculation_release(c);
 		auto * v = new fsb_vec_s;
 		v->ctx = c;
 		v->box = true;

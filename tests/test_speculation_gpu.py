@@ -49,6 +49,15 @@ def test_hit_miss_and_release_at_the_c_abi(ctx):
     mk = lambda a: F.Vector(ctx, n, 0).upload(a)
     x, p, r, w = mk(xh), mk(ph), mk(rh), mk(wh)
     ctx.set_option("speculate", 1)
+    try:
+        _hit_miss_and_release(ctx, n, xh, ph, rh, wh, x, p, r, w)
+    finally:
+        ctx.set_option("speculate", 0)  # the shared context must not keep launching ahead behind a failed assertion
+    for v in (x, p, r, w):
+        v.destroy()
+
+
+def _hit_miss_and_release(ctx, n, xh, ph, rh, wh, x, p, r, w):
     ctx.reset_stats()
     ref_x, ref_r = xh.copy(), rh.copy()
     rho = ctx.get(r.dot_token(r))
@@ -80,5 +89,3 @@ def test_hit_miss_and_release_at_the_c_abi(ctx):
     ctx.set_option("speculate", 0)  # ... and this lets it go
     ctx.sync()
     assert np.array_equal(w.download(), 2.0 * wh)
-    for v in (x, p, r, w):
-        v.destroy()
