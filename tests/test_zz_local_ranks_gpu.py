@@ -112,9 +112,9 @@ def test_split_spmv_reductions_and_jacobi(nranks):
     run_ranks(nranks, body)
 
 
-@pytest.mark.parametrize("kind,dims", [(7, (12, 11, 13)), (27, (9, 8, 11)), (107, (7, 9, 8))])
-def test_device_generator_and_solvers(kind, dims):
-    P = 2
+@pytest.mark.parametrize("kind,dims,P", [(7, (12, 11, 13), 2), (27, (9, 8, 11), 2), (107, (7, 9, 8), 2),
+                                         (7, (7, 5, 11), 3), (27, (5, 7, 10), 3)])  # 385 and 350 rows on 3 ranks: uneven blocks
+def test_device_generator_and_solvers(kind, dims, P):
     rp, col, val = O.stencil_csr(kind, *dims, 1e-3 if kind == 107 else 0.0, 1.0)
     n = len(rp) - 1
     M = O.ParCSR(rp, col, val, colours=P)
