@@ -518,6 +518,42 @@ int fsb_parcsr_create_box_stencil(fsb_ctx_t c, int dim, const int64_t * ext, con
 	*out = A;
 	return FSB_OK;
 }
+// same entries as the device library documents (include/fsb.h): towards c +- e  -(beta (b kface)), centre  beta sum (b kface) +
+// (alpha vol) a
+int fsb_parcsr_create_box_fvm(fsb_ctx_t c, int dim, const int64_t * ext, const int64_t * lo, const int64_t * hi, double beta,
+                              double alpha, double vol, const double * kface, const double * a, const double * const * bface,
+                              fsb_parcsr_t * out) {
+	fsb_vec_t shape = nullptr;
+	fsb_vec_create_box(c, dim, ext, lo, hi, &shape);
+	auto * A = new fsb_parcsr_s;
+	A->ctx = c;
+	A->box = true;
+	A->n = shape->n;
+	A->row_store = shape->map;
+	const int64_t stride[3] = {1, shape->ext[0], shape->ext[0] * shape->ext[1]};
+	auto face = [&](int64_t at, int ax) { return bface[ax][at] * kface[ax]; };
+	A->rowptr.push_back(0);
+	for (int64_t r = 0; r < A->n; ++r) {
+		const int64_t at = shape->map[r];
+		for (int ax = dim - 1; ax >= 0; --ax) {
+			A->col.push_back(at - stride[ax]);
+			A->val.push_back(-(beta * face(at - stride[ax], ax)));
+		}
+		double sum = 0.0;
+		for (int ax = 0; ax < dim; ++ax)
+			sum += face(at, ax) + face(at - stride[ax], ax);
+		A->col.push_back(at);
+		A->val.push_back(beta * sum + (alpha * vol) * a[at]);
+		for (int ax = 0; ax < dim; ++ax) {
+			A->col.push_back(at + stride[ax]);
+			A->val.push_back(-(beta * face(at, ax)));
+		}
+		A->rowptr.push_back(static_cast<int64_t>(A->col.size()));
+	}
+	delete shape;
+	*out = A;
+	return FSB_OK;
+}
 int fsb_parcsr_destroy(fsb_parcsr_t A) {
 	delete A;
 	return FSB_OK;

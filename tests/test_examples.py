@@ -23,6 +23,27 @@ def test_examples_build():
     assert all(os.path.exists(os.path.join(OUT, name)) for name in ("poisson", "implicit", "diffusion"))
 
 
+def test_equilibrium_diffusion_on_the_sequential_stand_in(tmp_path):
+    """examples/equilibrium_diffusion linked against the CPU stand-in for the C ABI (tests/hostcheck): the program's own
+    logic -- two finite-volume blocks on a vec::multi, boundary conditions through the face coefficients, CG from
+    diffusion.cfg -- drains v1 and keeps v2's constant, with no GPU involved"""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = str(tmp_path / "diffusion_cpu")
+    r = subprocess.run([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-Wno-unused-local-typedefs", "-Wno-unused-variable",
+                        "-I", os.path.join(ROOT, "flecsolve_b200", "include"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "equilibrium_diffusion", "diffusion.cc"),
+                        os.path.join(ROOT, "tests", "hostcheck", "fsb_cpu_standin.cpp"), "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    r = subprocess.run([exe, "24", os.path.join(ROOT, "examples", "equilibrium_diffusion", "diffusion.cfg")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"converged after (\d+) iterations.*v1 in \[([0-9.e+-]+), ([0-9.e+-]+)\], v2 in \[([0-9.]+), ([0-9.]+)\]", r.stdout)
+    assert m, r.stdout
+    assert 10 < int(m.group(1)) <= 500 and abs(float(m.group(2))) < 1e-3 and abs(float(m.group(3))) < 1e-3, r.stdout
+    assert abs(float(m.group(4)) - 2.0) < 1e-9 and abs(float(m.group(5)) - 2.0) < 1e-9, r.stdout
+
+
 @pytest.mark.gpu
 def test_examples_run():
     if F.device_count() == 0:
