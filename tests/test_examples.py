@@ -44,6 +44,30 @@ def test_equilibrium_diffusion_on_the_sequential_stand_in(tmp_path):
     assert abs(float(m.group(4)) - 2.0) < 1e-9 and abs(float(m.group(5)) - 2.0) < 1e-9, r.stdout
 
 
+@pytest.mark.parametrize("src,args,pattern", [
+    ("poisson/poisson.cc", ["32", "poisson/poisson.cfg"], r"converged after (\d+) iterations.*max error.*= ([0-9.e+-]+)"),
+    ("heat_equation/implicit.cc", ["10", "heat_equation/implicit.cfg"],
+     r"(\d+) steps \((\d+) attempts, (\d+) rejected\), max u = ([0-9.]+), heat ([0-9.]+) -> ([0-9.]+)"),
+])
+def test_other_examples_on_the_sequential_stand_in(tmp_path, src, args, pattern):
+    """examples/poisson and examples/heat_equation against the CPU stand-in: their own logic, no GPU"""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = str(tmp_path / "example_cpu")
+    r = subprocess.run([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-Wno-unused-local-typedefs", "-Wno-unused-variable",
+                        "-I", os.path.join(ROOT, "flecsolve_b200", "include"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", src), os.path.join(ROOT, "tests", "hostcheck", "fsb_cpu_standin.cpp"),
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    r = subprocess.run([exe, args[0], os.path.join(ROOT, "examples", args[1])], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(pattern, r.stdout)
+    assert m, r.stdout
+    if "poisson" in src:
+        assert 20 < int(m.group(1)) < 400 and float(m.group(2)) < 5e-3, r.stdout
+    else:
+        assert int(m.group(1)) >= 5 and 0.0 < float(m.group(4)) <= 50.0 and float(m.group(6)) <= float(m.group(5)) * (1 + 1e-9), r.stdout
+
+
 @pytest.mark.gpu
 def test_examples_run():
     if F.device_count() == 0:
