@@ -382,6 +382,9 @@ def run_ours(args):
                                       "of the reference on the same full-size system",
                               "iters_compared": int(m), "max_rel_diff": float(rel.max()), "tolerance": 1e-8,
                               "ok": bool(rel.max() <= 1e-8)}
+        serial = reference_serial(args.workload)
+        if serial:  # the reference's own serial code beside the port's one-thread figure: is the port representative?
+            base["reference_serial"] = serial
         line["cpu_baseline"] = base
     ctx.close()
     if world.is_root:
@@ -462,6 +465,39 @@ def cpu_baseline(workload: str, sample_iters: int, warm: int = 2) -> dict:
     return out
 
 
+def reference_serial(workload: str, iters: int = 8) -> dict | None:
+    """The reference's OWN serial code on one core: oracle/_ref/refcheck = flecsolve/solvers/cg.hh + matrices/seq.hh +
+    vectors/seq.hh compiled from the reference tree against stub FleCSI headers (oracle/refcheck/build.py), run on the same
+    system.  The binary reports no timings, so two runs (2 and 2 + iters iterations) are timed and subtracted."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "refcheck")
+    if not os.path.exists(exe):
+        return None
+    kind, nx, ny, nz, precond = WORKLOADS[workload]
+    if nx * ny * nz > 2 ** 25:  # the serial assembly of the larger systems takes minutes
+        return None
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "x.bin")
+            times = []
+            for maxiter in (2, 2 + iters):
+                t0 = time.perf_counter()
+                r = subprocess.run([exe, str(kind), str(nx), str(ny), str(nz), "cg", "1" if precond else "0", "0", str(maxiter),
+                                    "1", "0", "0", "1", "2", out], capture_output=True, text=True, timeout=600)
+                times.append(time.perf_counter() - t0)
+                if r.returncode != 0:
+                    return None
+        dt = times[1] - times[0]
+        if dt <= 0:
+            return None
+        return {"value": iters / dt, "unit": "iterations/s", "cores": 1, "kind": "reference",
+                "sample": f"the reference's own cg.hh + seq.hh (oracle/_ref/refcheck), {iters} iterations of the same system: "
+                          f"{times[1]:.1f} s for {2 + iters} iterations minus {times[0]:.1f} s for 2 (set-up included in both)"}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path is not buildable here
     (needs FleCSI/MPI/Boost), so this times its line-faithful restatement under oracle/ on ALL host cores."""
@@ -487,6 +523,9 @@ def run_reference(args):
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    serial = reference_serial(args.workload)
+    if serial:
+        line["reference_serial"] = serial
     print(json.dumps(line), flush=True)
 
 
